@@ -1,0 +1,203 @@
+/*
+ * recom_b200.h - C ABI of the B200 batched ReCom engine.
+ *
+ * GerryChain has no FFI: its plug points are Python callables.  This
+ * header is what a ctypes stub on the reference side binds (INTEGRATION.md shows the
+ * stub).  Every entry point cites the reference interface it replaces, relative to
+ * /root/reference/gerrychain/.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++ or torch types; no exceptions cross the ABI
+ *  - every function returns an int status (RC_OK == 0); rc_last_error() is thread local
+ *  - pointers named d_* are DEVICE pointers owned by the caller (torch tensors'
+ *    data_ptr() on the Python side); pointers named h_* are HOST pointers;
+ *    the library owns only what rc_engine_create allocates (graph copy + scratch)
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *    kernels are asynchronous on it unless the function says it synchronises
+ *  - one host thread per engine
+ *
+ * The same structs are used by the CPU oracle (oracle/recom_oracle.h) so that a replay
+ * record or a configuration means the same thing on both sides.
+ */
+#ifndef RECOM_B200_H
+#define RECOM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RC_ABI_VERSION 1
+
+/* ---- status codes (per call and per chain) -------------------------------------- */
+enum {
+  RC_OK = 0,
+  RC_ERR_INVALID_ARG = 1,   /* bad pointer / size / unsupported configuration         */
+  RC_ERR_CUDA = 2,          /* a CUDA runtime call failed; see rc_last_error()        */
+  RC_ERR_CAPACITY = 3,      /* merged pair larger than the engine's node/edge caps    */
+  RC_ERR_MAX_ATTEMPTS = 4,  /* tree.py:718  RuntimeError("Could not find a possible cut after N attempts.") */
+  RC_ERR_ALL_PAIRS_BAD = 5, /* proposals/tree_proposals.py:140-144  MetagraphError    */
+  RC_ERR_DISCONNECTED = 6,  /* merged subgraph not connected (invalid input plan)     */
+  RC_ERR_NO_CUT_EDGES = 7,  /* tree_proposals.py:106 random.choice(()) -> IndexError  */
+  RC_ERR_REPLAY = 8,        /* replay record inconsistent with the state              */
+  RC_ERR_NO_ROOT = 9,       /* tree.py:377 choice([]) : no tree node of degree > 1    */
+  RC_ERR_INVALID_STREAK = 10 /* proposals kept failing the population Bounds           */
+};
+
+/* per-chain flag bits (RcState.d_flags), sticky */
+enum {
+  RC_FLAG_WARNED = 1 /* tree.py:703-710 BipartitionWarning threshold was reached     */
+};
+
+enum { RC_TREE_MST = 0,   /* tree.py:60-94  random_spanning_tree (+ networkx Kruskal) */
+       RC_TREE_WILSON = 1 /* tree.py:97-132 uniform_spanning_tree                     */ };
+
+enum { RC_CUT_UNIFORM = 0,      /* tree.py:540-545 random.choice(cuts)                 */
+       RC_CUT_REGION_PREF = 1,  /* tree.py:548-578 power-set preference, then max weight */
+       RC_CUT_MAX_WEIGHT = 2    /* tree.py:446-480 _max_weight_choice                  */ };
+
+/* ---- graph: replaces Graph / FrozenGraph (graph/graph.py:51, :508) as input -------- */
+typedef struct RcGraph {
+  int32_t n_nodes;            /* N: node index = position in graph.nodes order         */
+  int32_t n_edges;            /* E: undirected; edge id = rank of (min,max) pair       */
+  const int32_t* row_ptr;     /* [N+1]                                                 */
+  const int32_t* col_idx;     /* [2E] neighbours, each row ascending                   */
+  const int32_t* slot_edge;   /* [2E] undirected edge id of each directed slot         */
+  const int32_t* edge_uv;     /* [E][2] u < v                                          */
+  const int32_t* pop;         /* [N] graph.nodes[n][pop_col], integers                 */
+  int32_t n_region_cols;      /* R = len(region_surcharge) (tree.py:80)                */
+  const int32_t* region_ids;  /* [R][N] dense code per region label; -1 == None        */
+  const double* surcharges;   /* [R] region_surcharge.values() in dict order           */
+} RcGraph;
+
+/* ---- configuration: the kwargs of recom / bipartition_tree / the Bounds constraint - */
+typedef struct RcConfig {
+  int32_t n_districts;        /* k = len(partition)                                    */
+  int32_t n_chains;           /* independent chains resident on this device            */
+  double pop_target;          /* recom(pop_target=)   tree_proposals.py:39             */
+  double epsilon;             /* recom(epsilon=)      tree_proposals.py:40             */
+  int32_t node_repeats;       /* recom(node_repeats=) tree.py:586, :680-682            */
+  int32_t max_attempts;       /* bipartition_tree(max_attempts=) tree.py:593; <=0: None */
+  int32_t warn_attempts;      /* tree.py:594                                           */
+  int32_t allow_pair_reselection; /* tree.py:595, tree_proposals.py:133-138            */
+  int32_t tree_kind;          /* RC_TREE_*                                             */
+  int32_t cut_policy;         /* RC_CUT_*                                              */
+  double pop_lower;           /* Bounds lower: constraints/validity.py:88-91, bounds.py:25-28 */
+  double pop_upper;           /* Bounds upper; lower > upper disables the check        */
+  uint64_t seed;              /* Philox key; chain c uses subsequence c + chain_offset */
+  int32_t chain_offset;       /* global id of local chain 0 (multi-GPU sharding)       */
+  int32_t cap_nodes;          /* max nodes of a merged pair (0: engine picks)          */
+  int32_t cap_edges;          /* max undirected edges of a merged pair (0: picks)      */
+  int32_t threads_per_cta;    /* 0: engine picks                                       */
+  int32_t max_invalid_streak; /* consecutive invalid proposals before RC_ERR_INVALID_STREAK (0: 1000) */
+} RcConfig;
+
+/* ---- chain state, resident in HBM, owned by the caller --------------------------- */
+typedef struct RcState {
+  uint8_t* d_assignment;   /* [n_chains][assign_stride] district index per node
+                              (partition/assignment.py:9 Assignment.mapping)          */
+  int64_t* d_tally;        /* [n_chains][k]  updaters/tally.py:69 Tally               */
+  uint32_t* d_cut_mask;    /* [n_chains][mask_stride] bit e set <=> edge e is cut
+                              (updaters/cut_edges.py:99)                              */
+  int32_t* d_cut_count;    /* [n_chains] len(partition["cut_edges"])                  */
+  int64_t* d_step_no;      /* [n_chains] accepted steps so far (chain.py:193)         */
+  uint32_t* d_proposal_no; /* [n_chains] proposals so far, valid or not (RNG counter) */
+  int32_t* d_status;       /* [n_chains] RC_OK or the RC_ERR_* that stopped the chain */
+  uint32_t* d_flags;       /* [n_chains] RC_FLAG_*                                    */
+  int64_t* d_counters;     /* [n_chains][RC_N_COUNTERS] see below                     */
+  int64_t assign_stride;   /* bytes between chains in d_assignment (multiple of 16)   */
+  int64_t mask_stride;     /* uint32 words between chains in d_cut_mask (multiple of 4) */
+} RcState;
+
+enum {
+  RC_CTR_TREES = 0,      /* spanning trees drawn                                      */
+  RC_CTR_ATTEMPTS = 1,   /* bipartition_tree attempts (tree.py:700)                   */
+  RC_CTR_NODES = 2,      /* sum of n_sub over proposals (roofline bytes)  */
+  RC_CTR_SLOTS = 3,      /* sum of d_sub (directed CSR slots of merged nodes)         */
+  RC_CTR_INVALID = 4,    /* proposals rejected by the population bounds               */
+  RC_CTR_RESELECT = 5,   /* ReselectException count                                   */
+  RC_CTR_WALK = 6,       /* Wilson successor draws                                    */
+  RC_CTR_ROUNDS = 7,     /* Boruvka rounds                                            */
+  RC_N_COUNTERS = 8
+};
+
+/* ---- replay (TEST HOOK): identical injected randomness ---------------------------- */
+typedef struct RcReplayStep {
+  int32_t pair_edge;   /* edge id picked at tree_proposals.py:106                      */
+  int32_t n_trees;     /* trees drawn by bipartition_tree in this step                 */
+  int64_t first_tree;  /* index of this step's first tree in the per-tree arrays       */
+  int32_t root;        /* node index chosen at tree.py:377 in the successful attempt   */
+  int32_t cut_edge;    /* edge id of the chosen Cut.edge; -1: apply cfg.cut_policy     */
+} RcReplayStep;
+
+typedef struct RcReplay {
+  int32_t n_steps;
+  int32_t chain;                 /* local chain index the record is applied to          */
+  const RcReplayStep* steps;     /* [n_steps]                                           */
+  const double* weights;         /* MST: [n_trees_total][E] random_weight per edge id   */
+  const int32_t* wilson_root;    /* Wilson: [n_trees_total] root (tree.py:112)          */
+  const int64_t* stack_ptr;      /* Wilson: [n_trees_total][N+1] into stack_val         */
+  const int32_t* stack_val;      /* Wilson: chosen neighbour node index per draw        */
+  uint8_t* assign_trace;         /* out, optional: [n_steps][N] assignment after step   */
+  int32_t* info_trace;           /* out, optional: [n_steps][4] {trees used, #balanced
+                                    cuts of the last tree, cut count after, status}    */
+} RcReplay;
+
+/* ---- engine ---------------------------------------------------------------------- */
+typedef struct RcEngine RcEngine;
+
+const char* rc_last_error(void);
+int rc_abi_version(void);
+
+/* Device-side sizes the caller must honour when allocating RcState buffers. */
+int rc_state_strides(const RcGraph* g, const RcConfig* c, int64_t* assign_stride,
+                     int64_t* mask_stride);
+
+/* Copies the (host) graph to the device, sizes caps and scratch.  Replaces the implicit
+ * graph capture of Partition.__init__ (partition/partition.py:122-151). */
+int rc_engine_create(const RcGraph* h_graph, const RcConfig* cfg, int device,
+                     RcEngine** out);
+int rc_engine_destroy(RcEngine* e);
+
+/* Remember the caller's state buffers (no copy). */
+int rc_engine_bind_state(RcEngine* e, const RcState* state);
+
+/* Full recompute of tally / cut mask / cut count from d_assignment and reset of the
+ * counters: Tally._initialize_tally (updaters/tally.py:118-141) and the first
+ * cut_edges scan (updaters/cut_edges.py:110-114). */
+int rc_engine_init_state(RcEngine* e, void* stream);
+
+/* Advance every chain by n_steps accepted steps: the body of MarkovChain.__next__
+ * (chain.py:185-195) with proposal = recom (proposals/tree_proposals.py:36-146),
+ * constraints = population Bounds, accept = always_accept (accept.py:15). */
+int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream);
+
+/* TEST HOOK: apply recorded reference steps to one chain (device pointers inside). */
+int rc_engine_replay(RcEngine* e, const RcReplay* d_replay_host_struct, void* stream);
+
+/* Ensemble histograms over this device's chains (int64 counts, caller zeroes/accumulates):
+ * cut_hist[min(cut_count, n_cut_bins-1)]++ ;
+ * dev_hist[min(floor(max_d |pop_d - ideal| / ideal / dev_bin_width), n_dev_bins-1)]++
+ * (constraints/validity.py:96-122 deviation_from_ideal). */
+int rc_engine_histograms(RcEngine* e, int64_t* d_cut_hist, int32_t n_cut_bins,
+                         int64_t* d_dev_hist, int32_t n_dev_bins, double dev_bin_width,
+                         void* stream);
+
+/* Introspection: caps chosen, shared memory per CTA, resident CTAs per SM, grid. */
+typedef struct RcEngineInfo {
+  int32_t cap_nodes, cap_edges, threads_per_cta, ctas_per_sm, n_sms, grid;
+  int64_t smem_bytes, scratch_bytes;
+  int64_t kernel_launches; /* launches of this library's kernels so far              */
+} RcEngineInfo;
+int rc_engine_info(RcEngine* e, RcEngineInfo* out);
+
+/* Device time (ms) of the last rc_engine_run, measured with CUDA events on its stream;
+ * synchronises on the end event. */
+int rc_engine_last_run_ms(RcEngine* e, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECOM_B200_H */

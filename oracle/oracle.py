@@ -1,0 +1,152 @@
+"""ctypes binding of the CPU oracle (oracle/librecom_oracle.so).
+
+TEST INFRASTRUCTURE ONLY - imported by tests/, __graft_entry__.smoke() and bench.py's CPU
+baseline legs; never by gerrychain_b200.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from gerrychain_b200 import _abi
+from gerrychain_b200.config import EngineConfig, strides
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", HERE], check=True)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "librecom_oracle.so")
+        if not os.path.exists(path):
+            build()
+        _lib = C.CDLL(path)
+        _lib.rco_work_create.restype = C.c_void_p
+        _lib.rco_work_create.argtypes = [C.POINTER(_abi.RcGraph)]
+        _lib.rco_work_destroy.argtypes = [C.c_void_p]
+        _lib.rco_replay.argtypes = [
+            C.POINTER(_abi.RcGraph), C.POINTER(_abi.RcConfig), C.c_void_p,
+            C.POINTER(_abi.RcReplay)] + [C.c_void_p] * 6
+        _lib.rco_init_chains.argtypes = [
+            C.POINTER(_abi.RcGraph), C.POINTER(_abi.RcConfig), C.POINTER(_abi.RcState)]
+        _lib.rco_run_chains.argtypes = [
+            C.POINTER(_abi.RcGraph), C.POINTER(_abi.RcConfig), C.c_int64,
+            C.POINTER(_abi.RcState), C.c_int]
+        _lib.rco_balanced_cuts_of_tree.argtypes = [
+            C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_void_p]
+        _lib.rco_mst_of_graph.argtypes = [C.POINTER(_abi.RcGraph), C.c_void_p, C.c_void_p]
+        _lib.rco_philox.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        _lib.rco_philox.restype = None
+    return _lib
+
+
+def philox(k0, k1, ctr):
+    out = np.zeros(4, dtype=np.uint32)
+    c = np.asarray(ctr, dtype=np.uint32)
+    load().rco_philox(k0, k1, c.ctypes.data, out.ctypes.data)
+    return out
+
+
+def balanced_cuts_of_tree(n, tree_edges, pops, ideal, eps, root):
+    uv = np.ascontiguousarray(tree_edges, dtype=np.int32)
+    p = np.ascontiguousarray(pops, dtype=np.int32)
+    out = np.zeros((n, 2), dtype=np.int32)
+    nb = load().rco_balanced_cuts_of_tree(n, uv.ctypes.data, p.ctypes.data, ideal, eps, root,
+                                          out.ctypes.data)
+    return [tuple(map(int, r)) for r in out[:nb]]
+
+
+def mst_of_graph(csr, weights):
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    out = np.zeros(csr.n_nodes, dtype=np.int32)
+    g = _abi.graph_struct(csr)
+    nt = load().rco_mst_of_graph(C.byref(g), w.ctypes.data, out.ctypes.data)
+    if nt < 0:
+        raise RuntimeError(_abi.STATUS_NAMES[-nt])
+    return np.sort(out[:nt])
+
+
+class OracleChains:
+    """Host-resident twin of the device engine's state, advanced by the C oracle."""
+
+    def __init__(self, csr, cfg: EngineConfig, assignment):
+        self.lib = load()
+        self.csr = csr
+        self.cfg = cfg
+        self.cstruct = cfg.to_struct()
+        self.gstruct = _abi.graph_struct(csr)
+        n, k = cfg.n_chains, cfg.n_districts
+        self.assign_stride, self.mask_stride = strides(csr.n_nodes, csr.n_edges)
+        a = np.asarray(assignment, dtype=np.uint8)
+        if a.ndim == 1:
+            a = np.broadcast_to(a, (n, csr.n_nodes))
+        self.assignment = np.zeros((n, self.assign_stride), dtype=np.uint8)
+        self.assignment[:, : csr.n_nodes] = a
+        self.tally = np.zeros((n, k), dtype=np.int64)
+        self.cut_mask = np.zeros((n, self.mask_stride), dtype=np.uint32)
+        self.cut_count = np.zeros(n, dtype=np.int32)
+        self.step_no = np.zeros(n, dtype=np.int64)
+        self.proposal_no = np.zeros(n, dtype=np.uint32)
+        self.status = np.zeros(n, dtype=np.int32)
+        self.flags = np.zeros(n, dtype=np.uint32)
+        self.counters = np.zeros((n, _abi.RC_N_COUNTERS), dtype=np.int64)
+        st = _abi.RcState()
+        st.d_assignment = self.assignment.ctypes.data
+        st.d_tally = self.tally.ctypes.data
+        st.d_cut_mask = self.cut_mask.ctypes.data
+        st.d_cut_count = self.cut_count.ctypes.data
+        st.d_step_no = self.step_no.ctypes.data
+        st.d_proposal_no = self.proposal_no.ctypes.data
+        st.d_status = self.status.ctypes.data
+        st.d_flags = self.flags.ctypes.data
+        st.d_counters = self.counters.ctypes.data
+        st.assign_stride = self.assign_stride
+        st.mask_stride = self.mask_stride
+        self.state = st
+        rc = self.lib.rco_init_chains(C.byref(self.gstruct), C.byref(self.cstruct), C.byref(st))
+        if rc:
+            raise RuntimeError(_abi.STATUS_NAMES.get(rc, rc))
+
+    def run(self, n_steps, n_threads=1):
+        self.lib.rco_run_chains(C.byref(self.gstruct), C.byref(self.cstruct), int(n_steps),
+                                C.byref(self.state), int(n_threads))
+        return self
+
+    def assignments(self):
+        return self.assignment[:, : self.csr.n_nodes]
+
+    def replay(self, rec, chain=0):
+        """rec: tests/_golden.ReplayArrays (host numpy).  Returns (assign_trace, info)."""
+        n_steps = len(rec.steps)
+        trace = np.zeros((n_steps, self.csr.n_nodes), dtype=np.uint8)
+        info = np.zeros((n_steps, 4), dtype=np.int32)
+        rp = _abi.RcReplay()
+        rp.n_steps = n_steps
+        rp.chain = chain
+        rp.steps = rec.steps.ctypes.data
+        rp.weights = rec.weights.ctypes.data if rec.weights is not None else None
+        rp.wilson_root = rec.wilson_root.ctypes.data if rec.wilson_root is not None else None
+        rp.stack_ptr = rec.stack_ptr.ctypes.data if rec.stack_ptr is not None else None
+        rp.stack_val = rec.stack_val.ctypes.data if rec.stack_val is not None else None
+        rp.assign_trace = trace.ctypes.data
+        rp.info_trace = info.ctypes.data
+        w = self.lib.rco_work_create(C.byref(self.gstruct))
+        try:
+            rc = self.lib.rco_replay(
+                C.byref(self.gstruct), C.byref(self.cstruct), w, C.byref(rp),
+                self.assignment[chain].ctypes.data, self.tally[chain].ctypes.data,
+                self.cut_mask[chain].ctypes.data,
+                self.cut_count[chain:].ctypes.data, self.counters[chain].ctypes.data,
+                self.flags[chain:].ctypes.data)
+        finally:
+            self.lib.rco_work_destroy(w)
+        return rc, trace, info

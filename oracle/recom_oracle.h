@@ -1,0 +1,40 @@
+/*
+ * recom_oracle.h - CPU oracle for the ReCom hot path.  TEST INFRASTRUCTURE ONLY:
+ * see the header of recom_oracle.c.  Shares the plain-C structs of the product ABI
+ * (include/recom_b200.h) so one replay record / configuration drives both sides; in the
+ * oracle every RcState / RcReplay pointer is a HOST pointer.
+ */
+#ifndef RECOM_ORACLE_H
+#define RECOM_ORACLE_H
+
+#include "../include/recom_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct RcoWork RcoWork;
+
+RcoWork* rco_work_create(const RcGraph* g);
+void rco_work_destroy(RcoWork* w);
+
+int rco_init_state(const RcGraph* g, const RcConfig* c, const uint8_t* assign,
+                   int64_t* tally, uint32_t* mask, int32_t* cut_count);
+int rco_step(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t global_chain,
+             uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
+             uint32_t* proposal_no, int64_t* counters, uint32_t* flags);
+int rco_replay(const RcGraph* g, const RcConfig* c, RcoWork* w, const RcReplay* rp,
+               uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
+               int64_t* counters, uint32_t* flags);
+int rco_balanced_cuts_of_tree(int32_t n, const int32_t* tree_uv, const int32_t* pops,
+                              double ideal, double eps, int32_t root, int32_t* out_uv);
+int rco_mst_of_graph(const RcGraph* g, const double* weights, int32_t* out_eids);
+int rco_init_chains(const RcGraph* g, const RcConfig* c, const RcState* st);
+int rco_run_chains(const RcGraph* g, const RcConfig* c, int64_t n_steps, const RcState* st,
+                   int n_threads);
+void rco_philox(uint32_t k0, uint32_t k1, const uint32_t* ctr, uint32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,87 @@
+"""CPU tests: the C oracle against the reference's own known answers and recorded steps.
+
+Known-answer trees: /root/reference/tests/test_tree.py:354-385.
+Recorded steps: tests/golden/replay_*.npz (oracle/record_reference.py, unmodified reference).
+"""
+
+import numpy as np
+import pytest
+
+import _golden
+from gerrychain_b200 import _abi
+from oracle import oracle
+
+
+def test_philox_known_answers(oracle_lib):
+    # Random123 kat_vectors, philox4x32-10
+    assert list(oracle.philox(0, 0, [0, 0, 0, 0])) == [
+        0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert list(oracle.philox(0xFFFFFFFF, 0xFFFFFFFF, [0xFFFFFFFF] * 4)) == [
+        0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert list(oracle.philox(0xA4093822, 0x299F31D0,
+                              [0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344])) == [
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_find_balanced_cuts_known_answer(oracle_lib):
+    # reference tests/test_tree.py:354-372: 9-node tree, unit pops, ideal 4.5, eps 0.5
+    tree = [(0, 1), (1, 2), (1, 4), (3, 4), (4, 5), (3, 6), (6, 7), (6, 8)]
+    for root in (1, 3, 4, 6):
+        cuts = oracle.balanced_cuts_of_tree(9, tree, [1] * 9, 4.5, 0.5, root)
+        assert {tuple(sorted(c)) for c in cuts} == {(1, 4), (3, 4), (3, 6)}
+
+
+def test_no_balanced_cuts_when_one_side_okay(oracle_lib):
+    # reference tests/test_tree.py:375-385: path, pops {4,4,3,3,3}, ideal 10, eps 0.1
+    tree = [(0, 1), (1, 2), (2, 3), (3, 4)]
+    for root in (1, 2, 3):
+        assert oracle.balanced_cuts_of_tree(5, tree, [4, 4, 3, 3, 3], 10, 0.1, root) == []
+
+
+def test_mst_matches_scipy(oracle_lib):
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import minimum_spanning_tree
+
+    g = _golden.load("replay_delaunay2400_mst")
+    rng = np.random.default_rng(5)
+    for _ in range(3):
+        w = rng.random(g.csr.n_edges) + 0.01
+        uv = g.csr.edge_uv
+        m = coo_matrix((w, (uv[:, 0], uv[:, 1])), shape=(g.csr.n_nodes,) * 2).tocsr()
+        t = minimum_spanning_tree(m).tocoo()
+        look = g.csr.edge_id_lookup()
+        want = sorted(look[(min(a, b), max(a, b))] for a, b in zip(t.row, t.col))
+        got = oracle.mst_of_graph(g.csr, w)
+        assert list(got) == want
+
+
+@pytest.mark.parametrize("name", _golden.names())
+def test_replay_matches_reference(oracle_lib, name):
+    g = _golden.load(name)
+    ch = oracle.OracleChains(g.csr, g.cfg, g.init_assignment)
+    rc, trace, info = ch.replay(g.rec)
+    assert rc == 0, _abi.STATUS_NAMES.get(rc)
+    assert np.array_equal(trace, g.assignment), "assignment differs from the reference"
+    assert np.array_equal(info[:, 2], g.n_cut_edges)
+    # the balanced-cut set the reference saw in its successful attempt
+    assert np.array_equal(info[:, 1], np.diff(g.balanced_ptr))
+    # trees used == trees the reference drew (earlier trees had no balanced cut)
+    assert np.array_equal(info[:, 0], np.diff(g.tree_ptr))
+    assert np.array_equal(ch.tally[0], g.population[-1])
+    # incremental cut mask == naive recomputation (updaters/test_cut_edges.py:144-161)
+    uv = g.csr.edge_uv
+    a = trace[-1]
+    naive = np.nonzero(a[uv[:, 0]] != a[uv[:, 1]])[0]
+    bits = np.unpackbits(ch.cut_mask[0].view(np.uint8), bitorder="little")[: g.csr.n_edges]
+    assert np.array_equal(np.nonzero(bits)[0], naive)
+
+
+@pytest.mark.parametrize("name", [n for n in _golden.names() if "region" in n])
+def test_region_cut_policy_matches_reference(oracle_lib, name):
+    """cut_edge not injected: the oracle's own power-set / max-weight choice must pick the
+    reference's cut (tree.py:501-578)."""
+    g = _golden.load(name, inject_cut=False)
+    ch = oracle.OracleChains(g.csr, g.cfg, g.init_assignment)
+    rc, trace, info = ch.replay(g.rec)
+    assert rc == 0
+    assert np.array_equal(trace, g.assignment)
