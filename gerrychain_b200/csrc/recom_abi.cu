@@ -1,0 +1,254 @@
+// recom_abi.cu - host side of the C ABI declared in include/recom_b200.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "recom_kernels.cu"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_OK(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(RC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),  \
+                  __FILE__, __LINE__);                                                  \
+  } while (0)
+
+template <typename T>
+int upload(const T* h, size_t n, T** d) {
+  *d = nullptr;
+  if (n == 0) return RC_OK;
+  CUDA_OK(cudaMalloc((void**)d, n * sizeof(T)));
+  CUDA_OK(cudaMemcpy(*d, h, n * sizeof(T), cudaMemcpyHostToDevice));
+  return RC_OK;
+}
+
+}  // namespace
+
+struct RcEngine {
+  int device = 0;
+  rc::Params p{};
+  bool bound = false;
+  int grid = 0, threads = 0, ctas_per_sm = 0, n_sms = 0;
+  size_t smem = 0, scratch_bytes = 0;
+  int64_t launches = 0;
+  // owned device memory
+  int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_slot_edge = nullptr, *d_edge_uv = nullptr,
+          *d_pop = nullptr, *d_region = nullptr;
+  void* d_scratch = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+};
+
+extern "C" {
+
+const char* rc_last_error(void) { return g_err; }
+int rc_abi_version(void) { return RC_ABI_VERSION; }
+
+int rc_state_strides(const RcGraph* g, const RcConfig* c, int64_t* assign_stride, int64_t* mask_stride) {
+  (void)c;
+  if (!g || !assign_stride || !mask_stride) return fail(RC_ERR_INVALID_ARG, "null argument");
+  *assign_stride = ((int64_t)g->n_nodes + 15) / 16 * 16;
+  *mask_stride = (((int64_t)g->n_edges + 31) / 32 + 3) / 4 * 4;
+  return RC_OK;
+}
+
+int rc_engine_destroy(RcEngine* e) {
+  if (!e) return RC_OK;
+  cudaSetDevice(e->device);
+  cudaFree(e->d_row_ptr); cudaFree(e->d_col_idx); cudaFree(e->d_slot_edge); cudaFree(e->d_edge_uv);
+  cudaFree(e->d_pop); cudaFree(e->d_region); cudaFree(e->d_scratch);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  delete e;
+  return RC_OK;
+}
+
+int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine** out) {
+  if (!g || !cfg || !out) return fail(RC_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if (g->n_nodes < 2 || g->n_edges < 1) return fail(RC_ERR_INVALID_ARG, "empty graph");
+  if (cfg->n_districts < 2 || cfg->n_districts > 255)
+    return fail(RC_ERR_INVALID_ARG, "n_districts must be in [2, 255] (uint8 assignment)");
+  if (cfg->n_chains < 1) return fail(RC_ERR_INVALID_ARG, "n_chains must be >= 1");
+  if (g->n_region_cols < 0 || g->n_region_cols > 8)
+    return fail(RC_ERR_INVALID_ARG, "at most 8 region columns");
+  if (cfg->tree_kind != RC_TREE_MST)
+    return fail(RC_ERR_INVALID_ARG, "tree_kind %d not supported by this build", cfg->tree_kind);
+  if (!(cfg->epsilon > 0.0) || !(cfg->pop_target > 0.0))
+    return fail(RC_ERR_INVALID_ARG, "epsilon and pop_target must be positive");
+  CUDA_OK(cudaSetDevice(device));
+  RcEngine* e = new (std::nothrow) RcEngine();
+  if (!e) return fail(RC_ERR_INVALID_ARG, "out of host memory");
+  e->device = device;
+  const int N = g->n_nodes, E = g->n_edges, R = g->n_region_cols;
+  int rc;
+#define UP(field, src, n) if ((rc = upload(src, (size_t)(n), &e->field)) != RC_OK) { rc_engine_destroy(e); return rc; }
+  UP(d_row_ptr, g->row_ptr, N + 1)
+  UP(d_col_idx, g->col_idx, 2 * (size_t)E)
+  UP(d_slot_edge, g->slot_edge, 2 * (size_t)E)
+  UP(d_edge_uv, g->edge_uv, 2 * (size_t)E)
+  UP(d_pop, g->pop, N)
+  UP(d_region, g->region_ids, (size_t)R * N)
+#undef UP
+  rc::Params& p = e->p;
+  p.g.N = N; p.g.E = E; p.g.R = R;
+  p.g.row_ptr = e->d_row_ptr; p.g.col_idx = e->d_col_idx; p.g.slot_edge = e->d_slot_edge;
+  p.g.edge_uv = e->d_edge_uv; p.g.pop = e->d_pop; p.g.region_ids = e->d_region;
+  for (int r = 0; r < R; ++r) p.g.surcharge[r] = g->surcharges[r];
+  p.cfg = *cfg;
+  // caps: merged pair of two districts, with head-room (RC_ERR_CAPACITY if exceeded)
+  const int k = cfg->n_districts;
+  int cap_nodes = cfg->cap_nodes > 0 ? cfg->cap_nodes : (int)(2.6 * N / k) + 32;
+  if (cap_nodes > N) cap_nodes = N;
+  if (cap_nodes > rc::kMaxLocal) cap_nodes = rc::kMaxLocal;
+  int cap_edges = cfg->cap_edges > 0 ? cfg->cap_edges
+                                     : (int)(1.15 * cap_nodes * ((double)E / N)) + 64;
+  if (cap_edges > E) cap_edges = E;
+  if (cap_edges > 65535) cap_edges = 65535;
+  cap_nodes = (cap_nodes + 7) & ~7;
+  cap_edges = (cap_edges + 31) & ~31;
+  p.cap_nodes = cap_nodes; p.cap_edges = cap_edges;
+  e->smem = rc::smem_layout(nullptr, nullptr, cap_nodes, cap_edges);
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  e->n_sms = prop.multiProcessorCount;
+  if (e->smem > (size_t)prop.sharedMemPerBlockOptin) {
+    rc_engine_destroy(e);
+    return fail(RC_ERR_CAPACITY, "merged pair of %d nodes / %d edges needs %zu B shared memory (> %zu)",
+                cap_nodes, cap_edges, e->smem, (size_t)prop.sharedMemPerBlockOptin);
+  }
+  CUDA_OK(cudaFuncSetAttribute(rc::recom_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  e->threads = cfg->threads_per_cta > 0 ? cfg->threads_per_cta : 256;
+  if (e->threads > 512) e->threads = 512;
+  e->threads = (e->threads + 31) & ~31;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->ctas_per_sm, rc::recom_step_kernel, e->threads, e->smem));
+  if (e->ctas_per_sm < 1) { rc_engine_destroy(e); return fail(RC_ERR_CAPACITY, "kernel does not fit an SM"); }
+  e->grid = cfg->n_chains;  // one CTA per chain; the hardware scheduler refills SMs
+  // scratch
+  const int64_t n16 = ((int64_t)N + 15) / 16 * 16;
+  p.g2l_stride = n16;
+  size_t b_g2l = (size_t)e->grid * n16 * sizeof(uint16_t);
+  size_t b_nodes = (size_t)e->grid * cap_nodes * sizeof(int32_t);
+  size_t b_eids = (size_t)e->grid * cap_edges * sizeof(int32_t);
+  size_t b_bad = cfg->allow_pair_reselection ? (size_t)e->grid * 2048 * sizeof(uint32_t) : 0;
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  e->scratch_bytes = al(b_g2l) + al(b_nodes) + al(b_eids) + al(b_bad) + 256;
+  CUDA_OK(cudaMalloc(&e->d_scratch, e->scratch_bytes));
+  char* base = (char*)e->d_scratch;
+  p.g2l = (uint16_t*)base; base += al(b_g2l);
+  p.nodes = (int32_t*)base; base += al(b_nodes);
+  p.eids = (int32_t*)base; base += al(b_eids);
+  p.badpairs = b_bad ? (uint32_t*)base : nullptr; base += al(b_bad);
+  p.work_counter = (int32_t*)base;
+  CUDA_OK(cudaEventCreate(&e->ev0));
+  CUDA_OK(cudaEventCreate(&e->ev1));
+  *out = e;
+  return RC_OK;
+}
+
+int rc_engine_bind_state(RcEngine* e, const RcState* st) {
+  if (!e || !st) return fail(RC_ERR_INVALID_ARG, "null argument");
+  if (!st->d_assignment || !st->d_tally || !st->d_cut_mask || !st->d_cut_count || !st->d_step_no ||
+      !st->d_proposal_no || !st->d_status || !st->d_flags || !st->d_counters)
+    return fail(RC_ERR_INVALID_ARG, "RcState has a null buffer");
+  int64_t as, ms;
+  RcGraph g{}; g.n_nodes = e->p.g.N; g.n_edges = e->p.g.E;
+  rc_state_strides(&g, &e->p.cfg, &as, &ms);
+  if (st->assign_stride < as || st->assign_stride % 16 || st->mask_stride < ms || st->mask_stride % 4)
+    return fail(RC_ERR_INVALID_ARG, "state strides must be >= rc_state_strides() and 16-byte multiples");
+  if (((uintptr_t)st->d_assignment & 15) || ((uintptr_t)st->d_cut_mask & 15))
+    return fail(RC_ERR_INVALID_ARG, "d_assignment and d_cut_mask must be 16-byte aligned");
+  e->p.st = *st;
+  e->bound = true;
+  return RC_OK;
+}
+
+int rc_engine_init_state(RcEngine* e, void* stream) {
+  if (!e || !e->bound) return fail(RC_ERR_INVALID_ARG, "engine has no bound state");
+  CUDA_OK(cudaSetDevice(e->device));
+  rc::Params p = e->p;
+  p.rp = RcReplay{};
+  rc::init_state_kernel<<<e->p.cfg.n_chains, 256, 0, (cudaStream_t)stream>>>(p);
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return RC_OK;
+}
+
+int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream) {
+  if (!e || !e->bound) return fail(RC_ERR_INVALID_ARG, "engine has no bound state");
+  if (n_steps <= 0) return RC_OK;
+  CUDA_OK(cudaSetDevice(e->device));
+  rc::Params p = e->p;
+  p.rp = RcReplay{};
+  p.n_steps = n_steps;
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_OK(cudaEventRecord(e->ev0, s));
+  rc::recom_step_kernel<<<e->grid, e->threads, e->smem, s>>>(p);
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(e->ev1, s));
+  e->timed = true;
+  return RC_OK;
+}
+
+int rc_engine_replay(RcEngine* e, const RcReplay* rp, void* stream) {
+  if (!e || !e->bound || !rp) return fail(RC_ERR_INVALID_ARG, "engine has no bound state / null replay");
+  if (rp->n_steps <= 0 || !rp->steps) return fail(RC_ERR_INVALID_ARG, "empty replay");
+  if (rp->chain < 0 || rp->chain >= e->p.cfg.n_chains) return fail(RC_ERR_INVALID_ARG, "bad chain index");
+  if (e->p.cfg.tree_kind == RC_TREE_MST && !rp->weights) return fail(RC_ERR_INVALID_ARG, "MST replay needs weights");
+  CUDA_OK(cudaSetDevice(e->device));
+  rc::Params p = e->p;
+  p.rp = *rp;
+  p.n_steps = rp->n_steps;
+  rc::recom_step_kernel<<<1, e->threads, e->smem, (cudaStream_t)stream>>>(p);
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return RC_OK;
+}
+
+int rc_engine_histograms(RcEngine* e, int64_t* d_cut_hist, int32_t n_cut_bins, int64_t* d_dev_hist,
+                         int32_t n_dev_bins, double dev_bin_width, void* stream) {
+  if (!e || !e->bound) return fail(RC_ERR_INVALID_ARG, "engine has no bound state");
+  if ((d_cut_hist && n_cut_bins < 1) || (d_dev_hist && (n_dev_bins < 1 || !(dev_bin_width > 0))))
+    return fail(RC_ERR_INVALID_ARG, "bad histogram shape");
+  CUDA_OK(cudaSetDevice(e->device));
+  const int n = e->p.cfg.n_chains;
+  rc::histogram_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      e->p, (unsigned long long*)d_cut_hist, n_cut_bins, (unsigned long long*)d_dev_hist, n_dev_bins, dev_bin_width);
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return RC_OK;
+}
+
+int rc_engine_info(RcEngine* e, RcEngineInfo* out) {
+  if (!e || !out) return fail(RC_ERR_INVALID_ARG, "null argument");
+  out->cap_nodes = e->p.cap_nodes; out->cap_edges = e->p.cap_edges;
+  out->threads_per_cta = e->threads; out->ctas_per_sm = e->ctas_per_sm; out->n_sms = e->n_sms;
+  out->grid = e->grid; out->smem_bytes = (int64_t)e->smem; out->scratch_bytes = (int64_t)e->scratch_bytes;
+  out->kernel_launches = e->launches;
+  return RC_OK;
+}
+
+int rc_engine_last_run_ms(RcEngine* e, float* ms) {
+  if (!e || !ms) return fail(RC_ERR_INVALID_ARG, "null argument");
+  if (!e->timed) return fail(RC_ERR_INVALID_ARG, "no rc_engine_run has been issued");
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaEventSynchronize(e->ev1));
+  CUDA_OK(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+  return RC_OK;
+}
+
+}  // extern "C"

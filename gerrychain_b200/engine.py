@@ -1,0 +1,182 @@
+"""Device engine: torch-owned chain state + the C-ABI calls of librecom_b200.so.
+
+PyTorch is plumbing here (device buffers, streams, torch.distributed); every compute
+step is a CUDA kernel of the in-tree library reached through ctypes.  There is no CPU
+fallback: constructing an ``Engine`` without the library or without a CUDA device raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+from .config import EngineConfig, strides
+from .csr import GraphCSR
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, message: str = ""):
+        self.code = code
+        name = _abi.STATUS_NAMES.get(code, str(code))
+        super().__init__(f"{name}: {message}" if message else name)
+
+
+def _check(lib, rc: int):
+    if rc != _abi.RC_OK:
+        raise EngineError(rc, lib.rc_last_error().decode())
+
+
+class Engine:
+    """n_chains independent ReCom chains resident on one GPU."""
+
+    def __init__(self, csr: GraphCSR, cfg: EngineConfig, assignment, device=None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("gerrychain_b200.Engine needs a CUDA device (no CPU fallback)")
+        self.lib = _abi.load()
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.csr = csr
+        self.cfg = cfg
+        n, k = cfg.n_chains, cfg.n_districts
+        self.assign_stride, self.mask_stride = strides(csr.n_nodes, csr.n_edges)
+        dev = self.device
+        a = np.asarray(assignment)
+        if a.ndim == 1:
+            a = np.broadcast_to(a, (n, csr.n_nodes))
+        if a.shape != (n, csr.n_nodes):
+            raise ValueError("assignment must be [N] or [n_chains, N]")
+        if a.min() < 0 or a.max() >= k:
+            raise ValueError("assignment entries must be district indices in [0, k)")
+        host = np.zeros((n, self.assign_stride), dtype=np.uint8)
+        host[:, : csr.n_nodes] = a
+        self.assignment = torch.from_numpy(host).to(dev)
+        self.tally = torch.zeros((n, k), dtype=torch.int64, device=dev)
+        self.cut_mask = torch.zeros((n, self.mask_stride), dtype=torch.int32, device=dev)
+        self.cut_count = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.step_no = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.proposal_no = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.flags = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.counters = torch.zeros((n, _abi.RC_N_COUNTERS), dtype=torch.int64, device=dev)
+        self._handle = C.c_void_p()
+        g = _abi.graph_struct(csr)
+        c = cfg.to_struct()
+        _check(self.lib, self.lib.rc_engine_create(C.byref(g), C.byref(c), self.device.index, C.byref(self._handle)))
+        st = _abi.RcState()
+        st.d_assignment = self.assignment.data_ptr()
+        st.d_tally = self.tally.data_ptr()
+        st.d_cut_mask = self.cut_mask.data_ptr()
+        st.d_cut_count = self.cut_count.data_ptr()
+        st.d_step_no = self.step_no.data_ptr()
+        st.d_proposal_no = self.proposal_no.data_ptr()
+        st.d_status = self.status.data_ptr()
+        st.d_flags = self.flags.data_ptr()
+        st.d_counters = self.counters.data_ptr()
+        st.assign_stride = self.assign_stride
+        st.mask_stride = self.mask_stride
+        self._state = st
+        _check(self.lib, self.lib.rc_engine_bind_state(self._handle, C.byref(st)))
+        self.init_state()
+
+    # -- lifecycle ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_handle", None) and self._handle.value:
+            self.torch.cuda.synchronize(self.device)
+            self.lib.rc_engine_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- ABI calls ---------------------------------------------------------------------
+    def init_state(self):
+        _check(self.lib, self.lib.rc_engine_init_state(self._handle, self._stream()))
+
+    def set_assignment(self, assignment):
+        """Host -> device copy of new plans (one per chain or one for all) + re-init."""
+        a = np.asarray(assignment, dtype=np.uint8)
+        if a.ndim == 1:
+            a = np.broadcast_to(a, (self.cfg.n_chains, self.csr.n_nodes))
+        host = np.zeros((self.cfg.n_chains, self.assign_stride), dtype=np.uint8)
+        host[:, : self.csr.n_nodes] = a
+        self.assignment.copy_(self.torch.from_numpy(host), non_blocking=False)
+        self.init_state()
+
+    def run(self, n_steps: int):
+        """Advance every chain by ``n_steps`` accepted steps (asynchronous)."""
+        _check(self.lib, self.lib.rc_engine_run(self._handle, int(n_steps), self._stream()))
+        return self
+
+    def last_run_ms(self) -> float:
+        ms = C.c_float()
+        _check(self.lib, self.lib.rc_engine_last_run_ms(self._handle, C.byref(ms)))
+        return float(ms.value)
+
+    def info(self) -> _abi.RcEngineInfo:
+        out = _abi.RcEngineInfo()
+        _check(self.lib, self.lib.rc_engine_info(self._handle, C.byref(out)))
+        return out
+
+    def histograms(self, n_cut_bins: int, n_dev_bins: int, dev_bin_width: float):
+        t = self.torch
+        cut = t.zeros(n_cut_bins, dtype=t.int64, device=self.device)
+        dev = t.zeros(n_dev_bins, dtype=t.int64, device=self.device)
+        _check(self.lib, self.lib.rc_engine_histograms(
+            self._handle, cut.data_ptr(), n_cut_bins, dev.data_ptr(), n_dev_bins,
+            float(dev_bin_width), self._stream()))
+        return cut, dev
+
+    def replay(self, rec, chain: int = 0):
+        """TEST HOOK: apply recorded reference steps (tests/_golden.ReplayArrays)."""
+        t = self.torch
+        dev = self.device
+        n_steps = len(rec.steps)
+        keep = []
+
+        def up(arr):
+            if arr is None:
+                return None
+            x = t.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(dev)
+            keep.append(x)
+            return x.data_ptr()
+
+        trace = t.zeros((n_steps, self.csr.n_nodes), dtype=t.uint8, device=dev)
+        info = t.zeros((n_steps, 4), dtype=t.int32, device=dev)
+        rp = _abi.RcReplay()
+        rp.n_steps = n_steps
+        rp.chain = chain
+        rp.steps = up(rec.steps)
+        rp.weights = up(rec.weights)
+        rp.wilson_root = up(rec.wilson_root)
+        rp.stack_ptr = up(rec.stack_ptr)
+        rp.stack_val = up(rec.stack_val)
+        rp.assign_trace = trace.data_ptr()
+        rp.info_trace = info.data_ptr()
+        _check(self.lib, self.lib.rc_engine_replay(self._handle, C.byref(rp), self._stream()))
+        t.cuda.synchronize(dev)
+        return trace.cpu().numpy(), info.cpu().numpy()
+
+    # -- read-backs --------------------------------------------------------------------
+    def synchronize(self):
+        self.torch.cuda.synchronize(self.device)
+
+    def assignments(self) -> np.ndarray:
+        return self.assignment[:, : self.csr.n_nodes].cpu().numpy()
+
+    def check_status(self):
+        """Raise the reference's exception for the first chain that stopped."""
+        st = self.status.cpu().numpy()
+        bad = np.nonzero(st)[0]
+        if len(bad):
+            raise EngineError(int(st[bad[0]]), f"chain {int(bad[0])} stopped ({len(bad)} chains in error)")

@@ -1,0 +1,175 @@
+"""GPU parity tests (run on the B200 box): the CUDA engine, called through the C ABI,
+against (1) recorded reference steps and (2) the CPU oracle on identical Philox draws."""
+
+import numpy as np
+import pytest
+
+import _golden
+from gerrychain_b200 import _abi, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(csr, cfg, plan):
+    from gerrychain_b200.engine import Engine
+
+    return Engine(csr, cfg, plan)
+
+
+def _naive_check(csr, k, assign, tally, cut_mask, cut_count):
+    """Incremental updaters == naive recomputation (reference tests/updaters/
+    test_cut_edges.py:144-161, tests/test_tally.py:56-76)."""
+    uv = csr.edge_uv
+    for c in range(assign.shape[0]):
+        a = assign[c]
+        want = np.bincount(a, weights=csr.pop, minlength=k).astype(np.int64)
+        assert np.array_equal(tally[c], want)
+        naive = a[uv[:, 0]] != a[uv[:, 1]]
+        bits = np.unpackbits(cut_mask[c].view(np.uint8), bitorder="little")[: csr.n_edges]
+        assert np.array_equal(bits.astype(bool), naive)
+        assert cut_count[c] == naive.sum()
+
+
+@pytest.mark.parametrize("name", _golden.names("mst"))
+def test_replay_bit_exact_with_reference(name):
+    g = _golden.load(name)
+    eng = _engine(g.csr, g.cfg, g.init_assignment)
+    trace, info = eng.replay(g.rec)
+    assert (info[:, 3] == 0).all(), [_abi.STATUS_NAMES.get(int(x)) for x in info[:, 3]]
+    assert np.array_equal(trace, g.assignment)
+    assert np.array_equal(info[:, 2], g.n_cut_edges)
+    assert np.array_equal(info[:, 1], np.diff(g.balanced_ptr))
+    assert np.array_equal(info[:, 0], np.diff(g.tree_ptr))
+    assert np.array_equal(eng.tally.cpu().numpy()[0], g.population[-1])
+    _naive_check(g.csr, g.cfg.n_districts, eng.assignments(), eng.tally.cpu().numpy(),
+                 eng.cut_mask.cpu().numpy(), eng.cut_count.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", [n for n in _golden.names("mst") if "region" in n])
+def test_replay_region_policy_on_device(name):
+    g = _golden.load(name, inject_cut=False)
+    eng = _engine(g.csr, g.cfg, g.init_assignment)
+    trace, info = eng.replay(g.rec)
+    assert (info[:, 3] == 0).all()
+    assert np.array_equal(trace, g.assignment)
+
+
+def _free_run_vs_oracle(csr, plan, cfg, steps):
+    from oracle import oracle
+
+    eng = _engine(csr, cfg, plan)
+    eng.run(steps).synchronize()
+    ora = oracle.OracleChains(csr, cfg, plan).run(steps, n_threads=8)
+    assert np.array_equal(eng.status.cpu().numpy(), ora.status)
+    assert (ora.status == 0).all()
+    assert np.array_equal(eng.assignments(), ora.assignments())
+    assert np.array_equal(eng.tally.cpu().numpy(), ora.tally)
+    assert np.array_equal(eng.cut_count.cpu().numpy(), ora.cut_count)
+    assert np.array_equal(eng.cut_mask.cpu().numpy().view(np.uint32), ora.cut_mask)
+    assert np.array_equal(eng.proposal_no.cpu().numpy().view(np.uint32), ora.proposal_no)
+    assert np.array_equal(eng.step_no.cpu().numpy(), ora.step_no)
+    ce, co = eng.counters.cpu().numpy(), ora.counters
+    for i in (_abi.RC_CTR_TREES, _abi.RC_CTR_ATTEMPTS, _abi.RC_CTR_NODES, _abi.RC_CTR_SLOTS,
+              _abi.RC_CTR_INVALID):
+        assert np.array_equal(ce[:, i], co[:, i]), i
+    _naive_check(csr, cfg.n_districts, eng.assignments(), eng.tally.cpu().numpy(),
+                 eng.cut_mask.cpu().numpy(), eng.cut_count.cpu().numpy())
+    return eng
+
+
+@pytest.mark.parametrize("name", ["replay_grid20_mst", "replay_grid10diag_mst",
+                                  "replay_delaunay2400_mst", "replay_delaunay2400_region",
+                                  "replay_8x8_region2", "replay_8x8_region3"])
+def test_free_run_bit_exact_with_oracle_small(name):
+    g = _golden.load(name)
+    cfg = g.cfg
+    cfg.n_chains = 16
+    cfg.seed = 1234
+    _free_run_vs_oracle(g.csr, g.init_assignment, cfg, 40)
+
+
+def test_free_run_config1():
+    csr, plan, cfg = workloads.config1(n_chains=64, seed=7)
+    _free_run_vs_oracle(csr, plan, cfg, 100)
+
+
+def test_free_run_config2():
+    csr, plan, cfg = workloads.config2(n_chains=32, seed=11)
+    _free_run_vs_oracle(csr, plan, cfg, 25)
+
+
+def test_free_run_config3():
+    csr, plan, cfg = workloads.config3(n_chains=32, seed=13)
+    _free_run_vs_oracle(csr, plan, cfg, 25)
+
+
+def test_free_run_config5_region_aware():
+    csr, plan, cfg = workloads.config5(n_chains=16, seed=17)
+    _free_run_vs_oracle(csr, plan, cfg, 15)
+
+
+def test_node_repeats_and_tight_bounds():
+    # percent != epsilon: proposals can be invalid and must not count as steps
+    csr, plan, cfg = workloads.config1(n_chains=16, seed=3, node_repeats=2)
+    ideal = cfg.pop_target
+    cfg.pop_lower, cfg.pop_upper = 0.98 * ideal, 1.02 * ideal
+    eng = _free_run_vs_oracle(csr, plan, cfg, 50)
+    assert eng.counters.cpu().numpy()[:, _abi.RC_CTR_INVALID].sum() > 0
+
+
+def test_max_attempts_status():
+    # reference tests/test_region_aware.py:102-112: max_attempts=1 -> RuntimeError
+    csr, plan, cfg = workloads.config1(n_chains=8, seed=5, max_attempts=1)
+    from oracle import oracle
+    from gerrychain_b200.engine import EngineError
+
+    eng = _engine(csr, cfg, plan)
+    eng.run(50).synchronize()
+    ora = oracle.OracleChains(csr, cfg, plan).run(50)
+    st = eng.status.cpu().numpy()
+    assert np.array_equal(st, ora.status)
+    assert (st == _abi.RC_ERR_MAX_ATTEMPTS).any()
+    assert np.array_equal(eng.step_no.cpu().numpy(), ora.step_no)
+    with pytest.raises(EngineError):
+        eng.check_status()
+
+
+def test_pair_reselection():
+    csr, plan, cfg = workloads.config1(n_chains=8, seed=5, max_attempts=2, allow_pair_reselection=True)
+    _free_run_vs_oracle(csr, plan, cfg, 60)
+
+
+def test_full_size_properties_config2():
+    """1024 chains at BASELINE's size: size-independent properties (naive == incremental,
+    population bounds, contiguity of every district)."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+
+    csr, plan, cfg = workloads.config2(n_chains=1024, seed=99)
+    eng = _engine(csr, cfg, plan)
+    eng.run(10).synchronize()
+    eng.check_status()
+    a = eng.assignments()
+    tally = eng.tally.cpu().numpy()
+    _naive_check(csr, cfg.n_districts, a, tally, eng.cut_mask.cpu().numpy(), eng.cut_count.cpu().numpy())
+    assert (tally >= cfg.pop_lower).all() and (tally <= cfg.pop_upper).all()
+    assert (eng.step_no.cpu().numpy() == 10).all()
+    uv = csr.edge_uv
+    for c in range(0, 1024, 64):
+        same = a[c][uv[:, 0]] == a[c][uv[:, 1]]
+        m = coo_matrix((np.ones(same.sum()), (uv[same, 0], uv[same, 1])), shape=(csr.n_nodes,) * 2)
+        ncomp, _ = connected_components(m, directed=False)
+        assert ncomp == cfg.n_districts
+    # different chains diverge (distinct Philox subsequences)
+    assert len({a[c].tobytes() for c in range(64)}) == 64
+
+
+def test_histograms():
+    csr, plan, cfg = workloads.config1(n_chains=128, seed=2)
+    eng = _engine(csr, cfg, plan)
+    eng.run(20)
+    cut, dev = eng.histograms(256, 64, 0.001)
+    eng.synchronize()
+    cc = eng.cut_count.cpu().numpy()
+    assert np.array_equal(cut.cpu().numpy(), np.bincount(np.minimum(cc, 255), minlength=256))
+    assert int(dev.sum()) == 128
