@@ -107,6 +107,7 @@ class RcState(C.Structure):
         ("d_counters", C.c_void_p),
         ("assign_stride", C.c_int64),
         ("mask_stride", C.c_int64),
+        ("d_last_pair", C.c_void_p),
     ]
 
 
@@ -157,6 +158,7 @@ EXPORTS = (
     "rc_engine_bind_state",
     "rc_engine_init_state",
     "rc_engine_run",
+    "rc_engine_step_host",
     "rc_engine_replay",
     "rc_engine_histograms",
     "rc_engine_info",
@@ -194,6 +196,9 @@ def load() -> C.CDLL:
     lib.rc_engine_bind_state.argtypes = [C.c_void_p, C.POINTER(RcState)]
     lib.rc_engine_init_state.argtypes = [C.c_void_p, C.c_void_p]
     lib.rc_engine_run.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    lib.rc_engine_step_host.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_void_p]
     lib.rc_engine_replay.argtypes = [C.c_void_p, C.POINTER(RcReplay), C.c_void_p]
     lib.rc_engine_histograms.argtypes = [
         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]

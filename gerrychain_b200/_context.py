@@ -1,0 +1,144 @@
+"""Per-graph host cache behind the GerryChain-shaped API: node index, canonical CSR per
+population column, and the device engines built for it.
+
+The reference keeps all of this implicitly in networkx dicts and ``functools.lru_cache``s
+(/root/reference/gerrychain/graph/graph.py:508-577); here it is the bridge from a
+``networkx``-style graph object to the flat arrays the C ABI takes.
+"""
+
+from __future__ import annotations
+
+import random
+import weakref
+from typing import Dict, Hashable, Optional, Tuple
+
+import numpy as np
+
+from . import _abi
+from .config import EngineConfig, cut_policy_for
+from .csr import GraphCSR, csr_from_edges
+
+_contexts: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def unwrap_graph(graph):
+    """Accept a networkx graph or anything forwarding ``.nodes`` / ``.edges`` to one
+    (the reference's FrozenGraph, graph/graph.py:508)."""
+    inner = getattr(graph, "graph", None)
+    if inner is not None and hasattr(inner, "nodes") and not isinstance(inner, dict):
+        return inner
+    return graph
+
+
+def context_of(graph) -> "GraphContext":
+    g = unwrap_graph(graph)
+    ctx = _contexts.get(g)
+    if ctx is None:
+        ctx = GraphContext(g)
+        _contexts[g] = ctx
+    return ctx
+
+
+class GraphContext:
+    def __init__(self, graph):
+        if not hasattr(graph, "nodes") or not hasattr(graph, "edges"):
+            raise TypeError(f"Unsupported Graph object with type {type(graph)}")
+        self.graph_ref = weakref.ref(graph)
+        self.labels = list(graph.nodes)
+        self.index: Dict[Hashable, int] = {lab: i for i, lab in enumerate(self.labels)}
+        self.n_nodes = len(self.labels)
+        self.edges = np.array([(self.index[u], self.index[v]) for u, v in graph.edges],
+                              dtype=np.int64).reshape(-1, 2)
+        self._csr: Dict[Tuple, GraphCSR] = {}
+        self._engines: Dict[Tuple, object] = {}
+        self._edge_labels = None
+
+    @property
+    def graph(self):
+        g = self.graph_ref()
+        if g is None:
+            raise ReferenceError("the graph of this partition has been garbage collected")
+        return g
+
+    # -- flat arrays -----------------------------------------------------------------
+    def column(self, fields) -> np.ndarray:
+        """Integer node-attribute column (sum of ``fields``) in node-index order."""
+        g = self.graph
+        if isinstance(fields, str):
+            fields = (fields,)
+        col = np.zeros(self.n_nodes, dtype=np.float64)
+        for f in fields:
+            col += np.array([g.nodes[lab][f] for lab in self.labels], dtype=np.float64)
+        if not np.all(col == np.floor(col)):
+            raise TypeError(f"node attribute {fields!r} is not integer valued; the device "
+                            "engine tallies integers only")
+        return col.astype(np.int64)
+
+    def csr(self, fields, region_surcharge=None) -> GraphCSR:
+        if isinstance(fields, str):
+            fields = (fields,)
+        fields = tuple(fields)
+        rkey = tuple(region_surcharge.items()) if region_surcharge else ()
+        key = (fields, rkey)
+        csr = self._csr.get(key)
+        if csr is None:
+            base = self._csr.get((fields, ()))
+            if base is None:
+                base = csr_from_edges(self.n_nodes, self.edges, self.column(fields), node_labels=self.labels)
+                self._csr[(fields, ())] = base
+            csr = base
+            if region_surcharge:
+                g = self.graph
+                cols = []
+                for name in region_surcharge:
+                    codes: Dict = {}
+                    col = np.empty(self.n_nodes, dtype=np.int32)
+                    for i, lab in enumerate(self.labels):
+                        val = g.nodes[lab].get(name)
+                        col[i] = -1 if val is None else codes.setdefault(val, len(codes))
+                    cols.append(col)
+                csr = base.with_regions(np.stack(cols), list(region_surcharge.values()),
+                                        tuple(region_surcharge))
+                self._csr[key] = csr
+        return csr
+
+    def edge_labels(self, csr: GraphCSR):
+        """Edge id -> the tuple the reference stores in ``cut_edges``
+        (updaters/cut_edges.py:110-114: ``tuple(sorted(edge))`` over node labels)."""
+        if self._edge_labels is None:
+            out = []
+            for u, v in csr.edge_uv:
+                a, b = self.labels[u], self.labels[v]
+                try:
+                    out.append((a, b) if a <= b else (b, a))
+                except TypeError:
+                    out.append((a, b))
+            self._edge_labels = out
+        return self._edge_labels
+
+    # -- engines ---------------------------------------------------------------------
+    def engine(self, key: Tuple, fields, k: int, region_surcharge=None, **cfg_kw):
+        """One single-chain device engine per distinct (column, configuration)."""
+        full = (key, tuple(fields) if not isinstance(fields, str) else (fields,), k)
+        eng = self._engines.get(full)
+        if eng is None:
+            from .engine import Engine
+
+            csr = self.csr(fields, region_surcharge)
+            cfg_kw.setdefault("pop_target", float(csr.pop.sum()) / k)
+            cfg_kw.setdefault("epsilon", 1.0)
+            # the reference seeds everything from Python's global `random`; so does this
+            cfg_kw.setdefault("seed", random.getrandbits(64))
+            cfg = EngineConfig(n_districts=k, n_chains=1, **cfg_kw)
+            eng = Engine(csr, cfg, np.zeros(self.n_nodes, dtype=np.uint8))
+            self._engines[full] = eng
+        return eng
+
+    def scan(self, vec: np.ndarray, fields, k: int):
+        """First-time Tally + cut_edges of a plan (rc_engine_init_state):
+        returns (tally[k] int64, cut_mask words uint32, cut_count)."""
+        eng = self.engine(("scan",), fields, k)
+        eng.set_assignment(vec)
+        eng.synchronize()
+        return (eng.tally[0].cpu().numpy().copy(), eng.cut_mask[0].cpu().numpy().view(np.uint32).copy(),
+                int(eng.cut_count[0].item()))

@@ -176,16 +176,19 @@ int rc_engine_bind_state(RcEngine* e, const RcState* st) {
   return RC_OK;
 }
 
-int rc_engine_init_state(RcEngine* e, void* stream) {
+static int init_state_impl(RcEngine* e, void* stream, int keep_counters) {
   if (!e || !e->bound) return fail(RC_ERR_INVALID_ARG, "engine has no bound state");
   CUDA_OK(cudaSetDevice(e->device));
   rc::Params p = e->p;
   p.rp = RcReplay{};
+  p.keep_counters = keep_counters;
   rc::init_state_kernel<<<e->p.cfg.n_chains, 256, 0, (cudaStream_t)stream>>>(p);
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return RC_OK;
 }
+
+int rc_engine_init_state(RcEngine* e, void* stream) { return init_state_impl(e, stream, 0); }
 
 int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream) {
   if (!e || !e->bound) return fail(RC_ERR_INVALID_ARG, "engine has no bound state");
@@ -201,6 +204,35 @@ int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream) {
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(e->ev1, s));
   e->timed = true;
+  return RC_OK;
+}
+
+int rc_engine_step_host(RcEngine* e, const uint8_t* h_assignment, int64_t h_stride, int64_t n_steps,
+                        uint8_t* h_assignment_out, int64_t* h_tally_out, int32_t* h_cut_count_out,
+                        int32_t* h_status_out, void* stream) {
+  if (!e || !e->bound) return fail(RC_ERR_INVALID_ARG, "engine has no bound state");
+  if (!h_assignment) return fail(RC_ERR_INVALID_ARG, "null h_assignment");
+  const int N = e->p.g.N, n = e->p.cfg.n_chains, k = e->p.cfg.n_districts;
+  if (h_stride < N) return fail(RC_ERR_INVALID_ARG, "h_stride must be >= n_nodes");
+  CUDA_OK(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const RcState& st = e->p.st;
+  CUDA_OK(cudaMemcpy2DAsync(st.d_assignment, (size_t)st.assign_stride, h_assignment, (size_t)h_stride,
+                            (size_t)N, (size_t)n, cudaMemcpyHostToDevice, s));
+  int rc = init_state_impl(e, stream, 1);
+  if (rc) return rc;
+  rc = rc_engine_run(e, n_steps, stream);
+  if (rc) return rc;
+  if (h_assignment_out)
+    CUDA_OK(cudaMemcpy2DAsync(h_assignment_out, (size_t)h_stride, st.d_assignment, (size_t)st.assign_stride,
+                              (size_t)N, (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (h_tally_out)
+    CUDA_OK(cudaMemcpyAsync(h_tally_out, st.d_tally, sizeof(int64_t) * (size_t)n * k, cudaMemcpyDeviceToHost, s));
+  if (h_cut_count_out)
+    CUDA_OK(cudaMemcpyAsync(h_cut_count_out, st.d_cut_count, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (h_status_out)
+    CUDA_OK(cudaMemcpyAsync(h_status_out, st.d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
   return RC_OK;
 }
 

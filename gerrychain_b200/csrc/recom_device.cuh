@@ -40,6 +40,7 @@ struct Params {
   int64_t g2l_stride;
   uint32_t* badpairs; // [grid][2048] bitset of (a*256+b), pair reselection only
   int32_t* work_counter;  // persistent scheduling ticket
+  int32_t keep_counters;  // init_state_kernel: leave step/proposal numbers and counters alone
 };
 
 // ---- shared-memory carve-up -------------------------------------------------------

@@ -639,6 +639,7 @@ __device__ ProposalResult propose(const Chain& c, uint32_t prop_no, const RcRepl
     c.tally[st.a] = pop_a;  // updaters/tally.py:162-165
     c.tally[st.b] = pop_b;
     p.st.d_cut_count[c.chain] = cut_count + s.misc[M_DELTA];
+    if (p.st.d_last_pair) { p.st.d_last_pair[2 * c.chain] = st.a; p.st.d_last_pair[2 * c.chain + 1] = st.b; }
   }
   __syncthreads();
   res.accepted = 1;
@@ -736,10 +737,13 @@ __global__ void init_state_kernel(const Params p) {
   __syncthreads();
   if (tid == 0) {
     p.st.d_cut_count[chain] = cnt;
-    p.st.d_step_no[chain] = 0;
-    p.st.d_proposal_no[chain] = 0;
-    p.st.d_flags[chain] = 0;
-    for (int i = 0; i < RC_N_COUNTERS; ++i) p.st.d_counters[(size_t)chain * RC_N_COUNTERS + i] = 0;
+    if (p.st.d_last_pair) { p.st.d_last_pair[2 * chain] = -1; p.st.d_last_pair[2 * chain + 1] = -1; }
+    if (!p.keep_counters) {  // a re-upload of plans keeps the RNG position and the statistics
+      p.st.d_step_no[chain] = 0;
+      p.st.d_proposal_no[chain] = 0;
+      p.st.d_flags[chain] = 0;
+      for (int i = 0; i < RC_N_COUNTERS; ++i) p.st.d_counters[(size_t)chain * RC_N_COUNTERS + i] = 0;
+    }
   }
   if (__syncthreads_or(bad) && tid == 0) p.st.d_status[chain] = RC_ERR_INVALID_ARG;
   else if (tid == 0) p.st.d_status[chain] = RC_OK;

@@ -77,6 +77,8 @@ class Engine:
         st.d_status = self.status.data_ptr()
         st.d_flags = self.flags.data_ptr()
         st.d_counters = self.counters.data_ptr()
+        self.last_pair = torch.full((n, 2), -1, dtype=torch.int32, device=dev)
+        st.d_last_pair = self.last_pair.data_ptr()
         st.assign_stride = self.assign_stride
         st.mask_stride = self.mask_stride
         self._state = st
@@ -116,6 +118,33 @@ class Engine:
     def run(self, n_steps: int):
         """Advance every chain by ``n_steps`` accepted steps (asynchronous)."""
         _check(self.lib, self.lib.rc_engine_run(self._handle, int(n_steps), self._stream()))
+        return self
+
+    def host_buffers(self):
+        """Pinned host buffers shaped for :meth:`step_host` (assignment, tally, cut_count, status)."""
+        t = self.torch
+        n, k = self.cfg.n_chains, self.cfg.n_districts
+        return (t.empty((n, self.csr.n_nodes), dtype=t.uint8).pin_memory(),
+                t.empty((n, k), dtype=t.int64).pin_memory(),
+                t.empty(n, dtype=t.int32).pin_memory(),
+                t.empty(n, dtype=t.int32).pin_memory())
+
+    def step_host(self, h_assignment, n_steps: int, h_out=None, h_tally=None, h_cut_count=None,
+                  h_status=None):
+        """Host plans in, ``n_steps`` ReCom steps on the device, host plans / Tally /
+        len(cut_edges) / status out (``rc_engine_step_host``); synchronous.  Arguments are
+        CPU torch tensors (pinned for asynchronous copies) or C-contiguous numpy arrays."""
+        def ptr(x):
+            if x is None:
+                return None
+            return x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data
+
+        n, N = self.cfg.n_chains, self.csr.n_nodes
+        if tuple(h_assignment.shape) != (n, N):
+            raise ValueError("h_assignment must be [n_chains, N] uint8")
+        _check(self.lib, self.lib.rc_engine_step_host(
+            self._handle, ptr(h_assignment), N, int(n_steps), ptr(h_out), ptr(h_tally),
+            ptr(h_cut_count), ptr(h_status), self._stream()))
         return self
 
     def last_run_ms(self) -> float:

@@ -109,6 +109,9 @@ typedef struct RcState {
   int64_t* d_counters;     /* [n_chains][RC_N_COUNTERS] see below                     */
   int64_t assign_stride;   /* bytes between chains in d_assignment (multiple of 16)   */
   int64_t mask_stride;     /* uint32 words between chains in d_cut_mask (multiple of 4) */
+  int32_t* d_last_pair;    /* [n_chains][2] optional (may be NULL): the district pair (a < b)
+                              merged by the chain's last committed proposal, i.e. the keys of
+                              its `flips` (tree.py:947-950); {-1,-1} before the first one   */
 } RcState;
 
 enum {
@@ -173,6 +176,20 @@ int rc_engine_init_state(RcEngine* e, void* stream);
  * (chain.py:185-195) with proposal = recom (proposals/tree_proposals.py:36-146),
  * constraints = population Bounds, accept = always_accept (accept.py:15). */
 int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream);
+
+/* The same call with HOST buffers: the whole reference-facing round trip of a batch of
+ * chains.  Copies h_assignment ([n_chains][h_stride] bytes, district index per node, only
+ * the first N bytes of a row are read) to the device, recomputes Tally / cut_edges
+ * (rc_engine_init_state), advances every chain by n_steps accepted steps (rc_engine_run)
+ * and copies back: the assignment (same layout, may alias h_assignment), Tally
+ * [n_chains][k] int64, len(cut_edges) [n_chains] int32 and the per-chain status
+ * [n_chains] int32 (any of the outputs may be NULL).  Host buffers should be pinned
+ * (cudaHostAlloc / torch pin_memory) for the copies to be asynchronous.  Synchronises
+ * `stream` before returning.  This is what one MarkovChain batch costs a caller who keeps
+ * its partitions on the host, as the reference does (chain.py:166-196). */
+int rc_engine_step_host(RcEngine* e, const uint8_t* h_assignment, int64_t h_stride,
+                        int64_t n_steps, uint8_t* h_assignment_out, int64_t* h_tally_out,
+                        int32_t* h_cut_count_out, int32_t* h_status_out, void* stream);
 
 /* TEST HOOK: apply recorded reference steps to one chain (device pointers inside). */
 int rc_engine_replay(RcEngine* e, const RcReplay* d_replay_host_struct, void* stream);

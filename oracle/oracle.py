@@ -109,6 +109,8 @@ class OracleChains:
         st.d_status = self.status.ctypes.data
         st.d_flags = self.flags.ctypes.data
         st.d_counters = self.counters.ctypes.data
+        self.last_pair = np.full((n, 2), -1, dtype=np.int32)
+        st.d_last_pair = self.last_pair.ctypes.data
         st.assign_stride = self.assign_stride
         st.mask_stride = self.mask_stride
         self.state = st

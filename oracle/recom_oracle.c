@@ -529,7 +529,7 @@ static int rco_propose(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t
                        uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
                        uint32_t prop_no, int64_t* counters, uint32_t* flags,
                        const RcReplay* rp, const RcReplayStep* rs, int32_t* info,
-                       int* accepted) {
+                       int* accepted, int32_t* last_pair) {
   int k = c->n_districts, words = (g->n_edges + 31) / 32;
   *accepted = 0;
   if (*cut_count <= 0) return RC_ERR_NO_CUT_EDGES;
@@ -583,6 +583,7 @@ static int rco_propose(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t
     }
     *cut_count += delta;
     *accepted = 1;
+    if (last_pair) { last_pair[0] = a; last_pair[1] = b; }
   } else {
     counters[RC_CTR_INVALID]++;
   }
@@ -593,13 +594,13 @@ static int rco_propose(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t
 /* chain.py:185-195: propose until a valid state, accept (always), count the step. */
 int rco_step(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t global_chain,
              uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
-             uint32_t* proposal_no, int64_t* counters, uint32_t* flags) {
+             uint32_t* proposal_no, int64_t* counters, uint32_t* flags, int32_t* last_pair) {
   int streak_cap = c->max_invalid_streak > 0 ? c->max_invalid_streak : 1000;
   for (int streak = 0; streak < streak_cap; ++streak) {
     int accepted = 0;
     uint32_t p = (*proposal_no)++;
     int rc = rco_propose(g, c, w, global_chain, assign, tally, mask, cut_count, p, counters,
-                         flags, NULL, NULL, NULL, &accepted);
+                         flags, NULL, NULL, NULL, &accepted, last_pair);
     if (rc) return rc;
     if (accepted) return RC_OK;
   }
@@ -613,7 +614,7 @@ int rco_replay(const RcGraph* g, const RcConfig* c, RcoWork* w, const RcReplay* 
     int accepted = 0;
     int32_t info[4] = {0, 0, 0, 0};
     int rc = rco_propose(g, c, w, 0, assign, tally, mask, cut_count, (uint32_t)s, counters,
-                         flags, rp, &rp->steps[s], info, &accepted);
+                         flags, rp, &rp->steps[s], info, &accepted, NULL);
     info[2] = *cut_count; info[3] = rc ? rc : (accepted ? RC_OK : RC_ERR_INVALID_STREAK);
     if (rp->info_trace) memcpy(rp->info_trace + 4 * s, info, sizeof info);
     if (rp->assign_trace) memcpy(rp->assign_trace + (size_t)s * g->n_nodes, assign, (size_t)g->n_nodes);
@@ -676,7 +677,7 @@ typedef struct {
   const RcGraph* g; const RcConfig* c; int64_t n_steps;
   uint8_t* assign; int64_t assign_stride; int64_t* tally; uint32_t* mask; int64_t mask_stride;
   int32_t* cut_count; uint32_t* proposal_no; int32_t* status; uint32_t* flags; int64_t* counters;
-  int64_t* step_no;
+  int64_t* step_no; int32_t* last_pair;
   int n_chains; volatile int next; pthread_mutex_t mu;
 } RcoJob;
 
@@ -693,7 +694,8 @@ static void* rco_worker(void* arg) {
       int rc = rco_step(j->g, j->c, w, (uint32_t)(ch + j->c->chain_offset),
                         j->assign + ch * j->assign_stride, j->tally + (int64_t)ch * j->c->n_districts,
                         j->mask + ch * j->mask_stride, &j->cut_count[ch], &j->proposal_no[ch],
-                        j->counters + (int64_t)ch * RC_N_COUNTERS, &j->flags[ch]);
+                        j->counters + (int64_t)ch * RC_N_COUNTERS, &j->flags[ch],
+                        j->last_pair ? j->last_pair + 2 * ch : NULL);
       if (rc) { j->status[ch] = rc; break; }
       j->step_no[ch]++;
     }
@@ -711,6 +713,7 @@ int rco_run_chains(const RcGraph* g, const RcConfig* c, int64_t n_steps, const R
   j.tally = st->d_tally; j.mask = st->d_cut_mask; j.mask_stride = st->mask_stride;
   j.cut_count = st->d_cut_count; j.proposal_no = st->d_proposal_no; j.status = st->d_status;
   j.flags = st->d_flags; j.counters = st->d_counters; j.step_no = st->d_step_no;
+  j.last_pair = st->d_last_pair;
   j.n_chains = c->n_chains; j.next = 0;
   pthread_mutex_init(&j.mu, NULL);
   if (n_threads < 1) n_threads = 1;
@@ -731,6 +734,7 @@ int rco_init_chains(const RcGraph* g, const RcConfig* c, const RcState* st) {
     if (rc) return rc;
     st->d_step_no[ch] = 0; st->d_proposal_no[ch] = 0; st->d_status[ch] = RC_OK;
     st->d_flags[ch] = 0;
+    if (st->d_last_pair) { st->d_last_pair[2 * ch] = -1; st->d_last_pair[2 * ch + 1] = -1; }
     memset(st->d_counters + (int64_t)ch * RC_N_COUNTERS, 0, RC_N_COUNTERS * 8);
   }
   return RC_OK;

@@ -22,7 +22,7 @@ int rco_init_state(const RcGraph* g, const RcConfig* c, const uint8_t* assign,
                    int64_t* tally, uint32_t* mask, int32_t* cut_count);
 int rco_step(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t global_chain,
              uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
-             uint32_t* proposal_no, int64_t* counters, uint32_t* flags);
+             uint32_t* proposal_no, int64_t* counters, uint32_t* flags, int32_t* last_pair);
 int rco_replay(const RcGraph* g, const RcConfig* c, RcoWork* w, const RcReplay* rp,
                uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
                int64_t* counters, uint32_t* flags);

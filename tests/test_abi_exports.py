@@ -25,7 +25,7 @@ def test_library_exports_header_symbols():
 def test_struct_sizes_match_header():
     assert ctypes.sizeof(_abi.RcReplayStep) == 24
     assert ctypes.sizeof(_abi.RcGraph) == 8 + 5 * 8 + 8 + 2 * 8
-    assert ctypes.sizeof(_abi.RcState) == 9 * 8 + 16
+    assert ctypes.sizeof(_abi.RcState) == 9 * 8 + 16 + 8
 
 
 def test_create_rejects_bad_arguments_without_gpu():
