@@ -127,6 +127,7 @@ class RcReplay(C.Structure):
         ("chain", C.c_int32),
         ("steps", C.c_void_p),
         ("weights", C.c_void_p),
+        ("weight_rank", C.c_void_p),
         ("wilson_root", C.c_void_p),
         ("stack_ptr", C.c_void_p),
         ("stack_val", C.c_void_p),

@@ -107,21 +107,31 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   p.g.N = N; p.g.E = E; p.g.R = R;
   p.g.row_ptr = e->d_row_ptr; p.g.col_idx = e->d_col_idx; p.g.slot_edge = e->d_slot_edge;
   p.g.edge_uv = e->d_edge_uv; p.g.pop = e->d_pop; p.g.region_ids = e->d_region;
-  for (int r = 0; r < R; ++r) p.g.surcharge[r] = g->surcharges[r];
+  uint64_t sfix_total = 0;
+  for (int r = 0; r < R; ++r) {
+    if (!(g->surcharges[r] >= 0.0) || g->surcharges[r] > 1e6) {
+      rc_engine_destroy(e);
+      return fail(RC_ERR_INVALID_ARG, "region surcharges must be in [0, 1e6]");
+    }
+    p.g.surcharge[r] = g->surcharges[r];
+    p.g.sfix[r] = rc_surcharge_fix(g->surcharges[r]);
+    sfix_total += p.g.sfix[r];
+  }
+  p.g.smult = rc_key_mult(sfix_total, R);
   p.cfg = *cfg;
   // caps: merged pair of two districts, with head-room (RC_ERR_CAPACITY if exceeded)
   const int k = cfg->n_districts;
-  int cap_nodes = cfg->cap_nodes > 0 ? cfg->cap_nodes : (int)(2.6 * N / k) + 32;
+  int cap_nodes = cfg->cap_nodes > 0 ? cfg->cap_nodes : (int)(2.4 * N / k) + 32;
   if (cap_nodes > N) cap_nodes = N;
   if (cap_nodes > rc::kMaxLocal) cap_nodes = rc::kMaxLocal;
   int cap_edges = cfg->cap_edges > 0 ? cfg->cap_edges
-                                     : (int)(1.15 * cap_nodes * ((double)E / N)) + 64;
+                                     : (int)(1.1 * cap_nodes * ((double)E / N)) + 64;
   if (cap_edges > E) cap_edges = E;
   if (cap_edges > 65535) cap_edges = 65535;
   cap_nodes = (cap_nodes + 7) & ~7;
   cap_edges = (cap_edges + 31) & ~31;
   p.cap_nodes = cap_nodes; p.cap_edges = cap_edges;
-  e->smem = rc::smem_layout(nullptr, nullptr, cap_nodes, cap_edges);
+  e->smem = rc::smem_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R);
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
   e->n_sms = prop.multiProcessorCount;
@@ -131,24 +141,20 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
                 cap_nodes, cap_edges, e->smem, (size_t)prop.sharedMemPerBlockOptin);
   }
   CUDA_OK(cudaFuncSetAttribute(rc::recom_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  e->threads = cfg->threads_per_cta > 0 ? cfg->threads_per_cta : 256;
+  e->threads = cfg->threads_per_cta > 0 ? cfg->threads_per_cta : 512;
   if (e->threads > 512) e->threads = 512;
   e->threads = (e->threads + 31) & ~31;
   CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->ctas_per_sm, rc::recom_step_kernel, e->threads, e->smem));
   if (e->ctas_per_sm < 1) { rc_engine_destroy(e); return fail(RC_ERR_CAPACITY, "kernel does not fit an SM"); }
   e->grid = cfg->n_chains;  // one CTA per chain; the hardware scheduler refills SMs
   // scratch
-  const int64_t n16 = ((int64_t)N + 15) / 16 * 16;
-  p.g2l_stride = n16;
-  size_t b_g2l = (size_t)e->grid * n16 * sizeof(uint16_t);
   size_t b_nodes = (size_t)e->grid * cap_nodes * sizeof(int32_t);
   size_t b_eids = (size_t)e->grid * cap_edges * sizeof(int32_t);
   size_t b_bad = cfg->allow_pair_reselection ? (size_t)e->grid * 2048 * sizeof(uint32_t) : 0;
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-  e->scratch_bytes = al(b_g2l) + al(b_nodes) + al(b_eids) + al(b_bad) + 256;
+  e->scratch_bytes = al(b_nodes) + al(b_eids) + al(b_bad) + 256;
   CUDA_OK(cudaMalloc(&e->d_scratch, e->scratch_bytes));
   char* base = (char*)e->d_scratch;
-  p.g2l = (uint16_t*)base; base += al(b_g2l);
   p.nodes = (int32_t*)base; base += al(b_nodes);
   p.eids = (int32_t*)base; base += al(b_eids);
   p.badpairs = b_bad ? (uint32_t*)base : nullptr; base += al(b_bad);
@@ -240,7 +246,7 @@ int rc_engine_replay(RcEngine* e, const RcReplay* rp, void* stream) {
   if (!e || !e->bound || !rp) return fail(RC_ERR_INVALID_ARG, "engine has no bound state / null replay");
   if (rp->n_steps <= 0 || !rp->steps) return fail(RC_ERR_INVALID_ARG, "empty replay");
   if (rp->chain < 0 || rp->chain >= e->p.cfg.n_chains) return fail(RC_ERR_INVALID_ARG, "bad chain index");
-  if (e->p.cfg.tree_kind == RC_TREE_MST && !rp->weights) return fail(RC_ERR_INVALID_ARG, "MST replay needs weights");
+  if (e->p.cfg.tree_kind == RC_TREE_MST && !rp->weight_rank) return fail(RC_ERR_INVALID_ARG, "MST replay needs weight_rank");
   CUDA_OK(cudaSetDevice(e->device));
   rc::Params p = e->p;
   p.rp = *rp;

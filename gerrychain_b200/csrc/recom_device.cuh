@@ -14,6 +14,7 @@ namespace rc {
 
 typedef uint16_t lid_t;  // local node / arc / edge-slot id inside one merged pair
 constexpr int kMaxLocal = 32760;  // 2*(n-1) arcs must fit 16 bits
+constexpr int kMaxThreads = 1024;
 
 struct DevGraph {
   int32_t N, E, R;
@@ -23,7 +24,9 @@ struct DevGraph {
   const int32_t* edge_uv;
   const int32_t* pop;
   const int32_t* region_ids;  // [R][N]
-  double surcharge[8];
+  double surcharge[8];        // region_surcharge values
+  uint64_t sfix[8];           // rc_surcharge_fix(surcharge[r])
+  uint64_t smult;             // rc_key_mult(sum sfix, R); 0 when R == 0
 };
 
 struct Params {
@@ -34,10 +37,8 @@ struct Params {
   int64_t n_steps;    // free-running: accepted steps per chain for this launch
   int32_t cap_nodes, cap_edges;
   // per-CTA global scratch (L2 resident)
-  uint16_t* g2l;      // [grid][N16]
-  int32_t* nodes;     // [grid][cap_nodes]
-  int32_t* eids;      // [grid][cap_edges]
-  int64_t g2l_stride;
+  int32_t* nodes;     // [grid][cap_nodes] local -> global node
+  int32_t* eids;      // [grid][cap_edges] local edge -> global edge id
   uint32_t* badpairs; // [grid][2048] bitset of (a*256+b), pair reselection only
   int32_t* work_counter;  // persistent scheduling ticket
   int32_t keep_counters;  // init_state_kernel: leave step/proposal numbers and counters alone
@@ -45,73 +46,85 @@ struct Params {
 
 // ---- shared-memory carve-up -------------------------------------------------------
 struct Smem {
+  int32_t* misc;     // [128]
   // whole step
+  uint32_t* mbits;   // [NW] membership bitmap of the merged pair over global node ids
+  lid_t* mpref;      // [NW] exclusive prefix popcount: local id = mpref[w] + popc(below)
   int32_t* pop;      // [CN]
   lid_t* eu;         // [CE]
   lid_t* ev;         // [CE]
-  lid_t* te;         // [CN] local edge index of tree edge t (ascending)
+  uint32_t* tflag;   // [CE/32] tree-edge bitmap over local edges
+  uint8_t* ecls;     // [CE] bitmask of region columns the edge crosses (R > 0 only)
   // spanning-tree phase
-  uint32_t* khi;     // [CE] high word of the 64-bit weight key
-  lid_t* comp;       // [CN]
-  lid_t* par;        // [CN]
-  uint32_t* best_hi; // [CN]
-  unsigned long long* best_lo;  // [CN] (low word << 32 | local edge)
-  uint32_t* tflag;   // [CE/32]
+  uint32_t* key;     // [CE] 32-bit weight key of local edge j
+  uint32_t* lab;     // [CE] live edge list: endpoints as current component ids (a | b << 16)
+  lid_t* lj;         // [CE] live edge list: local edge index
+  uint32_t* best;    // [CN] minimum key over the live edges of a component
+  uint32_t* bpos;    // [CN] (local edge << 16 | live-list position) of that minimum
+  lid_t* hook;       // [CN] component merge forest
   // Euler-tour phase (aliases the spanning-tree phase)
-  int32_t* toff;     // [CN+1]
-  int32_t* cur;      // [CN]
+  lid_t* te;         // [CN] local edge index of tree edge t (ascending)
+  lid_t* toff;       // [CN+1]
+  int32_t* cur;      // [CN] fill cursor; later population below tree edge t
   lid_t* tadj;       // [2CN] arcs leaving each node
   lid_t* apos;       // [2CN] slot of arc a in tadj; later: tour position of arc a
   uint32_t* lrA;     // [2CN] (next << 16 | dist)
   uint32_t* lrB;     // [2CN] ; later the prefix-sum array
-  lid_t* ent;        // [CN] tour position of the arc entering the node
-  // small
-  int32_t* misc;     // [128]
+  lid_t* ent;        // [CN] tour position of the arc entering the node (aliases tadj)
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
-__host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int CN, int CE) {
+// N: nodes of the whole graph, CN/CE: caps of a merged pair, R: region columns
+__host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int N, int CN, int CE, int R) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return r; };
+  const int NW = (N + 31) / 32;
   size_t o_misc = take(128 * 4);
+  size_t o_mbits = take(size_t(NW) * 4);
+  size_t o_mpref = take(size_t(NW) * 2);
   size_t o_pop = take(size_t(CN) * 4);
   size_t o_eu = take(size_t(CE) * 2);
   size_t o_ev = take(size_t(CE) * 2);
-  size_t o_te = take(size_t(CN) * 2);
+  size_t o_tfl = take(size_t((CE + 31) / 32) * 4);
+  size_t o_ecls = take(R > 0 ? size_t(CE) : 0);
   size_t phase = o;
   // spanning-tree phase
-  size_t o_khi = take(size_t(CE) * 4);
-  size_t o_comp = take(size_t(CN) * 2);
-  size_t o_par = take(size_t(CN) * 2);
-  size_t o_bhi = take(size_t(CN) * 4);
-  size_t o_blo = take(size_t(CN) * 8);
-  size_t o_tfl = take(size_t((CE + 31) / 32) * 4);
+  size_t o_key = take(size_t(CE) * 4);
+  size_t o_lab = take(size_t(CE) * 4);
+  size_t o_lj = take(size_t(CE) * 2);
+  size_t o_best = take(size_t(CN) * 4);
+  size_t o_bpos = take(size_t(CN) * 4);
+  size_t o_hook = take(size_t(CN) * 2);
   size_t end_a = o;
-  // Euler phase; tflag must survive until te[] is built, so the Euler arrays that are
-  // written before that point (none) may overlap it freely: te is built first.
+  // Euler phase
   o = phase;
-  size_t o_toff = take(size_t(CN + 1) * 4);
+  size_t o_te = take(size_t(CN) * 2);
+  size_t o_toff = take(size_t(CN + 1) * 2);
   size_t o_cur = take(size_t(CN) * 4);
   size_t o_tadj = take(size_t(2 * CN) * 2);
   size_t o_apos = take(size_t(2 * CN) * 2);
   size_t o_lrA = take(size_t(2 * CN) * 4);
   size_t o_lrB = take(size_t(2 * CN) * 4);
-  size_t o_ent = take(size_t(CN) * 2);
+  size_t o_ent = o_tadj;  // tadj is dead once the tour successors exist
   size_t end_b = o;
   if (s) {
     s->misc = (int32_t*)(base + o_misc);
+    s->mbits = (uint32_t*)(base + o_mbits);
+    s->mpref = (lid_t*)(base + o_mpref);
     s->pop = (int32_t*)(base + o_pop);
     s->eu = (lid_t*)(base + o_eu);
     s->ev = (lid_t*)(base + o_ev);
-    s->te = (lid_t*)(base + o_te);
-    s->khi = (uint32_t*)(base + o_khi);
-    s->comp = (lid_t*)(base + o_comp);
-    s->par = (lid_t*)(base + o_par);
-    s->best_hi = (uint32_t*)(base + o_bhi);
-    s->best_lo = (unsigned long long*)(base + o_blo);
     s->tflag = (uint32_t*)(base + o_tfl);
-    s->toff = (int32_t*)(base + o_toff);
+    s->ecls = (uint8_t*)(base + o_ecls);
+    s->key = (uint32_t*)(base + o_key);
+    s->lab = (uint32_t*)(base + o_lab);
+    s->lj = (lid_t*)(base + o_lj);
+    s->best = (uint32_t*)(base + o_best);
+    s->bpos = (uint32_t*)(base + o_bpos);
+    s->hook = (lid_t*)(base + o_hook);
+    s->te = (lid_t*)(base + o_te);
+    s->toff = (lid_t*)(base + o_toff);
     s->cur = (int32_t*)(base + o_cur);
     s->tadj = (lid_t*)(base + o_tadj);
     s->apos = (lid_t*)(base + o_apos);
@@ -123,52 +136,51 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
 }
 
 // misc[] slots
-enum { M_WSUM = 0 /* 0..32: warp sums + total */, M_A = 40, M_B, M_N, M_M, M_ERR, M_PICK,
-       M_FLAG, M_CNT, M_TOT, M_ROOT, M_NCOMP, M_SUBSET, M_DELTA, M_TSTAR,
-       M_BEST64 = 64 /* 64..65, 8-byte aligned */, M_CTR = 72 /* 72..79 counters */ };
+enum { M_WSUM = 0 /* 0..63: two alternating banks of 32 warp sums */,
+       M_ERR = 65, M_PICK, M_CNT, M_TOT, M_NINT, M_SUBSET, M_DELTA, M_TSTAR, M_NLIVE, M_NBAL,
+       M_BEST64 = 80 /* 80..81, 8-byte aligned */, M_CTR = 88 /* 88..95 counters */ };
 
 #ifdef __CUDACC__
 
-// Exclusive block scan of one int per thread; *total = block sum.  3 barriers.
-__device__ __forceinline__ int block_excl_scan(int v, int* total, int32_t* misc) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int inc = v;
+__device__ __forceinline__ int warp_incl_scan(int v) {
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    int n = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += n;
+    int n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += n;
   }
-  if (lane == 31) misc[M_WSUM + w] = inc;
-  __syncthreads();
-  if (w == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-    int s = lane < nw ? misc[M_WSUM + lane] : 0, si = s;
+  return v;
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int n = __shfl_up_sync(0xffffffffu, si, o);
-      if (lane >= o) si += n;
-    }
-    misc[M_WSUM + lane] = si - s;
-    if (lane == 31) misc[M_WSUM + 32] = si;
-  }
-  __syncthreads();
-  int res = misc[M_WSUM + w] + inc - v;
-  *total = misc[M_WSUM + 32];
-  __syncthreads();
-  return res;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
-__device__ __forceinline__ unsigned long long dbl_key(double w) {
-  return (unsigned long long)__double_as_longlong(w);  // w >= 0: order preserving
+// Exclusive block scan of one int per thread; *total = block sum.  ONE barrier: the warp
+// totals go to one of two alternating banks, so a slow reader of call k is never
+// overtaken by the writers of call k+2 (they are separated by the barrier of call k+1).
+// `parity` is a per-thread register that every thread toggles in lock step.
+__device__ __forceinline__ int block_excl_scan(int v, int* total, int32_t* misc, int& parity) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+  int32_t* bank = misc + M_WSUM + 32 * parity;
+  parity ^= 1;
+  const int inc = warp_incl_scan(v);
+  if (lane == 31) bank[w] = inc;
+  __syncthreads();
+  const int ws = lane < nw ? bank[lane] : 0;
+  const int wi = warp_incl_scan(ws);
+  const int wbase = __shfl_sync(0xffffffffu, wi - ws, w);
+  *total = __shfl_sync(0xffffffffu, wi, 31);
+  return wbase + inc - v;
 }
 
-__device__ __forceinline__ void atomic_min_u64_smem(unsigned long long* a, unsigned long long v) {
-  unsigned long long old = *a;
-  while (v < old) {
-    unsigned long long seen = atomicCAS(a, old, v);
-    if (seen == old) break;
-    old = seen;
-  }
+// odd chunk length for thread-contiguous loops: stride-odd shared-memory accesses are
+// bank-conflict free
+__device__ __forceinline__ int odd_chunk(int count) {
+  return ((count + (int)blockDim.x - 1) / (int)blockDim.x) | 1;
 }
 
 __device__ __forceinline__ void atomic_max_u64_smem(unsigned long long* a, unsigned long long v) {

@@ -29,142 +29,165 @@ struct Chain {
   uint8_t* assign;
   uint32_t* mask;
   int64_t* tally;
-  uint16_t* g2l;
   int32_t* nodes;
   int32_t* eids;
+  int par;              // block_excl_scan bank parity (toggled in lock step by all threads)
 };
 
-__device__ __forceinline__ bool in_pair(uint8_t x, int a, int b) { return x == a || x == b; }
+// ---- membership of a global node in the merged pair, and its local id ---------------------
+__device__ __forceinline__ bool is_member(const Smem& s, int g) { return (s.mbits[g >> 5] >> (g & 31)) & 1u; }
+__device__ __forceinline__ int local_id(const Smem& s, int g) {
+  return (int)s.mpref[g >> 5] + __popc(s.mbits[g >> 5] & ((1u << (g & 31)) - 1u));
+}
 
-// ---- weight key of local edge j for tree `tree_no` (tree.py:78-89) ---------------------
-__device__ __forceinline__ unsigned long long edge_key(const Chain& c, int j, uint32_t tree_no,
-                                                       uint32_t prop_no, const double* rweights) {
+// 4 assignment bytes -> 4 bits (byte k == a or == b)
+__device__ __forceinline__ uint32_t match4(uint32_t x, uint32_t a4, uint32_t b4) {
+  const uint32_t r = __vcmpeq4(x, a4) | __vcmpeq4(x, b4);
+  return ((((r >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
+}
+
+__device__ __forceinline__ uint32_t match16(const uint4 q, uint32_t a4, uint32_t b4) {
+  return match4(q.x, a4, b4) | match4(q.y, a4, b4) << 4 | match4(q.z, a4, b4) << 8 | match4(q.w, a4, b4) << 12;
+}
+
+// ---- weight key of local edge j for tree `tree_no` (tree.py:78-89) ------------------------
+__device__ __forceinline__ uint32_t finish_key(const Chain& c, int j, uint32_t raw) {
   const Params& p = *c.p;
-  const int eid = c.eids[j];
-  if (rweights) return dbl_key(rweights[eid]);
-  double w = rc_edge_unit_weight(p.cfg.seed, c.gchain, (uint32_t)eid, tree_no, prop_no);
-  if (p.g.R > 0) {
-    const int u = p.g.edge_uv[2 * eid], v = p.g.edge_uv[2 * eid + 1];
-    for (int r = 0; r < p.g.R; ++r) {
-      const int ru = p.g.region_ids[(size_t)r * p.g.N + u];
-      const int rv = p.g.region_ids[(size_t)r * p.g.N + v];
-      if (ru != rv || ru < 0 || rv < 0) w = __dadd_rn(w, p.g.surcharge[r]);
-    }
-  }
-  return dbl_key(w);
+  if (p.g.smult == 0) return raw;
+  uint64_t add = 0;
+  const uint32_t cls = c.s.ecls[j];
+  for (int r = 0; r < p.g.R; ++r)
+    if ((cls >> r) & 1u) add += p.g.sfix[r];
+  return rc_key_finish(raw, add, p.g.smult);
+}
+
+__device__ __forceinline__ uint32_t edge_key(const Chain& c, int j, uint32_t tree_no, uint32_t prop_no,
+                                             const uint32_t* rrank) {
+  const Params& p = *c.p;
+  if (rrank) return rrank[c.eids[j]];
+  return finish_key(c, j, rc_edge_raw(p.cfg.seed, c.gchain, (uint32_t)j, tree_no, prop_no));
 }
 
 // ---- P0: pick the cut edge (uniform over cut EDGES, tree_proposals.py:106) --------------
 // returns edge id (block uniform) or -1
-__device__ int pick_cut_edge(const Chain& c, int cut_count, uint32_t prop_no, uint32_t retry) {
+__device__ int pick_cut_edge(Chain& c, int cut_count, uint32_t prop_no, uint32_t retry) {
   const Params& p = *c.p;
-  const int tid = threadIdx.x, T = blockDim.x;
+  const int tid = threadIdx.x;
   RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_PAIR, retry, 0, prop_no, 0);
   const int kth = (int)rc_below(r.v[0], r.v[1], (uint32_t)cut_count);
   const int words = (p.g.E + 31) >> 5;
-  const int per = (words + T - 1) / T;
+  const int per = odd_chunk(words);
   const int lo = min(tid * per, words), hi = min(lo + per, words);
   int cnt = 0;
   for (int i = lo; i < hi; ++i) cnt += __popc(__ldcg(c.mask + i));
-  int tot;
-  const int excl = block_excl_scan(cnt, &tot, c.s.misc);
   if (tid == 0) c.s.misc[M_PICK] = -1;
-  __syncthreads();
+  int tot;
+  const int excl = block_excl_scan(cnt, &tot, c.s.misc, c.par);
   if (kth >= excl && kth < excl + cnt) {
     int k = kth - excl;
     for (int i = lo; i < hi; ++i) {
-      uint32_t x = __ldcg(c.mask + i);
+      const uint32_t x = __ldcg(c.mask + i);
       const int pc = __popc(x);
       if (k < pc) {
-        while (k--) x &= x - 1;
-        c.s.misc[M_PICK] = i * 32 + (__ffs(x) - 1);
+        c.s.misc[M_PICK] = i * 32 + (int)__fns(x, 0, k + 1);
         break;
       }
       k -= pc;
     }
   }
   __syncthreads();
-  return c.s.misc[M_PICK];
+  const int e = c.s.misc[M_PICK];
+  __syncthreads();
+  return e;
 }
 
 // ---- P1: gather the merged pair into shared memory ---------------------------------------
 // returns RC_OK / RC_ERR_CAPACITY (block uniform)
-__device__ int gather_pair(const Chain& c, Step& st, int* d_sub_out) {
+__device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
   const Params& p = *c.p;
   const Smem& s = c.s;
   const int tid = threadIdx.x, T = blockDim.x;
-  const int a = st.a, b = st.b;
-  const int N = p.g.N;
-  const int tiles = (N + 15) >> 4;
+  const int N = p.g.N, NW = (N + 31) >> 5;
+  const uint32_t a4 = 0x01010101u * (uint32_t)st.a, b4 = 0x01010101u * (uint32_t)st.b;
   if (tid == 0) { s.misc[M_TOT] = 0; s.misc[M_CNT] = 0; }
-  __syncthreads();
-  int nbase = 0, popsum = 0, slots = 0;
-  for (int t0 = 0; t0 < tiles; t0 += T) {
-    const int tile = t0 + tid;
-    uint32_t fm = 0;
-    if (tile < tiles) {
-      const uint4 q = __ldcg(reinterpret_cast<const uint4*>(c.assign) + tile);
-      const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const uint32_t x = (wv[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-        if ((int)x == a || (int)x == b) fm |= 1u << k;
-      }
-      const int rem = N - tile * 16;
-      if (rem < 16) fm &= (1u << rem) - 1u;
+  // pass 1: membership bitmap + exclusive popcount prefix, T words (32 nodes each) per sweep
+  int n = 0;
+  for (int w0 = 0; w0 < NW; w0 += T) {
+    const int w = w0 + tid;
+    uint32_t bits = 0;
+    if (w < NW) {
+      const uint4* src = reinterpret_cast<const uint4*>(c.assign + (size_t)w * 32);
+      bits = match16(__ldcg(src), a4, b4);
+      if (w * 32 + 16 < N) bits |= match16(__ldcg(src + 1), a4, b4) << 16;
+      const int rem = N - w * 32;
+      if (rem < 32) bits &= (1u << rem) - 1u;
+      s.mbits[w] = bits;
     }
     int tot;
-    int local = nbase + block_excl_scan(__popc(fm), &tot, s.misc);
-    while (fm) {
-      const int k = __ffs(fm) - 1;
-      fm &= fm - 1;
-      const int g = tile * 16 + k;
-      if (local < p.cap_nodes) {
-        c.nodes[local] = g;
-        c.g2l[g] = (uint16_t)local;
-        const int pg = p.g.pop[g];
-        s.pop[local] = pg;
-        popsum += pg;
-        slots += p.g.row_ptr[g + 1] - p.g.row_ptr[g];
-      }
-      ++local;
-    }
-    nbase += tot;
+    const int ex = block_excl_scan(__popc(bits), &tot, s.misc, c.par);
+    if (w < NW) s.mpref[w] = (lid_t)min(n + ex, 0xffff);
+    n += tot;
   }
-  atomicAdd(&s.misc[M_TOT], popsum);
-  atomicAdd(&s.misc[M_CNT], slots);
-  __syncthreads();  // nodes[], g2l[] (global) and pop[] visible to the block
-  st.n = nbase;
+  st.n = n;
+  __syncthreads();
+  if (n > p.cap_nodes || n > kMaxLocal) return RC_ERR_CAPACITY;
+  // pass 2: local id -> global node, population, degree sum
+  int popsum = 0, slots = 0;
+  for (int i = tid; i < n; i += T) {
+    int lo = 0, hi = NW;  // first word whose prefix exceeds i
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((int)s.mpref[mid] > i) hi = mid; else lo = mid + 1;
+    }
+    const int w = lo - 1;
+    const int g = w * 32 + (int)__fns(s.mbits[w], 0, i - (int)s.mpref[w] + 1);
+    c.nodes[i] = g;
+    const int pg = __ldg(p.g.pop + g);
+    s.pop[i] = pg;
+    popsum += pg;
+    slots += __ldg(p.g.row_ptr + g + 1) - __ldg(p.g.row_ptr + g);
+  }
+  popsum = warp_sum(popsum);
+  slots = warp_sum(slots);
+  if ((tid & 31) == 0) { atomicAdd(&s.misc[M_TOT], popsum); atomicAdd(&s.misc[M_CNT], slots); }
+  __syncthreads();  // nodes[] (global) visible to the block; totals complete
   st.tot = s.misc[M_TOT];
   *d_sub_out = s.misc[M_CNT];
-  if (st.n > p.cap_nodes || st.n > kMaxLocal) return RC_ERR_CAPACITY;
   // edges: each thread owns a contiguous run of local nodes so that edges come out in
   // ascending (u, v) == ascending edge id.
-  const int n = st.n;
-  const int per = (n + T - 1) / T;
+  const int per = odd_chunk(n);
   const int lo = min(tid * per, n), hi = min(lo + per, n);
   int cnt = 0;
   for (int i = lo; i < hi; ++i) {
     const int g = c.nodes[i];
-    const int r1 = p.g.row_ptr[g + 1];
-    for (int sl = p.g.row_ptr[g]; sl < r1; ++sl) {
-      const int h = p.g.col_idx[sl];
-      if (h > g && in_pair(c.assign[h], a, b)) ++cnt;
+    const int r1 = __ldg(p.g.row_ptr + g + 1);
+    for (int sl = __ldg(p.g.row_ptr + g); sl < r1; ++sl) {
+      const int h = __ldg(p.g.col_idx + sl);
+      if (h > g && is_member(s, h)) ++cnt;
     }
   }
   int m;
-  int j = block_excl_scan(cnt, &m, s.misc);
+  int j = block_excl_scan(cnt, &m, s.misc, c.par);
   st.m = m;
-  if (m > p.cap_edges || m > 65535) return RC_ERR_CAPACITY;
+  if (m > p.cap_edges || m > 65535) { __syncthreads(); return RC_ERR_CAPACITY; }
+  const int R = p.g.R;
   for (int i = lo; i < hi; ++i) {
     const int g = c.nodes[i];
-    const int r1 = p.g.row_ptr[g + 1];
-    for (int sl = p.g.row_ptr[g]; sl < r1; ++sl) {
-      const int h = p.g.col_idx[sl];
-      if (h > g && in_pair(c.assign[h], a, b)) {
+    const int r1 = __ldg(p.g.row_ptr + g + 1);
+    for (int sl = __ldg(p.g.row_ptr + g); sl < r1; ++sl) {
+      const int h = __ldg(p.g.col_idx + sl);
+      if (h > g && is_member(s, h)) {
         s.eu[j] = (lid_t)i;
-        s.ev[j] = (lid_t)c.g2l[h];
-        c.eids[j] = p.g.slot_edge[sl];
+        s.ev[j] = (lid_t)local_id(s, h);
+        c.eids[j] = __ldg(p.g.slot_edge + sl);
+        if (R > 0) {  // tree.py:80-87: surcharged when the labels differ or either is None
+          uint32_t cls = 0;
+          for (int r = 0; r < R; ++r) {
+            const int ru = __ldg(p.g.region_ids + (size_t)r * N + g), rv = __ldg(p.g.region_ids + (size_t)r * N + h);
+            if (ru != rv || ru < 0 || rv < 0) cls |= 1u << r;
+          }
+          s.ecls[j] = (uint8_t)cls;
+        }
         ++j;
       }
     }
@@ -173,90 +196,165 @@ __device__ int gather_pair(const Chain& c, Step& st, int* d_sub_out) {
   return RC_OK;
 }
 
-// ---- P2a: random-weight minimum spanning tree by Boruvka rounds --------------------------
-// Unique MST under the total order (weight, local edge index) == networkx Kruskal's tree.
-// On return te[0..n-2] lists the tree edges in ascending local edge index.
-__device__ int boruvka_mst(const Chain& c, const Step& st, uint32_t tree_no, uint32_t prop_no,
-                           const double* rweights, int* rounds_out) {
+// ---- P2a: random-weight minimum spanning tree by contracting Boruvka rounds ---------------
+// Unique MST under the total order (key32, local edge index) == Kruskal's tree.  Live edges
+// carry their endpoints as current component ids; edges inside a component are dropped
+// every round, so the work shrinks geometrically.  On return tflag marks the tree edges
+// and te[0..n-2] lists them in ascending local edge index.
+constexpr int kCompactK = 8;
+
+__device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t prop_no,
+                           const uint32_t* rrank, int* rounds_out) {
+  const Params& p = *c.p;
   const Smem& s = c.s;
   const int tid = threadIdx.x, T = blockDim.x;
   const int n = st.n, m = st.m;
-  for (int j = tid; j < m; j += T) s.khi[j] = (uint32_t)(edge_key(c, j, tree_no, prop_no, rweights) >> 32);
-  for (int i = tid; i < n; i += T) s.comp[i] = (lid_t)i;
-  for (int i = tid; i < (m + 31) / 32; i += T) s.tflag[i] = 0;
-  if (tid == 0) s.misc[M_ERR] = 0;
-  int ncomp = n, rounds = 0;
-  while (ncomp > 1) {
-    ++rounds;
-    for (int i = tid; i < n; i += T) { s.best_hi[i] = 0xffffffffu; s.best_lo[i] = ~0ull; }
-    __syncthreads();
-    // A: minimum high word per component (native 32-bit shared atomics)
-    for (int j = tid; j < m; j += T) {
-      const int cu = s.comp[s.eu[j]], cv = s.comp[s.ev[j]];
-      if (cu != cv) {
-        const uint32_t h = s.khi[j];
-        atomicMin(&s.best_hi[cu], h);
-        atomicMin(&s.best_hi[cv], h);
+  // weights: one Philox block per four edges
+  if (rrank) {
+    for (int j = tid; j < m; j += T) s.key[j] = rrank[c.eids[j]];
+  } else {
+    for (int q = tid; q < (m + 3) >> 2; q += T) {
+      const RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WEIGHT, (uint32_t)q, tree_no, prop_no, 0);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int j = 4 * q + w;
+        if (j < m) s.key[j] = finish_key(c, j, r.v[w]);
       }
     }
+  }
+  for (int j = tid; j < m; j += T) { s.lab[j] = (uint32_t)s.eu[j] | ((uint32_t)s.ev[j] << 16); s.lj[j] = (lid_t)j; }
+  for (int i = tid; i < n; i += T) { s.best[i] = 0xffffffffu; s.bpos[i] = 0xffffffffu; s.hook[i] = (lid_t)i; }
+  for (int i = tid; i < (m + 31) >> 5; i += T) s.tflag[i] = 0;
+  if (tid == 0) s.misc[M_NLIVE] = 0;
+  __syncthreads();
+  int nlive = m, rounds = 0;
+  while (nlive > 0) {
+    ++rounds;
+    // A: minimum key per component (native 32-bit shared atomics)
+    for (int q = tid; q < nlive; q += T) {
+      const uint32_t ab = s.lab[q];
+      const uint32_t k = s.key[s.lj[q]];
+      atomicMin(&s.best[ab & 0xffffu], k);
+      atomicMin(&s.best[ab >> 16], k);
+    }
     __syncthreads();
-    // B: among the (almost always single) edges matching the high word, the full key
-    for (int j = tid; j < m; j += T) {
-      const int cu = s.comp[s.eu[j]], cv = s.comp[s.ev[j]];
-      if (cu != cv) {
-        const uint32_t h = s.khi[j];
-        const bool mu = h == s.best_hi[cu], mv = h == s.best_hi[cv];
-        if (mu || mv) {
-          const unsigned long long key = edge_key(c, j, tree_no, prop_no, rweights);
-          const unsigned long long v = (key << 32) | (unsigned long long)j;
-          if (mu) atomic_min_u64_smem(&s.best_lo[cu], v);
-          if (mv) atomic_min_u64_smem(&s.best_lo[cv], v);
+    // B: among the (almost always single) edges attaining it, the lowest edge index
+    for (int q = tid; q < nlive; q += T) {
+      const uint32_t ab = s.lab[q];
+      const uint32_t j = s.lj[q];
+      const uint32_t k = s.key[j];
+      const uint32_t v = (j << 16) | (uint32_t)q;
+      if (k == s.best[ab & 0xffffu]) atomicMin(&s.bpos[ab & 0xffffu], v);
+      if (k == s.best[ab >> 16]) atomicMin(&s.bpos[ab >> 16], v);
+    }
+    __syncthreads();
+    // C: every component hooks onto the other side of its lightest edge; of a mutual pair
+    // the smaller id stays a root
+    for (int v = tid; v < n; v += T) {
+      const uint32_t bp = s.bpos[v];
+      if (bp == 0xffffffffu) continue;
+      const uint32_t ab = s.lab[bp & 0xffffu];
+      const int a = ab & 0xffffu, b = ab >> 16;
+      const int other = a == v ? b : a;
+      const bool mutual = s.bpos[other] == bp;
+      if (!(mutual && v < other)) s.hook[v] = (lid_t)other;
+      if (!(mutual && v > other)) atomicOr(&s.tflag[bp >> 21], 1u << ((bp >> 16) & 31u));
+    }
+    __syncthreads();
+    // D: relabel the live edges to the new roots and drop the ones inside a component;
+    // in place: a sweep's reads all precede its writes, and it writes below what it read
+    for (int base = 0; base < nlive; base += T * kCompactK) {
+      uint32_t nab[kCompactK], nj[kCompactK];
+      int cnt = 0;
+#pragma unroll
+      for (int k = 0; k < kCompactK; ++k) {
+        const int q = base + k * T + tid;
+        nab[k] = 0xffffffffu;
+        nj[k] = 0;
+        if (q < nlive) {
+          const uint32_t ab = s.lab[q];
+          int a = ab & 0xffffu, b = ab >> 16;
+          int h;
+          while ((h = s.hook[a]) != a) a = h;
+          while ((h = s.hook[b]) != b) b = h;
+          if (a != b) { nab[k] = (uint32_t)a | ((uint32_t)b << 16); nj[k] = s.lj[q]; ++cnt; }
         }
       }
+      // warp-aggregated allocation of output slots (their order is immaterial)
+      const int incl = warp_incl_scan(cnt);
+      __syncthreads();  // every read of this sweep is done
+      int wbase = 0;
+      if ((tid & 31) == 31 && incl > 0) wbase = atomicAdd(&s.misc[M_NLIVE], incl);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      int o = wbase + incl - cnt;
+#pragma unroll
+      for (int k = 0; k < kCompactK; ++k)
+        if (nab[k] != 0xffffffffu) { s.lab[o] = nab[k]; s.lj[o] = (lid_t)nj[k]; ++o; }
     }
+    for (int i = tid; i < n; i += T) { s.best[i] = 0xffffffffu; s.bpos[i] = 0xffffffffu; }
     __syncthreads();
-    // C: hook every component onto the other side of its lightest edge
-    for (int i = tid; i < n; i += T) {
-      if (s.comp[i] != i) continue;
-      if (s.best_hi[i] == 0xffffffffu && s.best_lo[i] == ~0ull) { s.misc[M_ERR] = RC_ERR_DISCONNECTED; s.par[i] = (lid_t)i; continue; }
-      const int j = (int)(s.best_lo[i] & 0xffffffffull);
-      const int cu = s.comp[s.eu[j]], cv = s.comp[s.ev[j]];
-      const int other = cu == i ? cv : cu;
-      const bool mutual = s.best_hi[other] == s.best_hi[i] && s.best_lo[other] == s.best_lo[i];
-      s.par[i] = (lid_t)((mutual && i < other) ? i : other);
-      atomicOr(&s.tflag[j >> 5], 1u << (j & 31));
-    }
+    nlive = s.misc[M_NLIVE];
     __syncthreads();
-    if (s.misc[M_ERR]) return s.misc[M_ERR];
-    for (int i = tid; i < n; i += T) if (s.comp[i] == i) s.comp[i] = s.par[i];
-    __syncthreads();
-    // D: flatten (no writes to comp[] while it is being walked)
-    for (int i = tid; i < n; i += T) {
-      int r = s.comp[i];
-      while (s.comp[r] != r) r = s.comp[r];
-      s.par[i] = (lid_t)r;
-    }
-    __syncthreads();
-    int roots = 0;
-    for (int i = tid; i < n; i += T) { const int r = s.par[i]; s.comp[i] = (lid_t)r; roots += (r == i); }
-    if (tid == 0) s.misc[M_NCOMP] = 0;
-    __syncthreads();
-    if (roots) atomicAdd(&s.misc[M_NCOMP], roots);
-    __syncthreads();
-    ncomp = s.misc[M_NCOMP];
+    if (tid == 0) s.misc[M_NLIVE] = 0;
   }
   *rounds_out = rounds;
-  // tree edges in ascending local edge index
-  const int per = (m + T - 1) / T;
-  const int lo = min(tid * per, m), hi = min(lo + per, m);
+  // tree edges in ascending local edge index (units of 8 edges per thread step)
+  const int units = (m + 7) >> 3;
+  const int per = odd_chunk(units);
+  const int lo = min(tid * per, units), hi = min(lo + per, units);
+  const uint8_t* fb = reinterpret_cast<const uint8_t*>(s.tflag);
   int cnt = 0;
-  for (int j = lo; j < hi; ++j) cnt += (s.tflag[j >> 5] >> (j & 31)) & 1;
+  for (int u = lo; u < hi; ++u) cnt += __popc((uint32_t)fb[u]);
   int nt;
-  int t = block_excl_scan(cnt, &nt, s.misc);
-  for (int j = lo; j < hi; ++j)
-    if ((s.tflag[j >> 5] >> (j & 31)) & 1) s.te[t++] = (lid_t)j;
+  int t = block_excl_scan(cnt, &nt, s.misc, c.par);
+  __syncthreads();  // te aliases the (now dead) spanning-tree arrays
+  if (nt != n - 1) return RC_ERR_DISCONNECTED;
+  for (int u = lo; u < hi; ++u) {
+    uint32_t x = fb[u];
+    while (x) { s.te[t++] = (lid_t)(u * 8 + (__ffs(x) - 1)); x &= x - 1; }
+  }
   __syncthreads();
-  return nt == n - 1 ? RC_OK : RC_ERR_DISCONNECTED;
+  return RC_OK;
+}
+
+// tree adjacency (arcs grouped by tail) from te[]; fills toff, tadj, apos(slot); counts
+// the tree nodes of degree > 1 into misc[M_NINT]
+__device__ void build_tree_adjacency(Chain& c, const Step& st) {
+  const Smem& s = c.s;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int n = st.n, nt = n - 1;
+  for (int i = tid; i < n; i += T) s.cur[i] = 0;
+  if (tid == 0) s.misc[M_NINT] = 0;
+  __syncthreads();
+  for (int t = tid; t < nt; t += T) {
+    const int j = s.te[t];
+    atomicAdd(&s.cur[s.eu[j]], 1);
+    atomicAdd(&s.cur[s.ev[j]], 1);
+  }
+  __syncthreads();
+  {
+    const int per = odd_chunk(n);
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    int sum = 0, internal = 0;
+    for (int i = lo; i < hi; ++i) { const int d = s.cur[i]; sum += d; internal += d > 1; }
+    int tot;
+    int run = block_excl_scan(sum, &tot, s.misc, c.par);
+    for (int i = lo; i < hi; ++i) { const int d = s.cur[i]; s.toff[i] = (lid_t)run; s.cur[i] = run; run += d; }
+    if (tid == 0) s.toff[n] = (lid_t)(2 * nt);
+    internal = warp_sum(internal);
+    if ((tid & 31) == 0 && internal) atomicAdd(&s.misc[M_NINT], internal);
+  }
+  __syncthreads();
+  for (int t = tid; t < nt; t += T) {
+    const int j = s.te[t];
+    const int pu = atomicAdd(&s.cur[s.eu[j]], 1);
+    s.tadj[pu] = (lid_t)(2 * t);
+    s.apos[2 * t] = (lid_t)pu;
+    const int pv = atomicAdd(&s.cur[s.ev[j]], 1);
+    s.tadj[pv] = (lid_t)(2 * t + 1);
+    s.apos[2 * t + 1] = (lid_t)pv;
+  }
+  __syncthreads();
 }
 
 // ---- P3: root the tree and compute every subtree population ----------------------------
@@ -265,29 +363,35 @@ __device__ int boruvka_mst(const Chain& c, const Step& st, uint32_t tree_no, uin
 //   apos[a]  = tour position of arc a
 //   ent[i]   = position of the arc entering node i (0xffff for the root)
 //   cur[t]   = population below tree edge t (the side away from the root)
-__device__ void euler_subtree_pops(const Chain& c, const Step& st, int root) {
+// The set of balanced edges does not depend on the root, so
+// the tour is rooted wherever convenient; the reference's root only decides the labels.
+__device__ void euler_subtree_pops(Chain& c, const Step& st, int root) {
   const Smem& s = c.s;
   const int tid = threadIdx.x, T = blockDim.x;
   const int n = st.n, nt = n - 1, L = 2 * nt;
-  // nxt + ranks
+  // successor of arc a = the arc after reverse(a) around head(a)
+  const int last = (int)s.tadj[s.toff[root + 1] - 1] ^ 1;
   for (int a = tid; a < L; a += T) {
     const int t = a >> 1, j = s.te[t];
     const int head = (a & 1) ? s.eu[j] : s.ev[j];
-    const int r = a ^ 1;
-    int pn = s.apos[r] + 1;
+    int pn = s.apos[a ^ 1] + 1;
     if (pn == s.toff[head + 1]) pn = s.toff[head];
-    s.lrA[a] = ((uint32_t)s.tadj[pn] << 16) | 1u;
+    s.lrA[a] = a == last ? ((uint32_t)a << 16) : (((uint32_t)s.tadj[pn] << 16) | 1u);
   }
   __syncthreads();
-  if (tid == 0) {
-    const int last = s.tadj[s.toff[root + 1] - 1] ^ 1;
-    s.lrA[last] = ((uint32_t)last << 16) | 0u;
-  }
-  __syncthreads();
-  uint32_t* A = s.lrA;
-  uint32_t* B = s.lrB;
+  uint32_t* __restrict__ A = s.lrA;
+  uint32_t* __restrict__ B = s.lrB;
   for (int span = 1; span < L; span <<= 1) {
-    for (int a = tid; a < L; a += T) {
+    int a = tid;
+    for (; a + 3 * T < L; a += 4 * T) {  // four independent chains per thread in flight
+      const uint32_t x0 = A[a], x1 = A[a + T], x2 = A[a + 2 * T], x3 = A[a + 3 * T];
+      const uint32_t y0 = A[x0 >> 16], y1 = A[x1 >> 16], y2 = A[x2 >> 16], y3 = A[x3 >> 16];
+      B[a] = (y0 & 0xffff0000u) | ((x0 & 0xffffu) + (y0 & 0xffffu));
+      B[a + T] = (y1 & 0xffff0000u) | ((x1 & 0xffffu) + (y1 & 0xffffu));
+      B[a + 2 * T] = (y2 & 0xffff0000u) | ((x2 & 0xffffu) + (y2 & 0xffffu));
+      B[a + 3 * T] = (y3 & 0xffff0000u) | ((x3 & 0xffffu) + (y3 & 0xffffu));
+    }
+    for (; a < L; a += T) {
       const uint32_t x = A[a];
       const uint32_t y = A[x >> 16];
       B[a] = (y & 0xffff0000u) | ((x & 0xffffu) + (y & 0xffffu));
@@ -313,12 +417,12 @@ __device__ void euler_subtree_pops(const Chain& c, const Step& st, int root) {
   __syncthreads();
   // inclusive prefix sum of W[0..L)
   {
-    const int per = (L + T - 1) / T;
+    const int per = odd_chunk(L);
     const int lo = min(tid * per, L), hi = min(lo + per, L);
     int sum = 0;
     for (int i = lo; i < hi; ++i) sum += W[i];
     int tot;
-    int run = block_excl_scan(sum, &tot, s.misc);
+    int run = block_excl_scan(sum, &tot, s.misc, c.par);
     for (int i = lo; i < hi; ++i) { run += W[i]; W[i] = run; }
   }
   __syncthreads();
@@ -333,63 +437,27 @@ __device__ void euler_subtree_pops(const Chain& c, const Step& st, int root) {
   __syncthreads();
 }
 
-// tree adjacency (arcs grouped by tail) from te[]; fills toff, tadj, apos(slot)
-__device__ void build_tree_adjacency(const Chain& c, const Step& st) {
-  const Smem& s = c.s;
-  const int tid = threadIdx.x, T = blockDim.x;
-  const int n = st.n, nt = n - 1;
-  for (int i = tid; i < n; i += T) s.cur[i] = 0;
-  __syncthreads();
-  for (int t = tid; t < nt; t += T) {
-    const int j = s.te[t];
-    atomicAdd(&s.cur[s.eu[j]], 1);
-    atomicAdd(&s.cur[s.ev[j]], 1);
-  }
-  __syncthreads();
-  {
-    const int per = (n + T - 1) / T;
-    const int lo = min(tid * per, n), hi = min(lo + per, n);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += s.cur[i];
-    int tot;
-    int run = block_excl_scan(sum, &tot, s.misc);
-    for (int i = lo; i < hi; ++i) { const int d = s.cur[i]; s.toff[i] = run; s.cur[i] = run; run += d; }
-    if (tid == T - 1 || hi == n) s.toff[n] = 2 * nt;
-  }
-  __syncthreads();
-  for (int t = tid; t < nt; t += T) {
-    const int j = s.te[t];
-    const int pu = atomicAdd(&s.cur[s.eu[j]], 1);
-    s.tadj[pu] = (lid_t)(2 * t);
-    s.apos[2 * t] = (lid_t)pu;
-    const int pv = atomicAdd(&s.cur[s.ev[j]], 1);
-    s.tadj[pv] = (lid_t)(2 * t + 1);
-    s.apos[2 * t + 1] = (lid_t)pv;
-  }
-  __syncthreads();
-}
-
 // k-th element (ascending index) with pred(i) true among [0, count); block uniform result.
 template <typename Pred>
-__device__ int select_kth(const Chain& c, int count, int kth, Pred pred, int* total_out) {
+__device__ int select_kth(Chain& c, int count, int kth, Pred pred) {
   const Smem& s = c.s;
-  const int tid = threadIdx.x, T = blockDim.x;
-  const int per = (count + T - 1) / T;
+  const int tid = threadIdx.x;
+  const int per = odd_chunk(count);
   const int lo = min(tid * per, count), hi = min(lo + per, count);
   int cnt = 0;
   for (int i = lo; i < hi; ++i) cnt += pred(i) ? 1 : 0;
-  int tot;
-  const int excl = block_excl_scan(cnt, &tot, s.misc);
   if (tid == 0) s.misc[M_PICK] = -1;
-  __syncthreads();
+  int tot;
+  const int excl = block_excl_scan(cnt, &tot, s.misc, c.par);
   if (kth >= excl && kth < excl + cnt) {
     int k = kth - excl;
     for (int i = lo; i < hi; ++i)
       if (pred(i) && k-- == 0) { s.misc[M_PICK] = i; break; }
   }
   __syncthreads();
-  *total_out = tot;
-  return s.misc[M_PICK];
+  const int r = s.misc[M_PICK];
+  __syncthreads();
+  return r;
 }
 
 __device__ __forceinline__ bool balanced(int tree_pop, int total_pop, double ideal, double thr) {
@@ -399,8 +467,8 @@ __device__ __forceinline__ bool balanced(int tree_pop, int total_pop, double ide
 }
 
 // ---- P5: region-aware cut choice (tree.py:501-578); returns tree edge index --------------
-__device__ int choose_cut_by_weight(const Chain& c, const Step& st, int policy, uint32_t tree_no,
-                                    uint32_t prop_no, const double* rweights, double ideal, double thr) {
+__device__ int choose_cut_by_weight(Chain& c, const Step& st, int policy, uint32_t tree_no,
+                                    uint32_t prop_no, const uint32_t* rrank, double ideal, double thr) {
   const Params& p = *c.p;
   const Smem& s = c.s;
   const int tid = threadIdx.x, T = blockDim.x;
@@ -429,14 +497,18 @@ __device__ int choose_cut_by_weight(const Chain& c, const Step& st, int policy, 
   unsigned long long* best = reinterpret_cast<unsigned long long*>(&s.misc[M_BEST64]);
   if (tid == 0) { s.misc[M_SUBSET] = 0; *best = 0ull; }
   __syncthreads();
-  // which subsets have a suitable cut
-  for (int t = tid; t < nt; t += T) {
-    if (!balanced(s.cur[t], st.tot, ideal, thr)) continue;
-    const int j = s.te[t];
+  // tree.py:552-561: a cut "crosses" a region column when its endpoints' labels differ
+  // (None == None there, unlike the weight loop)
+  auto crossed = [&](int j) {
     const int gu = c.nodes[s.eu[j]], gv = c.nodes[s.ev[j]];
     int cm = 0;
     for (int r = 0; r < R && r < 3; ++r)
       if (p.g.region_ids[(size_t)r * p.g.N + gu] != p.g.region_ids[(size_t)r * p.g.N + gv]) cm |= 1 << r;
+    return cm;
+  };
+  for (int t = tid; t < nt; t += T) {
+    if (!balanced(s.cur[t], st.tot, ideal, thr)) continue;
+    const int cm = crossed(s.te[t]);
     int has = 0;
     for (int i = 0; i < ns; ++i) if ((cm & subsets[i]) == subsets[i]) has |= 1 << i;
     if (has) atomicOr(&s.misc[M_SUBSET], has);
@@ -444,37 +516,19 @@ __device__ int choose_cut_by_weight(const Chain& c, const Step& st, int policy, 
   __syncthreads();
   const int has = s.misc[M_SUBSET];
   const int need = has ? subsets[__ffs(has) - 1] : 0;
+  // max key, ties -> lowest tree edge: pack (key << 32 | ~t)
   for (int t = tid; t < nt; t += T) {
     if (!balanced(s.cur[t], st.tot, ideal, thr)) continue;
     const int j = s.te[t];
-    if (need) {
-      const int gu = c.nodes[s.eu[j]], gv = c.nodes[s.ev[j]];
-      int cm = 0;
-      for (int r = 0; r < R && r < 3; ++r)
-        if (p.g.region_ids[(size_t)r * p.g.N + gu] != p.g.region_ids[(size_t)r * p.g.N + gv]) cm |= 1 << r;
-      if ((cm & need) != need) continue;
-    }
-    // max weight, ties -> lowest edge index.  Two rounds keep it exact with one 64-bit CAS:
-    atomic_max_u64_smem(best, edge_key(c, j, tree_no, prop_no, rweights));
+    if (need && (crossed(j) & need) != need) continue;
+    const unsigned long long v = ((unsigned long long)edge_key(c, j, tree_no, prop_no, rrank) << 32) |
+                                 (unsigned long long)(0xffffffffu - (uint32_t)t);
+    atomic_max_u64_smem(best, v);
   }
   __syncthreads();
-  const unsigned long long bw = *best;
-  if (tid == 0) s.misc[M_TSTAR] = 0x7fffffff;
+  const int tstar = (int)(0xffffffffu - (uint32_t)(*best & 0xffffffffull));
   __syncthreads();
-  for (int t = tid; t < nt; t += T) {
-    if (!balanced(s.cur[t], st.tot, ideal, thr)) continue;
-    const int j = s.te[t];
-    if (need) {
-      const int gu = c.nodes[s.eu[j]], gv = c.nodes[s.ev[j]];
-      int cm = 0;
-      for (int r = 0; r < R && r < 3; ++r)
-        if (p.g.region_ids[(size_t)r * p.g.N + gu] != p.g.region_ids[(size_t)r * p.g.N + gv]) cm |= 1 << r;
-      if ((cm & need) != need) continue;
-    }
-    if (edge_key(c, j, tree_no, prop_no, rweights) == bw) atomicMin(&s.misc[M_TSTAR], t);
-  }
-  __syncthreads();
-  return s.misc[M_TSTAR];
+  return tstar;
 }
 
 struct ProposalResult {
@@ -485,7 +539,7 @@ struct ProposalResult {
 };
 
 // One recom proposal + validity + commit (tree_proposals.py:36-146, chain.py:186-195).
-__device__ ProposalResult propose(const Chain& c, uint32_t prop_no, const RcReplayStep* rs,
+__device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep* rs,
                                   int32_t* ctr /* smem counters */) {
   const Params& p = *c.p;
   const Smem& s = c.s;
@@ -509,7 +563,8 @@ __device__ ProposalResult propose(const Chain& c, uint32_t prop_no, const RcRepl
   const bool warn_on = !p.cfg.allow_pair_reselection && p.cfg.warn_attempts > 0;
   const int n_rec = rs ? rs->n_trees : 0;
   const uint32_t t0 = (rs && nr == 0 && n_rec > 0) ? (uint32_t)(n_rec - 1) : 0u;
-  int tstar = -1;
+  const int r0 = 0;  // tour root: local node 0 (any node will do)
+  int tstar = -1, root = -1;
   for (uint32_t retry = 0;; ++retry) {  // tree_proposals.py:103-138
   if (resel && n_bad >= k * (k - 1) / 2) { res.status = RC_ERR_ALL_PAIRS_BAD; return res; }
   // ---- P0
@@ -546,51 +601,56 @@ __device__ ProposalResult propose(const Chain& c, uint32_t prop_no, const RcRepl
       return res;
     }
     if (rs && (int)tree_no >= n_rec) { res.status = RC_ERR_REPLAY; return res; }
-    const double* rweights = rs ? p.rp.weights + (rs->first_tree + tree_no) * (long long)p.g.E : nullptr;
+    const uint32_t* rrank = rs ? p.rp.weight_rank + (rs->first_tree + tree_no) * (long long)p.g.E : nullptr;
     // ---- P2
     int rounds = 0;
-    res.status = boruvka_mst(c, st, tree_no, prop_no, rweights, &rounds);
+    res.status = boruvka_mst(c, st, tree_no, prop_no, rrank, &rounds);
     if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_ROUNDS] += rounds; }
     res.trees = (int)tree_no + 1;
     if (res.status) return res;
     build_tree_adjacency(c, st);
-    // ---- root (tree.py:377): uniform over tree nodes of degree > 1
-    int root;
-    const bool last_rec = rs && (int)tree_no == n_rec - 1;
-    if (last_rec) {
-      const int gr = rs->root;
-      root = (gr >= 0 && gr < p.g.N && in_pair(c.assign[gr], st.a, st.b)) ? (int)c.g2l[gr] : -1;
-      if (root < 0 || s.toff[root + 1] - s.toff[root] < 2) { res.status = RC_ERR_REPLAY; return res; }
-    } else {
-      RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_ROOT, 0, tree_no, prop_no, 0);
-      int n_int = 0;
-      auto internal = [&](int i) { return s.toff[i + 1] - s.toff[i] > 1; };
-      // two passes: count, then select (the draw needs the count)
-      (void)select_kth(c, n, -1, internal, &n_int);
-      if (n_int == 0) { res.status = RC_ERR_NO_ROOT; return res; }
-      root = select_kth(c, n, (int)rc_below(r.v[0], r.v[1], (uint32_t)n_int), internal, &n_int);
-    }
+    // tree.py:377: the root is drawn among tree nodes of degree > 1 (none: IndexError)
+    const int n_int = s.misc[M_NINT];
+    if (n_int == 0) { res.status = RC_ERR_NO_ROOT; return res; }
     // ---- P3
-    euler_subtree_pops(c, st, root);
+    euler_subtree_pops(c, st, r0);
     // ---- P4: balanced tree edges (cur[t] = population below edge t)
     auto is_bal = [&](int t) { return balanced(s.cur[t], st.tot, ideal, thr); };
-    int nbal = 0;
-    (void)select_kth(c, nt, -1, is_bal, &nbal);
+    {
+      if (tid == 0) s.misc[M_NBAL] = 0;
+      __syncthreads();
+      int cnt = 0;
+      for (int t = tid; t < nt; t += T) cnt += is_bal(t) ? 1 : 0;
+      cnt = warp_sum(cnt);
+      if ((tid & 31) == 0 && cnt) atomicAdd(&s.misc[M_NBAL], cnt);
+      __syncthreads();
+    }
+    const int nbal = s.misc[M_NBAL];
     res.nbal = nbal;
     if (nbal > 0) {
+      const bool last_rec = rs && (int)tree_no == n_rec - 1;
       if (rs && !last_rec) { res.status = RC_ERR_REPLAY; return res; }
+      // ---- root (tree.py:377): uniform over tree nodes of degree > 1, ascending node index
+      if (last_rec) {
+        const int gr = rs->root;
+        root = (gr >= 0 && gr < p.g.N && is_member(s, gr)) ? local_id(s, gr) : -1;
+        if (root < 0 || s.toff[root + 1] - s.toff[root] < 2) { res.status = RC_ERR_REPLAY; return res; }
+      } else {
+        RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_ROOT, 0, tree_no, prop_no, 0);
+        root = select_kth(c, n, (int)rc_below(r.v[0], r.v[1], (uint32_t)n_int),
+                          [&](int i) { return s.toff[i + 1] - s.toff[i] > 1; });
+      }
       // ---- P5
       const int policy = p.cfg.tree_kind == RC_TREE_WILSON ? RC_CUT_UNIFORM : p.cfg.cut_policy;
       if (rs && rs->cut_edge >= 0) {
         const int want = rs->cut_edge;
-        tstar = select_kth(c, nt, 0, [&](int t) { return c.eids[s.te[t]] == want && is_bal(t); }, &nbal);
-        nbal = res.nbal;
+        tstar = select_kth(c, nt, 0, [&](int t) { return c.eids[s.te[t]] == want && is_bal(t); });
         if (tstar < 0) { res.status = RC_ERR_REPLAY; return res; }
       } else if (policy == RC_CUT_UNIFORM) {
         RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_CUT, 0, tree_no, prop_no, 0);
-        tstar = select_kth(c, nt, (int)rc_below(r.v[0], r.v[1], (uint32_t)nbal), is_bal, &nbal);
+        tstar = select_kth(c, nt, (int)rc_below(r.v[0], r.v[1], (uint32_t)nbal), is_bal);
       } else {
-        tstar = choose_cut_by_weight(c, st, policy, tree_no, prop_no, rweights, ideal, thr);
+        tstar = choose_cut_by_weight(c, st, policy, tree_no, prop_no, rrank, ideal, thr);
       }
       if (tid == 0) {
         ctr[RC_CTR_ATTEMPTS] += (int)min(attempts + 1, 0x7fffffffLL);
@@ -607,11 +667,14 @@ __device__ ProposalResult propose(const Chain& c, uint32_t prop_no, const RcRepl
   }
   break;
   }  // pair loop
-  // ---- P6: the side holding the root keeps the lower id (tree.py:421, :947-950)
+  // ---- P6: the side holding the reference's root keeps the lower id (tree.py:421, :947-950)
   const int pa = s.apos[2 * tstar], pb = s.apos[2 * tstar + 1];
   const int pd = min(pa, pb), pu = max(pa, pb);
+  auto below = [&](int i) { const int en = s.ent[i]; return en != 0xffff && en >= pd && en <= pu; };
+  const bool root_below = below(root);
   const int child_pop = s.cur[tstar];
-  const long long pop_b = child_pop, pop_a = (long long)st.tot - child_pop;
+  const long long pop_a = root_below ? (long long)child_pop : (long long)st.tot - child_pop;
+  const long long pop_b = (long long)st.tot - pop_a;
   bool valid = true;
   if (p.cfg.pop_lower <= p.cfg.pop_upper) {  // constraints/bounds.py:25-28
     const double lo = (double)min(pop_a, pop_b), hi = (double)max(pop_a, pop_b);
@@ -621,7 +684,8 @@ __device__ ProposalResult propose(const Chain& c, uint32_t prop_no, const RcRepl
     if (tid == 0) ctr[RC_CTR_INVALID] += 1;
     return res;
   }
-  auto side = [&](int i) { const int en = s.ent[i]; return en != 0xffff && en >= pd && en <= pu; };
+  // side(i): node i is cut away from the root's side and takes the higher id b
+  auto side = [&](int i) { return below(i) != root_below; };
   if (tid == 0) s.misc[M_DELTA] = 0;
   __syncthreads();
   int delta = 0;
@@ -632,7 +696,8 @@ __device__ ProposalResult propose(const Chain& c, uint32_t prop_no, const RcRepl
     const uint32_t old = now ? atomicOr(c.mask + (eid >> 5), bit) : atomicAnd(c.mask + (eid >> 5), ~bit);
     delta += (int)now - (int)((old & bit) != 0);
   }
-  if (delta) atomicAdd(&s.misc[M_DELTA], delta);
+  delta = warp_sum(delta);
+  if ((tid & 31) == 0 && delta) atomicAdd(&s.misc[M_DELTA], delta);
   for (int i = tid; i < st.n; i += T) c.assign[c.nodes[i]] = (uint8_t)(side(i) ? st.b : st.a);
   __syncthreads();
   if (tid == 0) {
@@ -647,11 +712,11 @@ __device__ ProposalResult propose(const Chain& c, uint32_t prop_no, const RcRepl
 }
 
 // =========================================================================================
-__global__ void __launch_bounds__(512) recom_step_kernel(const Params p) {
+__global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Chain c;
   c.p = &p;
-  smem_layout(&c.s, smem_raw, p.cap_nodes, p.cap_edges);
+  smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R);
   const int tid = threadIdx.x;
   const bool replay = p.rp.n_steps > 0;
   c.chain = replay ? p.rp.chain : (int)blockIdx.x;
@@ -659,9 +724,9 @@ __global__ void __launch_bounds__(512) recom_step_kernel(const Params p) {
   c.assign = p.st.d_assignment + (size_t)c.chain * p.st.assign_stride;
   c.mask = p.st.d_cut_mask + (size_t)c.chain * p.st.mask_stride;
   c.tally = p.st.d_tally + (size_t)c.chain * p.cfg.n_districts;
-  c.g2l = p.g2l + (size_t)blockIdx.x * p.g2l_stride;
   c.nodes = p.nodes + (size_t)blockIdx.x * p.cap_nodes;
   c.eids = p.eids + (size_t)blockIdx.x * p.cap_edges;
+  c.par = 0;
   int32_t* ctr = c.s.misc + M_CTR;  // [RC_N_COUNTERS]
   if (tid < RC_N_COUNTERS) ctr[tid] = 0;
   __syncthreads();
@@ -678,12 +743,12 @@ __global__ void __launch_bounds__(512) recom_step_kernel(const Params p) {
     for (; streak < streak_cap; ++streak) {
       r = propose(c, replay ? (uint32_t)sidx : prop_no, rs, ctr);
       ++prop_no;
+      __syncthreads();
       if (r.status || r.accepted || replay) break;
     }
     status = r.status;
     if (status == RC_OK && !r.accepted) status = RC_ERR_INVALID_STREAK;
     if (status == RC_OK) ++done;
-    __syncthreads();
     if (replay) {
       if (p.rp.info_trace && tid == 0) {
         int32_t* inf = p.rp.info_trace + 4 * sidx;
@@ -691,8 +756,8 @@ __global__ void __launch_bounds__(512) recom_step_kernel(const Params p) {
       }
       if (p.rp.assign_trace)
         for (int i = tid; i < p.g.N; i += blockDim.x) p.rp.assign_trace[(size_t)sidx * p.g.N + i] = c.assign[i];
+      __syncthreads();
     }
-    __syncthreads();
   }
   if (tid == 0) {
     p.st.d_proposal_no[c.chain] = prop_no;

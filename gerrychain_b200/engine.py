@@ -186,7 +186,8 @@ class Engine:
         rp.n_steps = n_steps
         rp.chain = chain
         rp.steps = up(rec.steps)
-        rp.weights = up(rec.weights)
+        rp.weights = None  # float64 weights are the oracle's input; the device takes ranks
+        rp.weight_rank = up(rec.weight_rank)
         rp.wilson_root = up(rec.wilson_root)
         rp.stack_ptr = up(rec.stack_ptr)
         rp.stack_val = up(rec.stack_val)

@@ -139,7 +139,11 @@ typedef struct RcReplay {
   int32_t n_steps;
   int32_t chain;                 /* local chain index the record is applied to          */
   const RcReplayStep* steps;     /* [n_steps]                                           */
-  const double* weights;         /* MST: [n_trees_total][E] random_weight per edge id   */
+  const double* weights;         /* MST: [n_trees_total][E] random_weight per edge id
+                                    (read by the CPU oracle)                            */
+  const uint32_t* weight_rank;   /* MST: [n_trees_total][E] rank of that weight among the
+                                    tree's recorded weights, ties by edge id (read by the
+                                    device engine: only the order matters, tree.py:91-93) */
   const int32_t* wilson_root;    /* Wilson: [n_trees_total] root (tree.py:112)          */
   const int64_t* stack_ptr;      /* Wilson: [n_trees_total][N+1] into stack_val         */
   const int32_t* stack_val;      /* Wilson: chosen neighbour node index per draw        */

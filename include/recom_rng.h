@@ -26,7 +26,8 @@
 
 enum {
   RC_DRAW_PAIR = 1,   /* which cut edge (tree_proposals.py:106); index = reselect retry  */
-  RC_DRAW_WEIGHT = 2, /* random_weight of edge e (tree.py:79); index = e >> 1, words 2*(e&1).. */
+  RC_DRAW_WEIGHT = 2, /* random_weight of the j-th edge of the merged subgraph, edges taken
+                         in ascending edge id (tree.py:79); index = j >> 2, word j & 3    */
   RC_DRAW_ROOT = 3,   /* BFS root among tree nodes of degree > 1 (tree.py:377)          */
   RC_DRAW_CUT = 4,    /* random.choice(cuts) (tree.py:545)                              */
   RC_DRAW_WROOT = 5,  /* Wilson root (tree.py:112)                                      */
@@ -90,13 +91,33 @@ RC_HD double rc_unit_double(uint32_t a, uint32_t b) {
   return (double)x * (1.0 / 9007199254740992.0);
 }
 
-/* random_weight of undirected edge `e` for tree `tree_no` of proposal `proposal_no`,
- * before surcharges (tree.py:79). */
-RC_HD double rc_edge_unit_weight(uint64_t seed, uint32_t chain, uint32_t e,
-                                 uint32_t tree_no, uint32_t proposal_no) {
-  RcPhilox p = rc_draw(seed, chain, RC_DRAW_WEIGHT, e >> 1, tree_no, proposal_no, 0);
-  uint32_t h = (e & 1u) * 2u;
-  return rc_unit_double(p.v[h], p.v[h + 1]);
+/*
+ * Edge weights.  The reference draws random.random() (53 bits) per edge and adds the
+ * surcharges of the region columns the edge crosses (tree.py:78-89); only the ORDER of
+ * the weights matters (Kruskal's sort, and the max-weight cut choice).  Free-running mode
+ * uses 32-bit fixed point: raw = one Philox word (u = raw / 2^32), surcharge s_r as
+ * sfix_r = round(s_r * 2^32), sum in 64-bit integers, rescaled monotonically into 32 bits;
+ * the total order is (key32, edge id).  Exact ties of key32 (p ~ m^2 / 2^33 per tree) fall
+ * to the lower edge id - as Kruskal's stable sort would do with tied floats.
+ */
+RC_HD uint64_t rc_surcharge_fix(double s) { return (uint64_t)(s * 4294967296.0 + 0.5); }
+
+/* mult = 0 when there are no region columns (key32 = raw). */
+RC_HD uint64_t rc_key_mult(uint64_t sfix_total, int n_region_cols) {
+  if (n_region_cols <= 0) return 0;
+  return 0xFFFFFFFFFFFFFFFFull / ((1ull << 32) + sfix_total);
+}
+
+RC_HD uint32_t rc_key_finish(uint32_t raw, uint64_t sadd, uint64_t mult) {
+  if (mult == 0) return raw;
+  return (uint32_t)((((uint64_t)raw + sadd) * mult) >> 32);
+}
+
+/* raw 32-bit weight of local edge j for tree `tree_no` of proposal `proposal_no`. */
+RC_HD uint32_t rc_edge_raw(uint64_t seed, uint32_t chain, uint32_t j, uint32_t tree_no,
+                           uint32_t proposal_no) {
+  RcPhilox p = rc_draw(seed, chain, RC_DRAW_WEIGHT, j >> 2, tree_no, proposal_no, 0);
+  return p.v[j & 3u];
 }
 
 #endif /* RECOM_RNG_H */

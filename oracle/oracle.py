@@ -136,6 +136,7 @@ class OracleChains:
         rp.chain = chain
         rp.steps = rec.steps.ctypes.data
         rp.weights = rec.weights.ctypes.data if rec.weights is not None else None
+        rp.weight_rank = None
         rp.wilson_root = rec.wilson_root.ctypes.data if rec.wilson_root is not None else None
         rp.stack_ptr = rec.stack_ptr.ctypes.data if rec.stack_ptr is not None else None
         rp.stack_val = rec.stack_val.ctypes.data if rec.stack_val is not None else None

@@ -179,21 +179,27 @@ static void rco_ungather(RcoWork* w) {
   for (int i = 0; i < w->n; ++i) w->g2l[w->nodes[i]] = -1;
 }
 
-/* tree.py:78-89: weight = random.random() + surcharges for region-crossing edges.       */
-static double surcharged(const RcGraph* g, int u, int v, double weight) {
+/* tree.py:78-89: weight = random.random() + surcharges for region-crossing edges, in the
+ * 32-bit fixed point of include/recom_rng.h (only the order of the weights matters). */
+static uint64_t surcharge_fix(const RcGraph* g, int u, int v) {
+  uint64_t add = 0;
   for (int r = 0; r < g->n_region_cols; ++r) {
     int ru = g->region_ids[(size_t)r * g->n_nodes + u];
     int rv = g->region_ids[(size_t)r * g->n_nodes + v];
-    if (ru != rv || ru < 0 || rv < 0) weight += g->surcharges[r];
+    if (ru != rv || ru < 0 || rv < 0) add += rc_surcharge_fix(g->surcharges[r]);
   }
-  return weight;
+  return add;
 }
 
 static void rco_random_weights(const RcGraph* g, const RcConfig* c, RcoWork* w,
                                uint32_t chain, uint32_t tree_no, uint32_t prop_no) {
-  for (int j = 0; j < w->m; ++j) {
-    double u01 = rc_edge_unit_weight(c->seed, chain, (uint32_t)w->eid[j], tree_no, prop_no);
-    w->w[j] = surcharged(g, w->nodes[w->eu[j]], w->nodes[w->ev[j]], u01);
+  uint64_t tot = 0;
+  for (int r = 0; r < g->n_region_cols; ++r) tot += rc_surcharge_fix(g->surcharges[r]);
+  uint64_t mult = rc_key_mult(tot, g->n_region_cols);
+  for (int j = 0; j < w->m; ++j) {   /* j-th edge in ascending edge id (rco_gather order) */
+    uint32_t raw = rc_edge_raw(c->seed, chain, (uint32_t)j, tree_no, prop_no);
+    uint64_t add = mult ? surcharge_fix(g, w->nodes[w->eu[j]], w->nodes[w->ev[j]]) : 0;
+    w->w[j] = (double)rc_key_finish(raw, add, mult);
   }
 }
 

@@ -27,6 +27,7 @@ assert STEP_DTYPE.itemsize == 24
 class ReplayArrays:
     steps: np.ndarray
     weights: Optional[np.ndarray] = None  # [T][E] f64
+    weight_rank: Optional[np.ndarray] = None  # [T][E] u32, order of weights (ties: edge id)
     wilson_root: Optional[np.ndarray] = None  # [T]
     stack_ptr: Optional[np.ndarray] = None  # [T][N+1] i64
     stack_val: Optional[np.ndarray] = None
@@ -88,6 +89,11 @@ def load(name, inject_cut=True) -> Golden:
         t_of = np.repeat(np.arange(T), np.diff(wp))
         w[t_of, z["w_eid"]] = z["w_val"]
         rec.weights = w
+        # NaN (edge outside the merged pair) sorts last; stable -> ties fall to the lower id
+        order = np.argsort(w, axis=1, kind="stable")
+        rank = np.empty_like(order)
+        np.put_along_axis(rank, order, np.broadcast_to(np.arange(csr.n_edges), order.shape), axis=1)
+        rec.weight_rank = rank.astype(np.uint32)
     else:
         rec.wilson_root = z["wilson_root"].astype(np.int32)
         sp = np.zeros((T, n_nodes + 1), dtype=np.int64)
