@@ -54,6 +54,8 @@ struct Smem {
   lid_t* eu;         // [CE]
   lid_t* ev;         // [CE]
   uint32_t* tflag;   // [CE/32] tree-edge bitmap over local edges
+  uint32_t* oldb;    // [CN/32] bit i: local node i carries the higher district id b
+  uint32_t* newb;    // [CN/32] the same after the proposed cut
   uint8_t* ecls;     // [CE] bitmask of region columns the edge crosses (R > 0 only)
   // spanning-tree phase
   uint32_t* key;     // [CE] 32-bit weight key of local edge j
@@ -64,13 +66,16 @@ struct Smem {
   lid_t* hook;       // [CN] component merge forest
   // Euler-tour phase (aliases the spanning-tree phase)
   lid_t* te;         // [CN] local edge index of tree edge t (ascending)
-  lid_t* toff;       // [CN+1]
-  int32_t* cur;      // [CN] fill cursor; later population below tree edge t
-  lid_t* tadj;       // [2CN] arcs leaving each node
-  lid_t* apos;       // [2CN] slot of arc a in tadj; later: tour position of arc a
-  uint32_t* lrA;     // [2CN] (next << 16 | dist)
-  uint32_t* lrB;     // [2CN] ; later the prefix-sum array
-  lid_t* ent;        // [CN] tour position of the arc entering the node (aliases tadj)
+  uint32_t* head;    // [CN] first out-arc of a node (linked adjacency)
+  lid_t* nxt;        // [2CN] next out-arc of the same node
+  lid_t* succ;       // [2CN] tour successor of an arc
+  int32_t* cur;      // [CN] population below tree edge t (aliases succ)
+  lid_t* P;          // [2CN] tour position of arc a
+  int32_t* W;        // [2CN] arc weight, later exclusive weight prefix in tour order
+  uint32_t* spX;     // [2][spCap] sublist ranking: (next << 16 | dist), ping-pong
+  int32_t* spY;      // [2][spCap] sublist ranking: weight
+  lid_t* ent;        // [CN] tour position of the arc entering the node
+  int spCap;
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
@@ -87,6 +92,8 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
   size_t o_eu = take(size_t(CE) * 2);
   size_t o_ev = take(size_t(CE) * 2);
   size_t o_tfl = take(size_t((CE + 31) / 32) * 4);
+  size_t o_oldb = take(size_t((CN + 31) / 32) * 4);
+  size_t o_newb = take(size_t((CN + 31) / 32) * 4);
   size_t o_ecls = take(R > 0 ? size_t(CE) : 0);
   size_t phase = o;
   // spanning-tree phase
@@ -99,14 +106,16 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
   size_t end_a = o;
   // Euler phase
   o = phase;
+  const int spCap = (2 * CN) / 8 + 4;
   size_t o_te = take(size_t(CN) * 2);
-  size_t o_toff = take(size_t(CN + 1) * 2);
-  size_t o_cur = take(size_t(CN) * 4);
-  size_t o_tadj = take(size_t(2 * CN) * 2);
-  size_t o_apos = take(size_t(2 * CN) * 2);
-  size_t o_lrA = take(size_t(2 * CN) * 4);
-  size_t o_lrB = take(size_t(2 * CN) * 4);
-  size_t o_ent = o_tadj;  // tadj is dead once the tour successors exist
+  size_t o_head = take(size_t(CN) * 4);
+  size_t o_nxt = take(size_t(2 * CN) * 2);
+  size_t o_succ = take(size_t(2 * CN) * 2);
+  size_t o_P = take(size_t(2 * CN) * 2);
+  size_t o_W = take(size_t(2 * CN) * 4);
+  size_t o_spX = take(size_t(2 * spCap) * 4);
+  size_t o_spY = take(size_t(2 * spCap) * 4);
+  size_t o_ent = take(size_t(CN) * 2);
   size_t end_b = o;
   if (s) {
     s->misc = (int32_t*)(base + o_misc);
@@ -116,6 +125,8 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
     s->eu = (lid_t*)(base + o_eu);
     s->ev = (lid_t*)(base + o_ev);
     s->tflag = (uint32_t*)(base + o_tfl);
+    s->oldb = (uint32_t*)(base + o_oldb);
+    s->newb = (uint32_t*)(base + o_newb);
     s->ecls = (uint8_t*)(base + o_ecls);
     s->key = (uint32_t*)(base + o_key);
     s->lab = (uint32_t*)(base + o_lab);
@@ -124,20 +135,23 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
     s->bpos = (uint32_t*)(base + o_bpos);
     s->hook = (lid_t*)(base + o_hook);
     s->te = (lid_t*)(base + o_te);
-    s->toff = (lid_t*)(base + o_toff);
-    s->cur = (int32_t*)(base + o_cur);
-    s->tadj = (lid_t*)(base + o_tadj);
-    s->apos = (lid_t*)(base + o_apos);
-    s->lrA = (uint32_t*)(base + o_lrA);
-    s->lrB = (uint32_t*)(base + o_lrB);
+    s->head = (uint32_t*)(base + o_head);
+    s->nxt = (lid_t*)(base + o_nxt);
+    s->succ = (lid_t*)(base + o_succ);
+    s->cur = (int32_t*)(base + o_succ);
+    s->P = (lid_t*)(base + o_P);
+    s->W = (int32_t*)(base + o_W);
+    s->spX = (uint32_t*)(base + o_spX);
+    s->spY = (int32_t*)(base + o_spY);
     s->ent = (lid_t*)(base + o_ent);
+    s->spCap = spCap;
   }
   return end_a > end_b ? end_a : end_b;
 }
 
 // misc[] slots
 enum { M_WSUM = 0 /* 0..63: two alternating banks of 32 warp sums */,
-       M_ERR = 65, M_PICK, M_CNT, M_TOT, M_NINT, M_SUBSET, M_DELTA, M_TSTAR, M_NLIVE, M_NBAL,
+       M_ERR = 65, M_PICK, M_CNT, M_TOT, M_NINT, M_SUBSET, M_DELTA, M_TSTAR, M_NLIVE, M_NBAL, M_TAILLEN,
        M_BEST64 = 80 /* 80..81, 8-byte aligned */, M_CTR = 88 /* 88..95 counters */ };
 
 #ifdef __CUDACC__

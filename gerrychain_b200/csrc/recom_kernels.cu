@@ -131,52 +131,48 @@ __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
   st.n = n;
   __syncthreads();
   if (n > p.cap_nodes || n > kMaxLocal) return RC_ERR_CAPACITY;
-  // pass 2: local id -> global node, population, degree sum
-  int popsum = 0, slots = 0;
-  for (int i = tid; i < n; i += T) {
-    int lo = 0, hi = NW;  // first word whose prefix exceeds i
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if ((int)s.mpref[mid] > i) hi = mid; else lo = mid + 1;
-    }
-    const int w = lo - 1;
-    const int g = w * 32 + (int)__fns(s.mbits[w], 0, i - (int)s.mpref[w] + 1);
-    c.nodes[i] = g;
-    const int pg = __ldg(p.g.pop + g);
-    s.pop[i] = pg;
-    popsum += pg;
-    slots += __ldg(p.g.row_ptr + g + 1) - __ldg(p.g.row_ptr + g);
-  }
-  popsum = warp_sum(popsum);
-  slots = warp_sum(slots);
-  if ((tid & 31) == 0) { atomicAdd(&s.misc[M_TOT], popsum); atomicAdd(&s.misc[M_CNT], slots); }
-  __syncthreads();  // nodes[] (global) visible to the block; totals complete
-  st.tot = s.misc[M_TOT];
-  *d_sub_out = s.misc[M_CNT];
-  // edges: each thread owns a contiguous run of local nodes so that edges come out in
-  // ascending (u, v) == ascending edge id.
-  const int per = odd_chunk(n);
-  const int lo = min(tid * per, n), hi = min(lo + per, n);
-  int cnt = 0;
-  for (int i = lo; i < hi; ++i) {
-    const int g = c.nodes[i];
-    const int r1 = __ldg(p.g.row_ptr + g + 1);
-    for (int sl = __ldg(p.g.row_ptr + g); sl < r1; ++sl) {
-      const int h = __ldg(p.g.col_idx + sl);
-      if (h > g && is_member(s, h)) ++cnt;
-    }
-  }
-  int m;
-  int j = block_excl_scan(cnt, &m, s.misc, c.par);
-  st.m = m;
-  if (m > p.cap_edges || m > 65535) { __syncthreads(); return RC_ERR_CAPACITY; }
+  // pass 2, T local nodes per sweep: local id -> global node, population, old side, and the
+  // node's forward edges inside the pair.  Thread order == node order and slots ascend, so
+  // edges come out in ascending (u, v) == ascending edge id.  The adjacency row is read
+  // once for the count; the qualifying slots are remembered as a bitmask.
   const int R = p.g.R;
-  for (int i = lo; i < hi; ++i) {
-    const int g = c.nodes[i];
-    const int r1 = __ldg(p.g.row_ptr + g + 1);
-    for (int sl = __ldg(p.g.row_ptr + g); sl < r1; ++sl) {
-      const int h = __ldg(p.g.col_idx + sl);
-      if (h > g && is_member(s, h)) {
+  int popsum = 0, slots = 0, m = 0;
+  for (int i0 = 0; i0 < n; i0 += T) {
+    const int i = i0 + tid;
+    int g = 0, r0 = 0, r1 = 0, extra = 0;
+    uint32_t qmask = 0;
+    bool isb = false;
+    if (i < n) {
+      int lo = 0, hi = NW;  // first word whose prefix exceeds i
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)s.mpref[mid] > i) hi = mid; else lo = mid + 1;
+      }
+      const int w = lo - 1;
+      g = w * 32 + (int)__fns(s.mbits[w], 0, i - (int)s.mpref[w] + 1);
+      r0 = __ldg(p.g.row_ptr + g);
+      r1 = __ldg(p.g.row_ptr + g + 1);
+      const int pg = __ldg(p.g.pop + g);
+      isb = (int)c.assign[g] == st.b;
+      c.nodes[i] = g;
+      s.pop[i] = pg;
+      popsum += pg;
+      slots += r1 - r0;
+      for (int sl = r0; sl < r1; ++sl) {
+        const int h = __ldg(p.g.col_idx + sl);
+        if (h > g && is_member(s, h)) {
+          if (sl - r0 < 32) qmask |= 1u << (sl - r0); else ++extra;
+        }
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, isb);
+    if ((tid & 31) == 0 && i < n) s.oldb[i >> 5] = bal;
+    const int cnt = __popc(qmask) + extra;
+    int tot;
+    int j = m + block_excl_scan(cnt, &tot, s.misc, c.par);
+    m += tot;
+    if (cnt && j + cnt <= p.cap_edges) {
+      auto emit = [&](int sl, int h) {
         s.eu[j] = (lid_t)i;
         s.ev[j] = (lid_t)local_id(s, h);
         c.eids[j] = __ldg(p.g.slot_edge + sl);
@@ -189,10 +185,26 @@ __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
           s.ecls[j] = (uint8_t)cls;
         }
         ++j;
+      };
+      while (qmask) {
+        const int sl = r0 + (__ffs(qmask) - 1);
+        qmask &= qmask - 1;
+        emit(sl, __ldg(p.g.col_idx + sl));
+      }
+      for (int sl = r0 + 32; extra && sl < r1; ++sl) {
+        const int h = __ldg(p.g.col_idx + sl);
+        if (h > g && is_member(s, h)) emit(sl, h);
       }
     }
   }
-  __syncthreads();
+  popsum = warp_sum(popsum);
+  slots = warp_sum(slots);
+  if ((tid & 31) == 0) { atomicAdd(&s.misc[M_TOT], popsum); atomicAdd(&s.misc[M_CNT], slots); }
+  __syncthreads();  // nodes[], eids[] (global) visible to the block; totals complete
+  st.tot = s.misc[M_TOT];
+  st.m = m;
+  *d_sub_out = s.misc[M_CNT];
+  if (m > p.cap_edges || m > 65535) return RC_ERR_CAPACITY;
   return RC_OK;
 }
 
@@ -261,6 +273,17 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
       if (!(mutual && v > other)) atomicOr(&s.tflag[bp >> 21], 1u << ((bp >> 16) & 31u));
     }
     __syncthreads();
+    // C': compress the merge forest (benign race: a reader may see a pointer that is already
+    // compressed - still an ancestor) so that D needs one lookup per endpoint
+    for (int v = tid; v < n; v += T) {
+      if (s.bpos[v] == 0xffffffffu) continue;
+      int r = v, h;
+      while ((h = s.hook[r]) != r) r = h;
+      s.hook[v] = (lid_t)r;
+      s.best[v] = 0xffffffffu;  // ready for the next round (only roots stay live)
+      s.bpos[v] = 0xffffffffu;
+    }
+    __syncthreads();
     // D: relabel the live edges to the new roots and drop the ones inside a component;
     // in place: a sweep's reads all precede its writes, and it writes below what it read
     for (int base = 0; base < nlive; base += T * kCompactK) {
@@ -271,12 +294,10 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
         const int q = base + k * T + tid;
         nab[k] = 0xffffffffu;
         nj[k] = 0;
+        if (base + k * T >= nlive) break;  // block uniform
         if (q < nlive) {
           const uint32_t ab = s.lab[q];
-          int a = ab & 0xffffu, b = ab >> 16;
-          int h;
-          while ((h = s.hook[a]) != a) a = h;
-          while ((h = s.hook[b]) != b) b = h;
+          const int a = s.hook[ab & 0xffffu], b = s.hook[ab >> 16];
           if (a != b) { nab[k] = (uint32_t)a | ((uint32_t)b << 16); nj[k] = s.lj[q]; ++cnt; }
         }
       }
@@ -288,10 +309,11 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
       wbase = __shfl_sync(0xffffffffu, wbase, 31);
       int o = wbase + incl - cnt;
 #pragma unroll
-      for (int k = 0; k < kCompactK; ++k)
+      for (int k = 0; k < kCompactK; ++k) {
+        if (base + k * T >= nlive) break;
         if (nab[k] != 0xffffffffu) { s.lab[o] = nab[k]; s.lj[o] = (lid_t)nj[k]; ++o; }
+      }
     }
-    for (int i = tid; i < n; i += T) { s.best[i] = 0xffffffffu; s.bpos[i] = 0xffffffffu; }
     __syncthreads();
     nlive = s.misc[M_NLIVE];
     __syncthreads();
@@ -317,122 +339,113 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
   return RC_OK;
 }
 
-// tree adjacency (arcs grouped by tail) from te[]; fills toff, tadj, apos(slot); counts
-// the tree nodes of degree > 1 into misc[M_NINT]
-__device__ void build_tree_adjacency(Chain& c, const Step& st) {
-  const Smem& s = c.s;
-  const int tid = threadIdx.x, T = blockDim.x;
-  const int n = st.n, nt = n - 1;
-  for (int i = tid; i < n; i += T) s.cur[i] = 0;
-  if (tid == 0) s.misc[M_NINT] = 0;
-  __syncthreads();
-  for (int t = tid; t < nt; t += T) {
-    const int j = s.te[t];
-    atomicAdd(&s.cur[s.eu[j]], 1);
-    atomicAdd(&s.cur[s.ev[j]], 1);
-  }
-  __syncthreads();
-  {
-    const int per = odd_chunk(n);
-    const int lo = min(tid * per, n), hi = min(lo + per, n);
-    int sum = 0, internal = 0;
-    for (int i = lo; i < hi; ++i) { const int d = s.cur[i]; sum += d; internal += d > 1; }
-    int tot;
-    int run = block_excl_scan(sum, &tot, s.misc, c.par);
-    for (int i = lo; i < hi; ++i) { const int d = s.cur[i]; s.toff[i] = (lid_t)run; s.cur[i] = run; run += d; }
-    if (tid == 0) s.toff[n] = (lid_t)(2 * nt);
-    internal = warp_sum(internal);
-    if ((tid & 31) == 0 && internal) atomicAdd(&s.misc[M_NINT], internal);
-  }
-  __syncthreads();
-  for (int t = tid; t < nt; t += T) {
-    const int j = s.te[t];
-    const int pu = atomicAdd(&s.cur[s.eu[j]], 1);
-    s.tadj[pu] = (lid_t)(2 * t);
-    s.apos[2 * t] = (lid_t)pu;
-    const int pv = atomicAdd(&s.cur[s.ev[j]], 1);
-    s.tadj[pv] = (lid_t)(2 * t + 1);
-    s.apos[2 * t + 1] = (lid_t)pv;
-  }
-  __syncthreads();
-}
-
 // ---- P3: root the tree and compute every subtree population ----------------------------
-// Euler tour of the tree (arcs 2t: eu->ev, 2t+1: ev->eu of tree edge t), list ranking by
-// pointer doubling, prefix sum in tour order.  After this call:
-//   apos[a]  = tour position of arc a
+// Euler tour of the tree (arcs 2t: eu->ev, 2t+1: ev->eu of tree edge t), ranked by a
+// work-efficient sublist scheme (Helman-JaJa): every kStride-th arc starts a sublist; one
+// thread walks each sublist (length and weight), the few hundred sublists are ranked by
+// pointer doubling, a second walk writes each arc's tour position and exclusive weight
+// prefix.  Arc (y -> x) carries pop[x] when it is the reverse of x's first out-arc (and x is
+// not the tour root): every arc entering x lies between the arc that descends into x and
+// the one that climbs out of it, so the weights between those two sum to the population
+// below the edge, whichever way the edge turns out to be oriented.  After this call:
+//   P[a]     = tour position of arc a
 //   ent[i]   = position of the arc entering node i (0xffff for the root)
 //   cur[t]   = population below tree edge t (the side away from the root)
 // The set of balanced edges does not depend on the root, so
 // the tour is rooted wherever convenient; the reference's root only decides the labels.
+constexpr int kStrideLog = 3, kStride = 1 << kStrideLog;
+constexpr uint32_t kNone = 0xffffu;
+
 __device__ void euler_subtree_pops(Chain& c, const Step& st, int root) {
   const Smem& s = c.s;
   const int tid = threadIdx.x, T = blockDim.x;
   const int n = st.n, nt = n - 1, L = 2 * nt;
-  // successor of arc a = the arc after reverse(a) around head(a)
-  const int last = (int)s.tadj[s.toff[root + 1] - 1] ^ 1;
-  for (int a = tid; a < L; a += T) {
-    const int t = a >> 1, j = s.te[t];
-    const int head = (a & 1) ? s.eu[j] : s.ev[j];
-    int pn = s.apos[a ^ 1] + 1;
-    if (pn == s.toff[head + 1]) pn = s.toff[head];
-    s.lrA[a] = a == last ? ((uint32_t)a << 16) : (((uint32_t)s.tadj[pn] << 16) | 1u);
+  // E1/E2: out-arcs of every node as a linked list (head, nxt)
+  for (int i = tid; i < n; i += T) s.head[i] = kNone;
+  __syncthreads();
+  for (int t = tid; t < nt; t += T) {
+    const int j = s.te[t];
+    s.nxt[2 * t] = (lid_t)atomicExch(&s.head[s.eu[j]], (uint32_t)(2 * t));
+    s.nxt[2 * t + 1] = (lid_t)atomicExch(&s.head[s.ev[j]], (uint32_t)(2 * t + 1));
   }
   __syncthreads();
-  uint32_t* __restrict__ A = s.lrA;
-  uint32_t* __restrict__ B = s.lrB;
-  for (int span = 1; span < L; span <<= 1) {
-    int a = tid;
-    for (; a + 3 * T < L; a += 4 * T) {  // four independent chains per thread in flight
-      const uint32_t x0 = A[a], x1 = A[a + T], x2 = A[a + 2 * T], x3 = A[a + 3 * T];
-      const uint32_t y0 = A[x0 >> 16], y1 = A[x1 >> 16], y2 = A[x2 >> 16], y3 = A[x3 >> 16];
-      B[a] = (y0 & 0xffff0000u) | ((x0 & 0xffffu) + (y0 & 0xffffu));
-      B[a + T] = (y1 & 0xffff0000u) | ((x1 & 0xffffu) + (y1 & 0xffffu));
-      B[a + 2 * T] = (y2 & 0xffff0000u) | ((x2 & 0xffffu) + (y2 & 0xffffu));
-      B[a + 3 * T] = (y3 & 0xffff0000u) | ((x3 & 0xffffu) + (y3 & 0xffffu));
+  // E3: successor of arc a = the out-arc after reverse(a) around head(a); arc weights
+  const int first = (int)s.head[root];
+  for (int a = tid; a < L; a += T) {
+    const int j = s.te[a >> 1];
+    const int x = (a & 1) ? s.eu[j] : s.ev[j];  // node the arc enters
+    const uint32_t hx = s.head[x];
+    uint32_t nx = s.nxt[a ^ 1];
+    if (nx == kNone) nx = hx;
+    s.succ[a] = (lid_t)((int)nx == first ? a : (int)nx);  // the arc that closes the tour ends the list
+    s.W[a] = ((uint32_t)(a ^ 1) == hx && x != root) ? s.pop[x] : 0;
+  }
+  __syncthreads();
+  // E5: walk 1 - length and weight of every sublist
+  const int S = (L + kStride - 1) >> kStrideLog;
+  const bool extra = (first & (kStride - 1)) != 0;  // the tour head is not a regular splitter
+  const int S1 = S + (extra ? 1 : 0);
+  auto split_id = [&](int a) { return a == first ? (extra ? S : (a >> kStrideLog)) : ((a & (kStride - 1)) == 0 ? (a >> kStrideLog) : -1); };
+  uint32_t* __restrict__ XA = s.spX;
+  uint32_t* __restrict__ XB = s.spX + s.spCap;
+  int32_t* __restrict__ YA = s.spY;
+  int32_t* __restrict__ YB = s.spY + s.spCap;
+  for (int k = tid; k < S1; k += T) {
+    int a = k < S ? (k << kStrideLog) : first;
+    int len = 0, w = 0, next = k;
+    for (;;) {
+      w += s.W[a];
+      ++len;
+      const int nx = s.succ[a];
+      if (nx == a) { next = k; s.misc[M_TAILLEN] = len; len = 0; w = 0; break; }  // terminal sublist
+      const int sid = split_id(nx);
+      if (sid >= 0) { next = sid; break; }
+      a = nx;
     }
-    for (; a < L; a += T) {
-      const uint32_t x = A[a];
-      const uint32_t y = A[x >> 16];
-      B[a] = (y & 0xffff0000u) | ((x & 0xffffu) + (y & 0xffffu));
+    XA[k] = ((uint32_t)next << 16) | (uint32_t)len;
+    YA[k] = w;
+  }
+  __syncthreads();
+  // E6: rank the sublists (distance / weight from the start of sublist k to the terminal one)
+  for (int span = 1; span < S1; span <<= 1) {
+    for (int k = tid; k < S1; k += T) {
+      const uint32_t x = XA[k];
+      const uint32_t y = XA[x >> 16];
+      XB[k] = (y & 0xffff0000u) | ((x & 0xffffu) + (y & 0xffffu));
+      YB[k] = YA[k] + YA[x >> 16];
     }
     __syncthreads();
-    uint32_t* tmp = A; A = B; B = tmp;
+    uint32_t* tx = XA; XA = XB; XB = tx;
+    int32_t* ty = YA; YA = YB; YB = ty;
   }
-  // tour positions; B is free and becomes the weight / prefix-sum array
-  int32_t* W = reinterpret_cast<int32_t*>(B);
-  for (int a = tid; a < L; a += T) s.apos[a] = (lid_t)(L - 1 - (int)(A[a] & 0xffffu));
+  // E7: walk 2 - tour position and exclusive weight prefix (up to a constant) of every arc
+  const int tail0 = L - s.misc[M_TAILLEN];
+  for (int k = tid; k < S1; k += T) {
+    int a = k < S ? (k << kStrideLog) : first;
+    int pos = tail0 - (int)(XA[k] & 0xffffu);
+    int w = -YA[k];
+    for (;;) {
+      const int wa = s.W[a];
+      s.P[a] = (lid_t)pos;
+      s.W[a] = w;
+      ++pos;
+      w += wa;
+      const int nx = s.succ[a];
+      if (nx == a || split_id(nx) >= 0) break;
+      a = nx;
+    }
+  }
   if (tid == 0) s.ent[root] = 0xffffu;
   __syncthreads();
+  // E8: population below every tree edge (cur aliases succ, which is dead now)
   for (int t = tid; t < nt; t += T) {
     const int j = s.te[t];
-    const int p0 = s.apos[2 * t], p1 = s.apos[2 * t + 1];
+    const int p0 = s.P[2 * t], p1 = s.P[2 * t + 1];
     const bool down0 = p0 < p1;  // arc 2t (eu -> ev) points away from the root
     const int child = down0 ? s.ev[j] : s.eu[j];
-    const int pd = down0 ? p0 : p1, pu = down0 ? p1 : p0;
-    W[pd] = s.pop[child];
-    W[pu] = 0;
-    s.ent[child] = (lid_t)pd;
-  }
-  __syncthreads();
-  // inclusive prefix sum of W[0..L)
-  {
-    const int per = odd_chunk(L);
-    const int lo = min(tid * per, L), hi = min(lo + per, L);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += W[i];
-    int tot;
-    int run = block_excl_scan(sum, &tot, s.misc, c.par);
-    for (int i = lo; i < hi; ++i) { run += W[i]; W[i] = run; }
-  }
-  __syncthreads();
-  for (int t = tid; t < nt; t += T) {
-    const int j = s.te[t];
-    const int p0 = s.apos[2 * t], p1 = s.apos[2 * t + 1];
-    const bool down0 = p0 < p1;
-    const int child = down0 ? s.ev[j] : s.eu[j];
-    const int pd = down0 ? p0 : p1, pu = down0 ? p1 : p0;
-    s.cur[t] = W[pu] - W[pd] + s.pop[child];
+    s.ent[child] = (lid_t)(down0 ? p0 : p1);
+    const int w0 = s.W[2 * t], w1 = s.W[2 * t + 1];
+    s.cur[t] = down0 ? w1 - w0 : w0 - w1;
   }
   __syncthreads();
 }
@@ -608,10 +621,9 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
     if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_ROUNDS] += rounds; }
     res.trees = (int)tree_no + 1;
     if (res.status) return res;
-    build_tree_adjacency(c, st);
-    // tree.py:377: the root is drawn among tree nodes of degree > 1 (none: IndexError)
-    const int n_int = s.misc[M_NINT];
-    if (n_int == 0) { res.status = RC_ERR_NO_ROOT; return res; }
+    // tree.py:377: the root is drawn among tree nodes of degree > 1 (none: IndexError);
+    // only the two-node tree has none
+    if (n < 3) { res.status = RC_ERR_NO_ROOT; return res; }
     // ---- P3
     euler_subtree_pops(c, st, r0);
     // ---- P4: balanced tree edges (cur[t] = population below edge t)
@@ -630,15 +642,23 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
     if (nbal > 0) {
       const bool last_rec = rs && (int)tree_no == n_rec - 1;
       if (rs && !last_rec) { res.status = RC_ERR_REPLAY; return res; }
+      auto internal = [&](int i) { return s.nxt[s.head[i]] != kNone; };  // tree degree > 1
       // ---- root (tree.py:377): uniform over tree nodes of degree > 1, ascending node index
       if (last_rec) {
         const int gr = rs->root;
         root = (gr >= 0 && gr < p.g.N && is_member(s, gr)) ? local_id(s, gr) : -1;
-        if (root < 0 || s.toff[root + 1] - s.toff[root] < 2) { res.status = RC_ERR_REPLAY; return res; }
+        if (root < 0 || !internal(root)) { res.status = RC_ERR_REPLAY; return res; }
       } else {
+        if (tid == 0) s.misc[M_NINT] = 0;
+        __syncthreads();
+        int cnt = 0;
+        for (int i = tid; i < n; i += T) cnt += internal(i) ? 1 : 0;
+        cnt = warp_sum(cnt);
+        if ((tid & 31) == 0 && cnt) atomicAdd(&s.misc[M_NINT], cnt);
+        __syncthreads();
+        const int n_int = s.misc[M_NINT];
         RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_ROOT, 0, tree_no, prop_no, 0);
-        root = select_kth(c, n, (int)rc_below(r.v[0], r.v[1], (uint32_t)n_int),
-                          [&](int i) { return s.toff[i + 1] - s.toff[i] > 1; });
+        root = select_kth(c, n, (int)rc_below(r.v[0], r.v[1], (uint32_t)n_int), internal);
       }
       // ---- P5
       const int policy = p.cfg.tree_kind == RC_TREE_WILSON ? RC_CUT_UNIFORM : p.cfg.cut_policy;
@@ -668,7 +688,7 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
   break;
   }  // pair loop
   // ---- P6: the side holding the reference's root keeps the lower id (tree.py:421, :947-950)
-  const int pa = s.apos[2 * tstar], pb = s.apos[2 * tstar + 1];
+  const int pa = s.P[2 * tstar], pb = s.P[2 * tstar + 1];
   const int pd = min(pa, pb), pu = max(pa, pb);
   auto below = [&](int i) { const int en = s.ent[i]; return en != 0xffff && en >= pd && en <= pu; };
   const bool root_below = below(root);
@@ -687,18 +707,29 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
   // side(i): node i is cut away from the root's side and takes the higher id b
   auto side = [&](int i) { return below(i) != root_below; };
   if (tid == 0) s.misc[M_DELTA] = 0;
+  for (int i0 = 0; i0 < st.n; i0 += T) {  // partition/assignment.py:76-86
+    const int i = i0 + tid;
+    const bool sd = i < st.n && side(i);
+    const uint32_t bal = __ballot_sync(0xffffffffu, sd);
+    if (i < st.n) {
+      if ((tid & 31) == 0) s.newb[i >> 5] = bal;
+      if (sd != (bool)((s.oldb[i >> 5] >> (i & 31)) & 1u)) c.assign[c.nodes[i]] = (uint8_t)(sd ? st.b : st.a);
+    }
+  }
   __syncthreads();
   int delta = 0;
-  for (int j = tid; j < st.m; j += T) {
-    const bool now = side(s.eu[j]) != side(s.ev[j]);
-    const int eid = c.eids[j];
-    const uint32_t bit = 1u << (eid & 31);
-    const uint32_t old = now ? atomicOr(c.mask + (eid >> 5), bit) : atomicAnd(c.mask + (eid >> 5), ~bit);
-    delta += (int)now - (int)((old & bit) != 0);
+  for (int j = tid; j < st.m; j += T) {  // updaters/cut_edges.py:118-120
+    const int u = s.eu[j], v = s.ev[j];
+    const bool was = ((s.oldb[u >> 5] >> (u & 31)) ^ (s.oldb[v >> 5] >> (v & 31))) & 1u;
+    const bool now = ((s.newb[u >> 5] >> (u & 31)) ^ (s.newb[v >> 5] >> (v & 31))) & 1u;
+    if (now != was) {
+      const int eid = c.eids[j];
+      atomicXor(c.mask + (eid >> 5), 1u << (eid & 31));
+      delta += (int)now - (int)was;
+    }
   }
   delta = warp_sum(delta);
   if ((tid & 31) == 0 && delta) atomicAdd(&s.misc[M_DELTA], delta);
-  for (int i = tid; i < st.n; i += T) c.assign[c.nodes[i]] = (uint8_t)(side(i) ? st.b : st.a);
   __syncthreads();
   if (tid == 0) {
     c.tally[st.a] = pop_a;  // updaters/tally.py:162-165
