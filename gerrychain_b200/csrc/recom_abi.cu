@@ -42,7 +42,7 @@ struct RcEngine {
   rc::Params p{};
   bool bound = false;
   int grid = 0, threads = 0, ctas_per_sm = 0, n_sms = 0;
-  size_t smem = 0, scratch_bytes = 0;
+  size_t smem = 0, scratch_bytes = 0, sched_bytes = 0;
   int64_t launches = 0;
   // owned device memory
   int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_slot_edge = nullptr, *d_edge_uv = nullptr,
@@ -146,19 +146,24 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   e->threads = (e->threads + 31) & ~31;
   CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->ctas_per_sm, rc::recom_step_kernel, e->threads, e->smem));
   if (e->ctas_per_sm < 1) { rc_engine_destroy(e); return fail(RC_ERR_CAPACITY, "kernel does not fit an SM"); }
-  e->grid = cfg->n_chains;  // one CTA per chain; the hardware scheduler refills SMs
+  // persistent grid: every CTA resident, (chain, step) tickets handed out in order
+  e->grid = e->ctas_per_sm * e->n_sms;
+  if (e->grid > cfg->n_chains) e->grid = cfg->n_chains;
   // scratch
   size_t b_nodes = (size_t)e->grid * cap_nodes * sizeof(int32_t);
   size_t b_eids = (size_t)e->grid * cap_edges * sizeof(int32_t);
   size_t b_bad = cfg->allow_pair_reselection ? (size_t)e->grid * 2048 * sizeof(uint32_t) : 0;
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-  e->scratch_bytes = al(b_nodes) + al(b_eids) + al(b_bad) + 256;
+  size_t b_prog = 256 + (size_t)cfg->n_chains * sizeof(int32_t);
+  e->scratch_bytes = al(b_nodes) + al(b_eids) + al(b_bad) + al(b_prog);
   CUDA_OK(cudaMalloc(&e->d_scratch, e->scratch_bytes));
   char* base = (char*)e->d_scratch;
   p.nodes = (int32_t*)base; base += al(b_nodes);
   p.eids = (int32_t*)base; base += al(b_eids);
   p.badpairs = b_bad ? (uint32_t*)base : nullptr; base += al(b_bad);
-  p.work_counter = (int32_t*)base;
+  p.work_counter = (unsigned long long*)base;
+  p.progress = (int32_t*)(base + 256);
+  e->sched_bytes = b_prog;
   CUDA_OK(cudaEventCreate(&e->ev0));
   CUDA_OK(cudaEventCreate(&e->ev1));
   *out = e;
@@ -205,6 +210,7 @@ int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream) {
   p.n_steps = n_steps;
   cudaStream_t s = (cudaStream_t)stream;
   CUDA_OK(cudaEventRecord(e->ev0, s));
+  CUDA_OK(cudaMemsetAsync(p.work_counter, 0, e->sched_bytes, s));
   rc::recom_step_kernel<<<e->grid, e->threads, e->smem, s>>>(p);
   e->launches++;
   CUDA_OK(cudaGetLastError());

@@ -40,7 +40,8 @@ struct Params {
   int32_t* nodes;     // [grid][cap_nodes] local -> global node
   int32_t* eids;      // [grid][cap_edges] local edge -> global edge id
   uint32_t* badpairs; // [grid][2048] bitset of (a*256+b), pair reselection only
-  int32_t* work_counter;  // persistent scheduling ticket
+  unsigned long long* work_counter;  // persistent scheduling: next (chain, step) ticket
+  int32_t* progress;      // [n_chains] steps of this launch completed per chain
   int32_t keep_counters;  // init_state_kernel: leave step/proposal numbers and counters alone
 };
 

@@ -153,7 +153,7 @@ __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
       r0 = __ldg(p.g.row_ptr + g);
       r1 = __ldg(p.g.row_ptr + g + 1);
       const int pg = __ldg(p.g.pop + g);
-      isb = (int)c.assign[g] == st.b;
+      isb = (int)__ldcg(c.assign + g) == st.b;
       c.nodes[i] = g;
       s.pop[i] = pg;
       popsum += pg;
@@ -590,7 +590,7 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
     if (e < 0) { res.status = RC_ERR_NO_CUT_EDGES; return res; }
   }
   {
-    const int la = c.assign[p.g.edge_uv[2 * e]], lb = c.assign[p.g.edge_uv[2 * e + 1]];
+    const int la = __ldcg(c.assign + p.g.edge_uv[2 * e]), lb = __ldcg(c.assign + p.g.edge_uv[2 * e + 1]);
     st.a = min(la, lb); st.b = max(la, lb);  // tree_proposals.py:113
   }
   if (resel && ((bad[(st.a * 256 + st.b) >> 5] >> ((st.a * 256 + st.b) & 31)) & 1)) continue;
@@ -743,58 +743,98 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
 }
 
 // =========================================================================================
+__device__ __forceinline__ int ld_acquire(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int32_t* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Free-running mode is a persistent grid: CTAs draw (chain, step) tickets from a global
+// counter, so every SM stays busy whatever the number of chains and however unevenly the
+// retries fall.  Step s of a chain waits (acquire) for step s-1 of the same chain, which an
+// earlier ticket - held by a CTA that is resident by construction - publishes (release).
+// Replay mode (TEST HOOK) is one CTA walking one chain through the record.
 __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Chain c;
   c.p = &p;
   smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R);
   const int tid = threadIdx.x;
-  const bool replay = p.rp.n_steps > 0;
-  c.chain = replay ? p.rp.chain : (int)blockIdx.x;
-  c.gchain = (uint32_t)(c.chain + p.cfg.chain_offset);
-  c.assign = p.st.d_assignment + (size_t)c.chain * p.st.assign_stride;
-  c.mask = p.st.d_cut_mask + (size_t)c.chain * p.st.mask_stride;
-  c.tally = p.st.d_tally + (size_t)c.chain * p.cfg.n_districts;
   c.nodes = p.nodes + (size_t)blockIdx.x * p.cap_nodes;
   c.eids = p.eids + (size_t)blockIdx.x * p.cap_edges;
   c.par = 0;
   int32_t* ctr = c.s.misc + M_CTR;  // [RC_N_COUNTERS]
   if (tid < RC_N_COUNTERS) ctr[tid] = 0;
   __syncthreads();
-  if (p.st.d_status[c.chain] != RC_OK) return;
-  uint32_t prop_no = p.st.d_proposal_no[c.chain];
+  const bool replay = p.rp.n_steps > 0;
+  const long long n_chains = p.cfg.n_chains;
+  const unsigned long long total =
+      replay ? (unsigned long long)p.rp.n_steps : (unsigned long long)n_chains * (unsigned long long)p.n_steps;
   const int streak_cap = p.cfg.max_invalid_streak > 0 ? p.cfg.max_invalid_streak : 1000;
-  const long long n_steps = replay ? p.rp.n_steps : p.n_steps;
-  int status = RC_OK;
-  long long done = 0;
-  for (long long sidx = 0; sidx < n_steps && status == RC_OK; ++sidx) {
-    const RcReplayStep* rs = replay ? p.rp.steps + sidx : nullptr;
-    ProposalResult r = {RC_OK, 0, 0, 0};
-    int streak = 0;
-    for (; streak < streak_cap; ++streak) {
-      r = propose(c, replay ? (uint32_t)sidx : prop_no, rs, ctr);
-      ++prop_no;
-      __syncthreads();
-      if (r.status || r.accepted || replay) break;
-    }
-    status = r.status;
-    if (status == RC_OK && !r.accepted) status = RC_ERR_INVALID_STREAK;
-    if (status == RC_OK) ++done;
+  unsigned long long* ticket = reinterpret_cast<unsigned long long*>(&c.s.misc[M_BEST64]);
+  unsigned long long rt = 0;  // replay: steps are taken in order
+  for (;;) {
+    unsigned long long t;
     if (replay) {
-      if (p.rp.info_trace && tid == 0) {
-        int32_t* inf = p.rp.info_trace + 4 * sidx;
-        inf[0] = r.trees; inf[1] = r.nbal; inf[2] = p.st.d_cut_count[c.chain]; inf[3] = status;
-      }
-      if (p.rp.assign_trace)
-        for (int i = tid; i < p.g.N; i += blockDim.x) p.rp.assign_trace[(size_t)sidx * p.g.N + i] = c.assign[i];
+      t = rt++;
+    } else {
+      if (tid == 0) *ticket = atomicAdd(p.work_counter, 1ull);
+      __syncthreads();
+      t = *ticket;
       __syncthreads();
     }
-  }
-  if (tid == 0) {
-    p.st.d_proposal_no[c.chain] = prop_no;
-    p.st.d_step_no[c.chain] += done;
-    if (status != RC_OK) p.st.d_status[c.chain] = status;
-    for (int i = 0; i < RC_N_COUNTERS; ++i) p.st.d_counters[(size_t)c.chain * RC_N_COUNTERS + i] += ctr[i];
+    if (t >= total) break;
+    const int chain = replay ? p.rp.chain : (int)(t % (unsigned long long)n_chains);
+    const int seg = replay ? 0 : (int)(t / (unsigned long long)n_chains);
+    c.chain = chain;
+    c.gchain = (uint32_t)(chain + p.cfg.chain_offset);
+    c.assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
+    c.mask = p.st.d_cut_mask + (size_t)chain * p.st.mask_stride;
+    c.tally = p.st.d_tally + (size_t)chain * p.cfg.n_districts;
+    if (!replay) {
+      if (tid == 0)
+        while (ld_acquire(p.progress + chain) < seg) __nanosleep(64);
+      __syncthreads();
+    }
+    int status = __ldcg(p.st.d_status + chain);
+    if (status == RC_OK) {
+      // one accepted step (chain.py:185-195): propose until valid, accept always
+      uint32_t prop_no = __ldcg(p.st.d_proposal_no + chain);
+      const RcReplayStep* rs = replay ? p.rp.steps + t : nullptr;
+      ProposalResult r = {RC_OK, 0, 0, 0};
+      for (int streak = 0; streak < streak_cap; ++streak) {
+        r = propose(c, replay ? (uint32_t)t : prop_no, rs, ctr);
+        ++prop_no;
+        __syncthreads();
+        if (r.status || r.accepted || replay) break;
+      }
+      status = r.status ? r.status : (r.accepted ? RC_OK : RC_ERR_INVALID_STREAK);
+      if (tid == 0) {
+        p.st.d_proposal_no[chain] = prop_no;
+        if (status == RC_OK) p.st.d_step_no[chain] = __ldcg(p.st.d_step_no + chain) + 1;
+        else p.st.d_status[chain] = status;
+      }
+      if (tid < RC_N_COUNTERS) {
+        int64_t* g = p.st.d_counters + (size_t)chain * RC_N_COUNTERS + tid;
+        *g = __ldcg(g) + ctr[tid];
+        ctr[tid] = 0;
+      }
+      if (replay) {
+        if (p.rp.info_trace && tid == 0) {
+          int32_t* inf = p.rp.info_trace + 4 * t;
+          inf[0] = r.trees; inf[1] = r.nbal; inf[2] = p.st.d_cut_count[chain]; inf[3] = status;
+        }
+        if (p.rp.assign_trace)
+          for (int i = tid; i < p.g.N; i += blockDim.x) p.rp.assign_trace[(size_t)t * p.g.N + i] = c.assign[i];
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (!replay && tid == 0) st_release(p.progress + chain, seg + 1);
+    if (replay && status != RC_OK) break;
   }
 }
 
