@@ -64,6 +64,8 @@ class GraphContext:
     def column(self, fields) -> np.ndarray:
         """Integer node-attribute column (sum of ``fields``) in node-index order."""
         g = self.graph
+        if fields is None:  # no attribute needed (cut edges only): unit weights
+            return np.ones(self.n_nodes, dtype=np.int64)
         if isinstance(fields, str):
             fields = (fields,)
         col = np.zeros(self.n_nodes, dtype=np.float64)
@@ -77,14 +79,19 @@ class GraphContext:
     def csr(self, fields, region_surcharge=None) -> GraphCSR:
         if isinstance(fields, str):
             fields = (fields,)
-        fields = tuple(fields)
+        if fields is None and self._csr:  # any cached column serves when only the edges matter
+            return next(iter(self._csr.values()))
+        fields = tuple(fields) if fields is not None else None
         rkey = tuple(region_surcharge.items()) if region_surcharge else ()
         key = (fields, rkey)
         csr = self._csr.get(key)
         if csr is None:
             base = self._csr.get((fields, ()))
             if base is None:
-                base = csr_from_edges(self.n_nodes, self.edges, self.column(fields), node_labels=self.labels)
+                col = self.column(fields)
+                if np.abs(col).sum() >= 2**31:
+                    raise OverflowError(f"total of {fields!r} must fit in int32")
+                base = csr_from_edges(self.n_nodes, self.edges, col, node_labels=self.labels)
                 self._csr[(fields, ())] = base
             csr = base
             if region_surcharge:
@@ -119,7 +126,9 @@ class GraphContext:
     # -- engines ---------------------------------------------------------------------
     def engine(self, key: Tuple, fields, k: int, region_surcharge=None, **cfg_kw):
         """One single-chain device engine per distinct (column, configuration)."""
-        full = (key, tuple(fields) if not isinstance(fields, str) else (fields,), k)
+        if isinstance(fields, str):
+            fields = (fields,)
+        full = (key, tuple(fields) if fields is not None else None, k)
         eng = self._engines.get(full)
         if eng is None:
             from .engine import Engine

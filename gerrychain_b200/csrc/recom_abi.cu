@@ -229,13 +229,18 @@ int rc_engine_step_host(RcEngine* e, const uint8_t* h_assignment, int64_t h_stri
   CUDA_OK(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
   const RcState& st = e->p.st;
-  CUDA_OK(cudaMemcpy2DAsync(st.d_assignment, (size_t)st.assign_stride, h_assignment, (size_t)h_stride,
-                            (size_t)N, (size_t)n, cudaMemcpyHostToDevice, s));
+  if (h_stride == st.assign_stride)  // same pitch on both sides: one contiguous copy
+    CUDA_OK(cudaMemcpyAsync(st.d_assignment, h_assignment, (size_t)h_stride * n, cudaMemcpyHostToDevice, s));
+  else
+    CUDA_OK(cudaMemcpy2DAsync(st.d_assignment, (size_t)st.assign_stride, h_assignment, (size_t)h_stride,
+                              (size_t)N, (size_t)n, cudaMemcpyHostToDevice, s));
   int rc = init_state_impl(e, stream, 1);
   if (rc) return rc;
   rc = rc_engine_run(e, n_steps, stream);
   if (rc) return rc;
-  if (h_assignment_out)
+  if (h_assignment_out && h_stride == st.assign_stride)
+    CUDA_OK(cudaMemcpyAsync(h_assignment_out, st.d_assignment, (size_t)h_stride * n, cudaMemcpyDeviceToHost, s));
+  else if (h_assignment_out)
     CUDA_OK(cudaMemcpy2DAsync(h_assignment_out, (size_t)h_stride, st.d_assignment, (size_t)st.assign_stride,
                               (size_t)N, (size_t)n, cudaMemcpyDeviceToHost, s));
   if (h_tally_out)

@@ -124,7 +124,8 @@ class Engine:
         """Pinned host buffers shaped for :meth:`step_host` (assignment, tally, cut_count, status)."""
         t = self.torch
         n, k = self.cfg.n_chains, self.cfg.n_districts
-        return (t.empty((n, self.csr.n_nodes), dtype=t.uint8).pin_memory(),
+        # rows padded to the device pitch: each direction is then one contiguous copy
+        return (t.zeros((n, self.assign_stride), dtype=t.uint8).pin_memory()[:, : self.csr.n_nodes],
                 t.empty((n, k), dtype=t.int64).pin_memory(),
                 t.empty(n, dtype=t.int32).pin_memory(),
                 t.empty(n, dtype=t.int32).pin_memory())
@@ -139,11 +140,16 @@ class Engine:
                 return None
             return x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data
 
+        def pitch(x):
+            return int(x.stride(0)) if hasattr(x, "data_ptr") else int(x.strides[0])
+
         n, N = self.cfg.n_chains, self.csr.n_nodes
         if tuple(h_assignment.shape) != (n, N):
             raise ValueError("h_assignment must be [n_chains, N] uint8")
+        if h_out is not None and (tuple(h_out.shape) != (n, N) or pitch(h_out) != pitch(h_assignment)):
+            raise ValueError("h_out must have the shape and row pitch of h_assignment")
         _check(self.lib, self.lib.rc_engine_step_host(
-            self._handle, ptr(h_assignment), N, int(n_steps), ptr(h_out), ptr(h_tally),
+            self._handle, ptr(h_assignment), pitch(h_assignment), int(n_steps), ptr(h_out), ptr(h_tally),
             ptr(h_cut_count), ptr(h_status), self._stream()))
         return self
 

@@ -188,7 +188,8 @@ int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream);
  * and copies back: the assignment (same layout, may alias h_assignment), Tally
  * [n_chains][k] int64, len(cut_edges) [n_chains] int32 and the per-chain status
  * [n_chains] int32 (any of the outputs may be NULL).  Host buffers should be pinned
- * (cudaHostAlloc / torch pin_memory) for the copies to be asynchronous.  Synchronises
+ * (cudaHostAlloc / torch pin_memory) for the copies to be asynchronous; with h_stride equal
+ * to the device pitch (rc_state_strides) each direction is one contiguous copy.  Synchronises
  * `stream` before returning.  This is what one MarkovChain batch costs a caller who keeps
  * its partitions on the host, as the reference does (chain.py:166-196). */
 int rc_engine_step_host(RcEngine* e, const uint8_t* h_assignment, int64_t h_stride,

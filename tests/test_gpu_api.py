@@ -1,0 +1,192 @@
+"""GPU tests of the GerryChain-shaped API: the reference's own hot-path tests, run against
+the CUDA engine: recom as a proposal keeps districts contiguous
+(reference tests/test_tree.py:291-302), incremental cut_edges / Tally == naive recomputation
+at every step (tests/updaters/test_cut_edges.py:128-161, tests/test_tally.py:56-76), the
+chain's step accounting (tests/test_chain.py), the max_attempts error and warn_attempts
+warning (tests/test_region_aware.py:102-112, :236-250), and the batched runner against the
+oracle."""
+
+import functools
+import random
+import warnings
+
+import networkx
+import numpy as np
+import pytest
+
+import gerrychain_b200 as gc
+from gerrychain_b200 import Grid, MarkovChain, Partition, Tally, cut_edges, recom
+from gerrychain_b200.accept import always_accept
+from gerrychain_b200.constraints import within_percent_of_ideal_population
+
+pytestmark = pytest.mark.gpu
+
+
+def _contiguous(partition):
+    g = partition.graph
+    return all(networkx.is_connected(g.subgraph(nodes)) for nodes in partition.parts.values())
+
+
+def _naive_cut_edges(partition):
+    m = partition.assignment.mapping
+    return {tuple(sorted(e)) for e in partition.graph.edges if m[e[0]] != m[e[1]]}
+
+
+def _naive_tally(partition, field):
+    out = {}
+    for node, part in partition.assignment.items():
+        out[part] = out.get(part, 0) + partition.graph.nodes[node][field]
+    return out
+
+
+def _three_by_three():
+    g = networkx.grid_2d_graph(3, 3)
+    g = networkx.convert_node_labels_to_integers(g)
+    for n in g.nodes:
+        g.nodes[n]["pop"] = 1
+    return g
+
+
+def test_recom_works_as_a_proposal():
+    graph = _three_by_three()
+    partition = Partition(graph, {0: 1, 1: 1, 2: 1, 3: 1, 4: 1, 5: 2, 6: 2, 7: 2, 8: 2}, {"pop": Tally("pop")})
+    ideal = sum(partition["pop"].values()) / 2
+    proposal = functools.partial(recom, pop_col="pop", pop_target=ideal, epsilon=0.25, node_repeats=5)
+    constraints = [within_percent_of_ideal_population(partition, 0.25, "pop")]
+    chain = MarkovChain(proposal, constraints, always_accept, partition, total_steps=100)
+    n = 0
+    for state in chain:
+        assert _contiguous(state)
+        assert set(state["pop"].values()) <= {4, 5}
+        n += 1
+    assert n == 100
+
+
+def test_grid_chain_incremental_updaters_equal_naive():
+    random.seed(2024)
+    grid = Grid((10, 10), with_diagonals=True)
+    ideal = sum(grid["population"].values()) / len(grid)
+    assert grid["cut_edges"] == _naive_cut_edges(grid)
+    proposal = functools.partial(recom, pop_col="population", pop_target=ideal, epsilon=0.5, node_repeats=1)
+    chain = MarkovChain(proposal, [within_percent_of_ideal_population(grid, 0.5)], always_accept, grid, 60)
+    states = []
+    for state in chain:
+        assert state["cut_edges"] == _naive_cut_edges(state)
+        assert state["population"] == _naive_tally(state, "population")
+        assert state["area"] == _naive_tally(state, "area")
+        assert len(state["cut_edges"]) == state.n_cut_edges
+        assert _contiguous(state)
+        states.append(state)
+    assert states[0] is grid and len(states) == 60
+    assert isinstance(states[-1], Grid) and states[-1].dimensions == (10, 10)
+    child = states[-1]
+    assert child.parent is not None and child.flips
+    merged = set(child.flips)
+    touched = {child.parent.assignment.mapping[n] for n in merged}
+    assert len(touched) == 2  # flips list every node of the two merged districts (tree.py:947-961)
+    assert merged == set().union(*(child.parent.parts[d] for d in touched))
+    assert len({tuple(s.assignment_vector()) for s in states}) > 10
+
+
+def test_flip_and_first_time_scans():
+    grid = Grid((6, 6))
+    flipped = grid.flip({(2, 2): 1, (2, 3): 1})
+    assert flipped["cut_edges"] == _naive_cut_edges(flipped)
+    assert flipped["population"] == _naive_tally(flipped, "population")
+    assert flipped.crosses_parts(((2, 2), (2, 1))) != grid.crosses_parts(((2, 2), (2, 1)))
+    assert repr(grid).startswith("6x6 Grid")
+    with pytest.raises(KeyError):
+        Partition(grid.graph, {(0, 0): 1}, {})
+    with pytest.raises(TypeError):
+        Partition(42, {}, {})
+
+
+def test_same_seed_same_chain():
+    def run(seed):
+        random.seed(seed)
+        grid = Grid((12, 12))
+        ideal = sum(grid["population"].values()) / 4
+        p = functools.partial(recom, pop_col="population", pop_target=ideal, epsilon=0.1)
+        chain = MarkovChain(p, [within_percent_of_ideal_population(grid, 0.1)], always_accept, grid, 30)
+        return [s.assignment_vector().tobytes() for s in chain]
+
+    assert run(7) == run(7)
+    assert run(7) != run(8)
+
+
+def test_max_attempts_raises_like_the_reference():
+    random.seed(0)
+    grid = Grid((20, 20))
+    ideal = sum(grid["population"].values()) / 4
+    method = functools.partial(gc.bipartition_tree, max_attempts=1)
+    p = functools.partial(recom, pop_col="population", pop_target=ideal, epsilon=0.01, method=method)
+    chain = MarkovChain(p, [within_percent_of_ideal_population(grid, 0.01)], always_accept, grid, 200)
+    with pytest.raises(RuntimeError, match="Could not find a possible cut after 1 attempts."):
+        for _ in chain:
+            pass
+
+
+def test_warn_attempts_warns_like_the_reference():
+    random.seed(0)
+    grid = Grid((20, 20))
+    ideal = sum(grid["population"].values()) / 4
+    method = functools.partial(gc.bipartition_tree, warn_attempts=2)
+    p = functools.partial(recom, pop_col="population", pop_target=ideal, epsilon=0.01, method=method)
+    chain = MarkovChain(p, [within_percent_of_ideal_population(grid, 0.01)], always_accept, grid, 60)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        for _ in chain:
+            pass
+    assert any(issubclass(x.category, gc.BipartitionWarning) and
+               "Failed to find a balanced cut after 2 attempts." in str(x.message) for x in w)
+
+
+def test_region_aware_recom_through_the_api():
+    random.seed(1)
+    g = networkx.grid_2d_graph(8, 8)
+    for (i, j) in g.nodes:
+        g.nodes[(i, j)].update(TOTPOP=1, county=i // 4 * 2 + j // 4, district=i // 2)
+    part = Partition(g, "district", {"population": Tally("TOTPOP", alias="population"), "cut_edges": cut_edges})
+    p = functools.partial(recom, pop_col="TOTPOP", pop_target=16, epsilon=0.1, region_surcharge={"county": 2.0})
+    chain = MarkovChain(p, [within_percent_of_ideal_population(part, 0.1)], always_accept, part, 80)
+    last = None
+    for state in chain:
+        assert _contiguous(state)
+        last = state
+    # a surcharge of 2.0 keeps trees inside counties: few county-splitting edges are cut
+    county = {n: g.nodes[n]["county"] for n in g.nodes}
+    splits = sum(len({county[n] for n in nodes}) > 1 for nodes in last.parts.values())
+    assert splits <= 2
+
+
+def test_batched_markov_chain_matches_oracle_and_api():
+    from oracle import oracle
+    from gerrychain_b200 import BatchedMarkovChain
+    from gerrychain_b200.config import EngineConfig
+
+    grid = Grid((20, 20))
+    ideal = sum(grid["population"].values()) / 4
+    p = functools.partial(recom, pop_col="population", pop_target=ideal, epsilon=0.05)
+    cons = [within_percent_of_ideal_population(grid, 0.05)]
+    runner = BatchedMarkovChain(p, cons, always_accept, grid, total_steps=41, n_chains=48, seed=99)
+    batches = list(runner)
+    assert len(batches) == 41 and batches[0].step == 1 and batches[-1].step == 41
+    last = batches[-1]
+    eng = runner.engine
+    cfg = EngineConfig(n_districts=4, n_chains=48, pop_target=ideal, epsilon=0.05, seed=99,
+                       pop_lower=cons[0].bounds[0], pop_upper=cons[0].bounds[1])
+    ora = oracle.OracleChains(eng.csr, cfg, grid.assignment_vector()).run(40, n_threads=4)
+    assert np.array_equal(last.assignment.cpu().numpy(), ora.assignments())
+    assert np.array_equal(last.cut_edge_counts(), ora.cut_count)
+    assert np.array_equal(last.population(), ora.tally)
+    part = last.partition(5)
+    assert part["cut_edges"] == _naive_cut_edges(part)
+    assert part["population"] == _naive_tally(part, "population")
+    assert len(part["cut_edges"]) == int(ora.cut_count[5])
+    cut, dev = last.histograms(256, 64, 0.001)
+    assert int(cut.sum()) == 48 and int(dev.sum()) == 48
+    # run_to_end from a fresh iterator gives the same ensemble in one launch
+    runner2 = BatchedMarkovChain(p, cons, always_accept, grid, total_steps=41, n_chains=48, seed=99)
+    assert np.array_equal(runner2.run_to_end().assignment.cpu().numpy(), ora.assignments())
+    with pytest.raises(TypeError):
+        BatchedMarkovChain(p, cons, lambda s: True, grid, 10, 4)

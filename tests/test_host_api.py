@@ -1,0 +1,179 @@
+"""CPU tests of the host-side mirror of GerryChain's interface (no GPU, no engine):
+MarkovChain's iterator contract (reference tests/test_chain.py:23-88), Validator / Bounds
+(reference tests/constraints/test_bounds.py:5-43, test_validity.py), recom-argument parsing,
+chain sharding and the histogram all-reduce over gloo (world_size 2)."""
+
+import functools
+import os
+import subprocess
+import sys
+import textwrap
+from unittest.mock import MagicMock
+
+import pytest
+
+import gerrychain_b200 as gc
+from gerrychain_b200 import _abi
+from gerrychain_b200.chain import MarkovChain, _device_bounds, _recom_arguments
+from gerrychain_b200.constraints import Bounds, Validator, within_percent_of_ideal_population
+from gerrychain_b200.distributed import shard_chains
+from gerrychain_b200.proposals import engine_kwargs, method_config, raise_for_status
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class MockState:
+    def flip(self, changes):
+        return MockState()
+
+
+def mock_proposal(state):
+    return state.flip({1: 2})
+
+
+def mock_accept(state):
+    return True
+
+
+def mock_is_valid(state):
+    return True
+
+
+def test_markov_chain_yields_total_steps_and_first_is_initial():
+    initial = MockState()
+    chain = MarkovChain(mock_proposal, mock_is_valid, mock_accept, initial, total_steps=10)
+    states = list(chain)
+    assert len(states) == 10
+    assert states[0] is initial
+    assert len(chain) == 10
+    assert repr(chain) == "<MarkovChain [10 steps]>"
+    assert len(list(chain)) == 10  # __iter__ resets
+
+
+def test_markov_chain_rejects_invalid_initial_state():
+    def never(state):
+        return False
+
+    with pytest.raises(ValueError) as e:
+        MarkovChain(mock_proposal, [never], mock_accept, MockState(), total_steps=10)
+    assert "never" in str(e.value)
+
+
+def test_markov_chain_only_counts_valid_and_reyields_rejected():
+    calls = {"n": 0}
+
+    def valid_every_other(state):
+        calls["n"] += 1
+        return calls["n"] % 2 == 1
+
+    initial = MockState()
+    rejecting = MarkovChain(mock_proposal, valid_every_other, lambda s: False, initial, total_steps=5)
+    states = list(rejecting)
+    assert len(states) == 5
+    assert all(s is initial for s in states)  # accept() False: the old state is yielded again
+
+
+def test_validator_needs_real_booleans():
+    v = Validator([lambda p: 1])
+    with pytest.raises(TypeError):
+        v(MagicMock())
+    import numpy
+
+    assert Validator([lambda p: numpy.bool_(True)])(MagicMock()) is True
+    assert Validator([lambda p: True, lambda p: False])(MagicMock()) is False
+
+
+def test_within_percent_of_ideal_population_on_plain_dicts():
+    # reference tests/constraints/test_bounds.py: a dict works as the "partition"
+    initial = {"population": {0: 100, 1: 100, 2: 100}}
+    c = within_percent_of_ideal_population(initial, percent=0.05)
+    assert isinstance(c, Bounds) and c.pop_key == "population"
+    assert c.bounds == (95.0, 105.0)
+    assert c({"population": {0: 95, 1: 105, 2: 100}}) is True
+    assert c({"population": {0: 94, 1: 106, 2: 100}}) is False
+    assert c.__name__.startswith("Bounds(population")
+
+
+def test_method_config_reads_partials_like_the_reference():
+    assert method_config(gc.bipartition_tree)["tree_kind"] == _abi.RC_TREE_MST
+    m = functools.partial(gc.bipartition_tree, max_attempts=7, allow_pair_reselection=True,
+                          spanning_tree_fn=gc.tree.uniform_spanning_tree)
+    cfg = method_config(functools.partial(m, warn_attempts=3))
+    assert cfg == dict(tree_kind=_abi.RC_TREE_WILSON, cut="region", max_attempts=7, warn_attempts=3,
+                       allow_pair_reselection=True)
+    with pytest.raises(NotImplementedError):
+        method_config(functools.partial(gc.bipartition_tree, choice=min))
+    with pytest.raises(NotImplementedError):
+        method_config(lambda *a, **k: None)
+    kw = engine_kwargs(100, 0.1, 2, {"county": 0.5}, gc.bipartition_tree)
+    assert kw["cut_policy"] == _abi.RC_CUT_REGION_PREF and kw["node_repeats"] == 2
+    kw = engine_kwargs(100, 0.1, 1, {"a": 1, "b": 1, "c": 1, "d": 1}, gc.bipartition_tree)
+    assert kw["cut_policy"] == _abi.RC_CUT_MAX_WEIGHT  # tree.py:548: more than 3 regions
+
+
+def test_selectors_have_no_host_implementation():
+    with pytest.raises(NotImplementedError):
+        gc.tree.random_spanning_tree(None)
+    with pytest.raises(NotImplementedError):
+        gc.bipartition_tree(None, "p", 1, 0.1)
+
+
+def test_status_words_map_to_the_reference_exceptions():
+    with pytest.raises(RuntimeError, match="Could not find a possible cut after 1 attempts."):
+        raise_for_status(_abi.RC_ERR_MAX_ATTEMPTS, 1)  # reference tests/test_region_aware.py:102-112
+    with pytest.raises(gc.MetagraphError):
+        raise_for_status(_abi.RC_ERR_ALL_PAIRS_BAD, 10, 6.0)
+    with pytest.raises(IndexError):
+        raise_for_status(_abi.RC_ERR_NO_CUT_EDGES, 10)
+    raise_for_status(_abi.RC_OK, 10)
+
+
+def test_batched_runner_refuses_host_only_callables():
+    p = functools.partial(gc.recom, pop_col="population", pop_target=10, epsilon=0.1)
+    assert _recom_arguments(p)[:4] == ("population", 10, 0.1, 1)
+    assert _recom_arguments(gc.ReCom("population", 10, 0.1))[0] == "population"
+    with pytest.raises(TypeError):
+        _recom_arguments(lambda s: s)
+    with pytest.raises(TypeError):
+        _device_bounds([lambda p: True], "population")
+    b = within_percent_of_ideal_population({"population": {0: 10, 1: 10}}, 0.1)
+    _, lo, hi = _device_bounds(Validator([b]), "population")
+    assert (lo, hi) == (9.0, 11.0)
+
+
+def test_shard_chains_covers_every_chain_once():
+    for total, world in ((8192, 8), (1000, 3), (5, 8)):
+        spans = [shard_chains(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0
+        for (o0, n0), (o1, _) in zip(spans, spans[1:]):
+            assert o0 + n0 == o1
+        assert spans[-1][0] + spans[-1][1] == total
+
+
+def test_histogram_all_reduce_over_gloo_world_size_2(tmp_path):
+    """The only collective of the path, exercised on CPU tensors with two processes."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import torch, torch.distributed as dist
+        from gerrychain_b200.distributed import all_reduce_histograms, gather_chain_scalars, shard_chains
+        dist.init_process_group("gloo")
+        r, w = dist.get_rank(), dist.get_world_size()
+        off, n = shard_chains(10, r, w)
+        cut = torch.zeros(8, dtype=torch.int64); cut[r] = n
+        dev = torch.ones(4, dtype=torch.int64) * (r + 1)
+        all_reduce_histograms(cut, dev)
+        assert cut.tolist()[:2] == [5, 5] and dev.tolist() == [3] * 4, (cut, dev)
+        vals = gather_chain_scalars(torch.arange(off, off + n, dtype=torch.int32))
+        assert vals.tolist() == list(range(10)), vals
+        dist.destroy_process_group()
+        print("ok", r)
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+        capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "ok 0" in out.stdout and "ok 1" in out.stdout
