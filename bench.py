@@ -44,7 +44,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config5"])
@@ -108,7 +108,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -346,7 +346,9 @@ def run_b200(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.workload)
+            per_step = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_recom_step")
+            if per_step is not None:  # per launch, like `achieved`
+                traffic = per_step * total_steps / world / args.steps
         except Exception:
             traffic = None
     roofline = {
