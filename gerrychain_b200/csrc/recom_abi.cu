@@ -85,8 +85,8 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   if (cfg->n_chains < 1) return fail(RC_ERR_INVALID_ARG, "n_chains must be >= 1");
   if (g->n_region_cols < 0 || g->n_region_cols > 8)
     return fail(RC_ERR_INVALID_ARG, "at most 8 region columns");
-  if (cfg->tree_kind != RC_TREE_MST)
-    return fail(RC_ERR_INVALID_ARG, "tree_kind %d not supported by this build", cfg->tree_kind);
+  if (cfg->tree_kind != RC_TREE_MST && cfg->tree_kind != RC_TREE_WILSON)
+    return fail(RC_ERR_INVALID_ARG, "tree_kind %d is neither RC_TREE_MST nor RC_TREE_WILSON", cfg->tree_kind);
   if (!(cfg->epsilon > 0.0) || !(cfg->pop_target > 0.0))
     return fail(RC_ERR_INVALID_ARG, "epsilon and pop_target must be positive");
   CUDA_OK(cudaSetDevice(device));
@@ -131,7 +131,7 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   cap_nodes = (cap_nodes + 7) & ~7;
   cap_edges = (cap_edges + 31) & ~31;
   p.cap_nodes = cap_nodes; p.cap_edges = cap_edges;
-  e->smem = rc::smem_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R);
+  e->smem = rc::smem_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R, cfg->tree_kind == RC_TREE_WILSON);
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
   e->n_sms = prop.multiProcessorCount;
@@ -258,6 +258,8 @@ int rc_engine_replay(RcEngine* e, const RcReplay* rp, void* stream) {
   if (rp->n_steps <= 0 || !rp->steps) return fail(RC_ERR_INVALID_ARG, "empty replay");
   if (rp->chain < 0 || rp->chain >= e->p.cfg.n_chains) return fail(RC_ERR_INVALID_ARG, "bad chain index");
   if (e->p.cfg.tree_kind == RC_TREE_MST && !rp->weight_rank) return fail(RC_ERR_INVALID_ARG, "MST replay needs weight_rank");
+  if (e->p.cfg.tree_kind == RC_TREE_WILSON && (!rp->wilson_root || !rp->stack_ptr || !rp->stack_val))
+    return fail(RC_ERR_INVALID_ARG, "Wilson replay needs wilson_root, stack_ptr and stack_val");
   CUDA_OK(cudaSetDevice(e->device));
   rc::Params p = e->p;
   p.rp = *rp;

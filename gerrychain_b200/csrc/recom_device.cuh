@@ -58,10 +58,21 @@ struct Smem {
   uint32_t* oldb;    // [CN/32] bit i: local node i carries the higher district id b
   uint32_t* newb;    // [CN/32] the same after the proposed cut
   uint8_t* ecls;     // [CE] bitmask of region columns the edge crosses (R > 0 only)
+  // Wilson only: adjacency of the merged pair, rows in ascending neighbour id
+  lid_t* loff;       // [CN+1]
+  lid_t* ladj;       // [2CE] neighbour (local id)
+  lid_t* ladje;      // [2CE] local edge index of that slot
   // spanning-tree phase
   uint32_t* key;     // [CE] 32-bit weight key of local edge j
   uint32_t* lab;     // [CE] live edge list: endpoints as current component ids (a | b << 16)
   lid_t* lj;         // [CE] live edge list: local edge index
+  // uniform-spanning-tree phase (Wilson; aliases the same region)
+  uint32_t* wtmp;    // [CN] row cursors while the adjacency is built
+  lid_t* wcnt;       // [CN] successor draws consumed by node u
+  lid_t* wsl;        // [CN] adjacency slot of u's current successor
+  lid_t* wgA;        // [CN] pointer doubling, ping
+  lid_t* wgB;        // [CN] pointer doubling, pong
+  uint32_t* wmark;   // [CN/32] nodes found on a cycle
   uint32_t* best;    // [CN] minimum key over the live edges of a component
   uint32_t* bpos;    // [CN] (local edge << 16 | live-list position) of that minimum
   lid_t* hook;       // [CN] component merge forest
@@ -82,7 +93,8 @@ struct Smem {
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
 // N: nodes of the whole graph, CN/CE: caps of a merged pair, R: region columns
-__host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int N, int CN, int CE, int R) {
+__host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int N, int CN, int CE, int R,
+                                              int wilson) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return r; };
   const int NW = (N + 31) / 32;
@@ -96,14 +108,23 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
   size_t o_oldb = take(size_t((CN + 31) / 32) * 4);
   size_t o_newb = take(size_t((CN + 31) / 32) * 4);
   size_t o_ecls = take(R > 0 ? size_t(CE) : 0);
+  size_t o_loff = take(wilson ? size_t(CN + 1) * 2 : 0);
+  size_t o_ladj = take(wilson ? size_t(2 * CE) * 2 : 0);
+  size_t o_ladje = take(wilson ? size_t(2 * CE) * 2 : 0);
   size_t phase = o;
-  // spanning-tree phase
-  size_t o_key = take(size_t(CE) * 4);
-  size_t o_lab = take(size_t(CE) * 4);
-  size_t o_lj = take(size_t(CE) * 2);
-  size_t o_best = take(size_t(CN) * 4);
-  size_t o_bpos = take(size_t(CN) * 4);
-  size_t o_hook = take(size_t(CN) * 2);
+  // spanning-tree phase (Boruvka arrays are not needed in Wilson mode and vice versa)
+  size_t o_key = take(wilson ? 0 : size_t(CE) * 4);
+  size_t o_lab = take(wilson ? 0 : size_t(CE) * 4);
+  size_t o_lj = take(wilson ? 0 : size_t(CE) * 2);
+  size_t o_best = take(wilson ? 0 : size_t(CN) * 4);
+  size_t o_bpos = take(wilson ? 0 : size_t(CN) * 4);
+  size_t o_hook = take(wilson ? 0 : size_t(CN) * 2);
+  size_t o_wtmp = take(wilson ? size_t(CN) * 4 : 0);
+  size_t o_wcnt = take(wilson ? size_t(CN) * 2 : 0);
+  size_t o_wsl = take(wilson ? size_t(CN) * 2 : 0);
+  size_t o_wgA = take(wilson ? size_t(CN) * 2 : 0);
+  size_t o_wgB = take(wilson ? size_t(CN) * 2 : 0);
+  size_t o_wmark = take(wilson ? size_t((CN + 31) / 32) * 4 : 0);
   size_t end_a = o;
   // Euler phase
   o = phase;
@@ -129,6 +150,15 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
     s->oldb = (uint32_t*)(base + o_oldb);
     s->newb = (uint32_t*)(base + o_newb);
     s->ecls = (uint8_t*)(base + o_ecls);
+    s->loff = (lid_t*)(base + o_loff);
+    s->ladj = (lid_t*)(base + o_ladj);
+    s->ladje = (lid_t*)(base + o_ladje);
+    s->wtmp = (uint32_t*)(base + o_wtmp);
+    s->wcnt = (lid_t*)(base + o_wcnt);
+    s->wsl = (lid_t*)(base + o_wsl);
+    s->wgA = (lid_t*)(base + o_wgA);
+    s->wgB = (lid_t*)(base + o_wgB);
+    s->wmark = (uint32_t*)(base + o_wmark);
     s->key = (uint32_t*)(base + o_key);
     s->lab = (uint32_t*)(base + o_lab);
     s->lj = (lid_t*)(base + o_lj);
@@ -153,7 +183,7 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
 // misc[] slots
 enum { M_WSUM = 0 /* 0..63: two alternating banks of 32 warp sums */,
        M_ERR = 65, M_PICK, M_CNT, M_TOT, M_NINT, M_SUBSET, M_DELTA, M_TSTAR, M_NLIVE, M_NBAL, M_TAILLEN,
-       M_BEST64 = 80 /* 80..81, 8-byte aligned */, M_CTR = 88 /* 88..95 counters */ };
+       M_BEST64 = 80 /* 80..81, 8-byte aligned */, M_TICKET = 82 /* 82..85: two 8-byte slots */, M_CTR = 88 /* 88..95 counters */ };
 
 #ifdef __CUDACC__
 

@@ -101,6 +101,47 @@ __device__ int pick_cut_edge(Chain& c, int cut_count, uint32_t prop_no, uint32_t
   return e;
 }
 
+// Wilson only: adjacency lists of the merged pair (loff / ladj / ladje), every row in
+// ascending neighbour id - the order in which the walk's draw indexes the neighbours.
+__device__ void build_local_adjacency(Chain& c, const Step& st) {
+  const Smem& s = c.s;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int n = st.n, m = st.m;
+  for (int i = tid; i < n; i += T) s.wtmp[i] = 0;
+  __syncthreads();
+  for (int j = tid; j < m; j += T) { atomicAdd(&s.wtmp[s.eu[j]], 1u); atomicAdd(&s.wtmp[s.ev[j]], 1u); }
+  __syncthreads();
+  {
+    const int per = odd_chunk(n);
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += (int)s.wtmp[i];
+    int tot;
+    int run = block_excl_scan(sum, &tot, s.misc, c.par);
+    for (int i = lo; i < hi; ++i) { const int d = (int)s.wtmp[i]; s.loff[i] = (lid_t)run; s.wtmp[i] = (uint32_t)run; run += d; }
+    if (tid == 0) s.loff[n] = (lid_t)(2 * m);
+  }
+  __syncthreads();
+  for (int j = tid; j < m; j += T) {
+    const int u = s.eu[j], v = s.ev[j];
+    const int pu = (int)atomicAdd(&s.wtmp[u], 1u);
+    s.ladj[pu] = (lid_t)v; s.ladje[pu] = (lid_t)j;
+    const int pv = (int)atomicAdd(&s.wtmp[v], 1u);
+    s.ladj[pv] = (lid_t)u; s.ladje[pv] = (lid_t)j;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += T) {  // insertion sort of a short row
+    const int r0 = s.loff[i], r1 = s.loff[i + 1];
+    for (int a = r0 + 1; a < r1; ++a) {
+      const lid_t kv = s.ladj[a], ke = s.ladje[a];
+      int b = a - 1;
+      while (b >= r0 && s.ladj[b] > kv) { s.ladj[b + 1] = s.ladj[b]; s.ladje[b + 1] = s.ladje[b]; --b; }
+      s.ladj[b + 1] = kv; s.ladje[b + 1] = ke;
+    }
+  }
+  __syncthreads();
+}
+
 // ---- P1: gather the merged pair into shared memory ---------------------------------------
 // returns RC_OK / RC_ERR_CAPACITY (block uniform)
 __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
@@ -205,6 +246,31 @@ __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
   st.m = m;
   *d_sub_out = s.misc[M_CNT];
   if (m > p.cap_edges || m > 65535) return RC_ERR_CAPACITY;
+  if (p.cfg.tree_kind == RC_TREE_WILSON) build_local_adjacency(c, st);
+  return RC_OK;
+}
+
+// te[0..n-2] = the tree edges flagged in tflag, ascending local edge index (8 edges per
+// thread step); RC_ERR_DISCONNECTED unless there are exactly n - 1
+__device__ int tree_edge_list(Chain& c, const Step& st) {
+  const Smem& s = c.s;
+  const int tid = threadIdx.x;
+  const int n = st.n, m = st.m;
+  const int units = (m + 7) >> 3;
+  const int per = odd_chunk(units);
+  const int lo = min(tid * per, units), hi = min(lo + per, units);
+  const uint8_t* fb = reinterpret_cast<const uint8_t*>(s.tflag);
+  int cnt = 0;
+  for (int u = lo; u < hi; ++u) cnt += __popc((uint32_t)fb[u]);
+  int nt;
+  int t = block_excl_scan(cnt, &nt, s.misc, c.par);
+  __syncthreads();  // te aliases the (now dead) spanning-tree arrays
+  if (nt != n - 1) return RC_ERR_DISCONNECTED;
+  for (int u = lo; u < hi; ++u) {
+    uint32_t x = fb[u];
+    while (x) { s.te[t++] = (lid_t)(u * 8 + (__ffs(x) - 1)); x &= x - 1; }
+  }
+  __syncthreads();
   return RC_OK;
 }
 
@@ -320,23 +386,143 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     if (tid == 0) s.misc[M_NLIVE] = 0;
   }
   *rounds_out = rounds;
-  // tree edges in ascending local edge index (units of 8 edges per thread step)
-  const int units = (m + 7) >> 3;
-  const int per = odd_chunk(units);
-  const int lo = min(tid * per, units), hi = min(lo + per, units);
-  const uint8_t* fb = reinterpret_cast<const uint8_t*>(s.tflag);
-  int cnt = 0;
-  for (int u = lo; u < hi; ++u) cnt += __popc((uint32_t)fb[u]);
-  int nt;
-  int t = block_excl_scan(cnt, &nt, s.misc, c.par);
-  __syncthreads();  // te aliases the (now dead) spanning-tree arrays
-  if (nt != n - 1) return RC_ERR_DISCONNECTED;
-  for (int u = lo; u < hi; ++u) {
-    uint32_t x = fb[u];
-    while (x) { s.te[t++] = (lid_t)(u * 8 + (__ffs(x) - 1)); x &= x - 1; }
+  return tree_edge_list(c, st);
+}
+
+// ---- P2b: uniform spanning tree (Wilson, tree.py:97-132) by parallel cycle popping -------
+// Every node owns a stack of successor draws: draw j at node u is a pure function of (u, j)
+// (recom_rng.h).  Pointing every node at the top of its stack gives a functional graph; its
+// cycles are popped (every node on a cycle takes its next draw) until none is left.  The
+// popped cycles and the final tree do not depend on the popping order (Wilson 1996), so
+// this is the tree - and the per-node draw counts - of the reference's sequential
+// loop-erased walks fed with the same stacks.  Short cycles (<= 4) are found by a local
+// look-ahead; what remains by pointer doubling over the functional graph.
+__device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t prop_no, long long tree_idx,
+                           int32_t* ctr) {
+  const Params& p = *c.p;
+  const Smem& s = c.s;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int n = st.n, m = st.m;
+  const bool replay = p.rp.n_steps > 0;
+  int root;
+  if (replay) {
+    const int gr = p.rp.wilson_root[tree_idx];
+    root = (gr >= 0 && gr < p.g.N && is_member(s, gr)) ? local_id(s, gr) : -1;
+    if (root < 0) return RC_ERR_REPLAY;
+  } else {
+    const RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WROOT, 0, tree_no, prop_no, 0);
+    root = (int)rc_below(r.v[0], r.v[1], (uint32_t)n);
   }
+  const int64_t* sp = replay ? p.rp.stack_ptr + tree_idx * ((long long)p.g.N + 1) : nullptr;
+  // take the next draw of node u (tree.py:119)
+  auto draw = [&](int u) {
+    const uint32_t j = s.wcnt[u];
+    s.wcnt[u] = (lid_t)(j + 1);
+    const int r0 = s.loff[u], d = s.loff[u + 1] - r0;
+    if (replay) {
+      const int gu = c.nodes[u];
+      int slot = -1;
+      if (sp[gu] + (long long)j < sp[gu + 1]) {
+        const int gv = p.rp.stack_val[sp[gu] + j];
+        if (gv >= 0 && gv < p.g.N && is_member(s, gv)) {
+          const int lv = local_id(s, gv);
+          for (int q = 0; q < d; ++q) if (s.ladj[r0 + q] == lv) slot = r0 + q;
+        }
+      }
+      if (slot < 0) { s.misc[M_ERR] = RC_ERR_REPLAY; slot = r0; }
+      s.wsl[u] = (lid_t)slot;
+    } else {
+      const RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WALK, (uint32_t)u, tree_no, prop_no, j >> 2);
+      s.wsl[u] = (lid_t)(r0 + (int)rc_below32(r.v[j & 3u], (uint32_t)d));
+    }
+  };
+  auto succ_of = [&](int u) { return u == root ? u : (int)s.ladj[s.wsl[u]]; };
+  if (tid == 0) s.misc[M_ERR] = 0;
+  for (int u = tid; u < n; u += T) {
+    s.wcnt[u] = 0;
+    if (u != root) {
+      if (s.loff[u + 1] == s.loff[u]) s.misc[M_ERR] = RC_ERR_DISCONNECTED; else draw(u);
+    } else {
+      s.wsl[u] = 0;
+    }
+  }
+  for (int i = tid; i < (m + 31) >> 5; i += T) s.tflag[i] = 0;
   __syncthreads();
-  return RC_OK;
+  if (s.misc[M_ERR]) return s.misc[M_ERR];
+  int walk = 0;
+  for (;;) {
+    // local look-ahead: u is on a cycle of length <= 4 iff it comes back to itself
+    for (;;) {
+      bool on[4];
+      int popped = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int u = tid + k * T;
+        on[k] = false;
+        if (u < n && u != root) {
+          const int v1 = succ_of(u), v2 = succ_of(v1);
+          bool hit = v2 == u;
+          if (!hit) { const int v3 = succ_of(v2); hit = v3 == u || succ_of(v3) == u; }
+          on[k] = hit;
+        }
+      }
+      for (int u = tid + 4 * T; u < n; u += T) {  // merged pairs larger than 4 T nodes
+        if (u == root) continue;
+        const int v1 = succ_of(u), v2 = succ_of(v1), v3 = succ_of(v2);
+        if (v2 == u || v3 == u || succ_of(v3) == u) atomicOr(&s.wmark[u >> 5], 1u << (u & 31));
+      }
+      __syncthreads();  // every pointer has been read
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (on[k]) { draw(tid + k * T); ++popped; }
+      for (int u = tid + 4 * T; u < n; u += T)
+        if ((s.wmark[u >> 5] >> (u & 31)) & 1u) { draw(u); ++popped; }
+      walk += popped;
+      const int any = __syncthreads_or(popped);
+      if (n > 4 * T) {
+        for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
+        __syncthreads();
+      }
+      if (!any) break;
+    }
+    // global detection: after >= n steps of the functional graph every node sits on a cycle
+    // or at the root, and every cycle node is somebody's landing point
+    for (int u = tid; u < n; u += T) s.wgA[u] = (lid_t)succ_of(u);
+    for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
+    __syncthreads();
+    lid_t* __restrict__ A = s.wgA;
+    lid_t* __restrict__ B = s.wgB;
+    for (int span = 1; span < n; span <<= 1) {
+      for (int u = tid; u < n; u += T) B[u] = A[A[u]];
+      __syncthreads();
+      lid_t* tmp = A; A = B; B = tmp;
+    }
+    for (int u = tid; u < n; u += T) {
+      const int v = A[u];
+      if (v != root) atomicOr(&s.wmark[v >> 5], 1u << (v & 31));
+    }
+    __syncthreads();
+    int popped = 0;
+    for (int u = tid; u < n; u += T)
+      if ((s.wmark[u >> 5] >> (u & 31)) & 1u) { draw(u); ++popped; }
+    walk += popped;
+    const int any = __syncthreads_or(popped);
+    for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
+    __syncthreads();
+    if (!any) break;
+  }
+  if (s.misc[M_ERR]) return s.misc[M_ERR];
+  // the tree: edge (u, successor of u) for every node but the root
+  for (int u = tid; u < n; u += T) {
+    walk += (u != root);  // the first draw of every node
+    if (u == root) continue;
+    const int j = s.ladje[s.wsl[u]];
+    atomicOr(&s.tflag[j >> 5], 1u << (j & 31));
+  }
+  walk = warp_sum(walk);
+  if ((tid & 31) == 0 && walk) atomicAdd(&ctr[RC_CTR_WALK], walk);
+  __syncthreads();
+  return tree_edge_list(c, st);
 }
 
 // ---- P3: root the tree and compute every subtree population ----------------------------
@@ -614,10 +800,12 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
       return res;
     }
     if (rs && (int)tree_no >= n_rec) { res.status = RC_ERR_REPLAY; return res; }
-    const uint32_t* rrank = rs ? p.rp.weight_rank + (rs->first_tree + tree_no) * (long long)p.g.E : nullptr;
+    const bool wilson = p.cfg.tree_kind == RC_TREE_WILSON;
+    const uint32_t* rrank = (rs && !wilson) ? p.rp.weight_rank + (rs->first_tree + tree_no) * (long long)p.g.E : nullptr;
     // ---- P2
     int rounds = 0;
-    res.status = boruvka_mst(c, st, tree_no, prop_no, rrank, &rounds);
+    res.status = wilson ? wilson_tree(c, st, tree_no, prop_no, rs ? rs->first_tree + tree_no : 0, ctr)
+                        : boruvka_mst(c, st, tree_no, prop_no, rrank, &rounds);
     if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_ROUNDS] += rounds; }
     res.trees = (int)tree_no + 1;
     if (res.status) return res;
@@ -761,7 +949,7 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Chain c;
   c.p = &p;
-  smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R);
+  smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R, p.cfg.tree_kind == RC_TREE_WILSON);
   const int tid = threadIdx.x;
   c.nodes = p.nodes + (size_t)blockIdx.x * p.cap_nodes;
   c.eids = p.eids + (size_t)blockIdx.x * p.cap_edges;
@@ -774,17 +962,31 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
   const unsigned long long total =
       replay ? (unsigned long long)p.rp.n_steps : (unsigned long long)n_chains * (unsigned long long)p.n_steps;
   const int streak_cap = p.cfg.max_invalid_streak > 0 ? p.cfg.max_invalid_streak : 1000;
-  unsigned long long* ticket = reinterpret_cast<unsigned long long*>(&c.s.misc[M_BEST64]);
+  // ticket hand-out: thread 0 fetches the NEXT ticket while the current step runs, waits for
+  // that chain's previous step, and publishes the ticket through one of two alternating
+  // shared slots - one barrier per step on this path
+  unsigned long long* slots = reinterpret_cast<unsigned long long*>(&c.s.misc[M_TICKET]);
   unsigned long long rt = 0;  // replay: steps are taken in order
+  unsigned long long pre = 0;  // thread 0: prefetched ticket
+  int flip = 0;
+  if (!replay && tid == 0) pre = atomicAdd(p.work_counter, 1ull);
   for (;;) {
     unsigned long long t;
     if (replay) {
       t = rt++;
     } else {
-      if (tid == 0) *ticket = atomicAdd(p.work_counter, 1ull);
+      if (tid == 0) {
+        if (pre < total) {
+          const int ch = (int)(pre % (unsigned long long)n_chains);
+          const int sg = (int)(pre / (unsigned long long)n_chains);
+          while (ld_acquire(p.progress + ch) < sg) __nanosleep(32);
+        }
+        slots[flip] = pre;
+      }
       __syncthreads();
-      t = *ticket;
-      __syncthreads();
+      t = slots[flip];
+      flip ^= 1;
+      if (tid == 0 && t < total) pre = atomicAdd(p.work_counter, 1ull);  // in flight during the step
     }
     if (t >= total) break;
     const int chain = replay ? p.rp.chain : (int)(t % (unsigned long long)n_chains);
@@ -794,11 +996,6 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
     c.assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
     c.mask = p.st.d_cut_mask + (size_t)chain * p.st.mask_stride;
     c.tally = p.st.d_tally + (size_t)chain * p.cfg.n_districts;
-    if (!replay) {
-      if (tid == 0)
-        while (ld_acquire(p.progress + chain) < seg) __nanosleep(64);
-      __syncthreads();
-    }
     int status = __ldcg(p.st.d_status + chain);
     if (status == RC_OK) {
       // one accepted step (chain.py:185-195): propose until valid, accept always

@@ -31,8 +31,10 @@ enum {
   RC_DRAW_ROOT = 3,   /* BFS root among tree nodes of degree > 1 (tree.py:377)          */
   RC_DRAW_CUT = 4,    /* random.choice(cuts) (tree.py:545)                              */
   RC_DRAW_WROOT = 5,  /* Wilson root (tree.py:112)                                      */
-  RC_DRAW_WALK = 6    /* Wilson successor draw j at node u (tree.py:119): index = u,
-                         sub = j >> 2, word j & 3                                       */
+  RC_DRAW_WALK = 6    /* Wilson successor draw j at node u (tree.py:119): index = rank of u
+                         among the nodes of the merged pair (ascending node index),
+                         sub = j >> 2, word j & 3; the value picks among u's neighbours
+                         inside the pair in ascending node index                       */
 };
 
 typedef struct RcPhilox { uint32_t v[4]; } RcPhilox;

@@ -281,7 +281,7 @@ static int rco_wilson(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t 
       } else {
         int d = sub_neighbors(g, w, u, nb, NULL);
         if (d > 512) return RC_ERR_CAPACITY;
-        RcPhilox p = rc_draw(c->seed, chain, RC_DRAW_WALK, (uint32_t)w->nodes[u], tree_no,
+        RcPhilox p = rc_draw(c->seed, chain, RC_DRAW_WALK, (uint32_t)u, tree_no,
                              prop_no, j >> 2);
         v = nb[rc_below32(p.v[j & 3], (uint32_t)d)];
       }

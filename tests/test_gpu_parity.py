@@ -45,6 +45,43 @@ def test_replay_bit_exact_with_reference(name):
                  eng.cut_mask.cpu().numpy(), eng.cut_count.cpu().numpy())
 
 
+@pytest.mark.parametrize("name", _golden.names("wilson"))
+def test_wilson_replay_bit_exact_with_reference(name):
+    """uniform_spanning_tree (tree.py:97-132): the reference's recorded per-node successor
+    draws, replayed through the device's parallel cycle popping, give the reference's
+    assignment after every step."""
+    g = _golden.load(name)
+    eng = _engine(g.csr, g.cfg, g.init_assignment)
+    trace, info = eng.replay(g.rec)
+    assert (info[:, 3] == 0).all(), [_abi.STATUS_NAMES.get(int(x)) for x in info[:, 3]]
+    assert np.array_equal(trace, g.assignment)
+    assert np.array_equal(info[:, 2], g.n_cut_edges)
+    assert np.array_equal(info[:, 1], np.diff(g.balanced_ptr))
+    assert np.array_equal(info[:, 0], np.diff(g.tree_ptr))
+    # every recorded draw was consumed: same number of walk steps as the reference
+    assert int(eng.counters.cpu().numpy()[0, _abi.RC_CTR_WALK]) == len(g.rec.stack_val)
+    _naive_check(g.csr, g.cfg.n_districts, eng.assignments(), eng.tally.cpu().numpy(),
+                 eng.cut_mask.cpu().numpy(), eng.cut_count.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", _golden.names("wilson"))
+def test_wilson_free_run_bit_exact_with_oracle(name):
+    g = _golden.load(name)
+    cfg = g.cfg
+    cfg.n_chains = 16
+    cfg.seed = 4321
+    eng = _free_run_vs_oracle(g.csr, g.init_assignment, cfg, 30)
+    from oracle import oracle  # walk-step counts agree as well
+
+    ora = oracle.OracleChains(g.csr, cfg, g.init_assignment).run(30, n_threads=8)
+    assert np.array_equal(eng.counters.cpu().numpy()[:, _abi.RC_CTR_WALK], ora.counters[:, _abi.RC_CTR_WALK])
+
+
+def test_wilson_free_run_config3():
+    csr, plan, cfg = workloads.config3(n_chains=16, seed=21, tree_kind=_abi.RC_TREE_WILSON)
+    _free_run_vs_oracle(csr, plan, cfg, 10)
+
+
 @pytest.mark.parametrize("name", [n for n in _golden.names("mst") if "region" in n])
 def test_replay_region_policy_on_device(name):
     g = _golden.load(name, inject_cut=False)

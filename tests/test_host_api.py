@@ -168,7 +168,7 @@ def test_histogram_all_reduce_over_gloo_world_size_2(tmp_path):
         vals = gather_chain_scalars(torch.arange(off, off + n, dtype=torch.int32))
         assert vals.tolist() == list(range(10)), vals
         dist.destroy_process_group()
-        print("ok", r)
+        print("rank%d_ok" % r, flush=True)
     """))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     out = subprocess.run(
@@ -176,4 +176,4 @@ def test_histogram_all_reduce_over_gloo_world_size_2(tmp_path):
          "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
         capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
-    assert "ok 0" in out.stdout and "ok 1" in out.stdout
+    assert "rank0_ok" in out.stdout and "rank1_ok" in out.stdout
