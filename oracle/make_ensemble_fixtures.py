@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Ensemble fixtures for the KS tests (tests/golden/ensemble_*.npz).
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container, where /root/reference exists:
+
+    python oracle/make_ensemble_fixtures.py
+
+Runs the UNMODIFIED reference (`MarkovChain` + `recom`, one chain per process-pool worker,
+`random.seed(chain id)` - the reference's own pattern for ensembles,
+/root/reference/tests/test_region_aware.py:82-99) for many independent chains from one seed
+plan and records, at a fixed step index, the statistics the north star names: the number of
+cut edges and the population deviation of every district (constraints/validity.py:96-122).
+Samples are taken ACROSS chains at a fixed step (independent), never along a chain.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import random
+import sys
+from concurrent.futures import ProcessPoolExecutor
+from functools import partial
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, REPO)
+from oracle.record_reference import import_reference  # noqa: E402
+
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+CASES = {
+    # name: (grid dims, k via plan, epsilon, tree, region_surcharge, steps, chains)
+    "grid20_mst": dict(dims=(20, 20), eps=0.05, tree="mst", steps=60, chains=384),
+    "grid20_wilson": dict(dims=(20, 20), eps=0.05, tree="wilson", steps=60, chains=384),
+    "grid12_region": dict(dims=(12, 12), eps=0.1, tree="mst", steps=60, chains=384, region=True),
+}
+
+
+def _build(case):
+    import_reference()
+    import networkx
+    from gerrychain import Graph, Partition
+    from gerrychain.updaters import Tally, cut_edges
+
+    m, n = case["dims"]
+    g = networkx.grid_2d_graph(m, n)
+    for (i, j) in g.nodes:
+        g.nodes[(i, j)]["population"] = 1
+        g.nodes[(i, j)]["county"] = (i // (m // 3)) * 3 + j // (n // 3)
+    plan = {(i, j): (0 if i < m // 2 else 1) + (0 if j < n // 2 else 2) for (i, j) in g.nodes}
+    graph = Graph.from_networkx(g)
+    part = Partition(graph, plan, {"population": Tally("population"), "cut_edges": cut_edges})
+    return graph, part, plan
+
+
+def run_chain(seed, case):
+    import_reference()
+    from gerrychain import MarkovChain, accept, constraints
+    from gerrychain.proposals import recom
+    from gerrychain.tree import bipartition_tree, uniform_spanning_tree
+
+    graph, part, plan = _build(case)
+    random.seed(seed)
+    ideal = sum(part["population"].values()) / len(part)
+    method = bipartition_tree
+    if case["tree"] == "wilson":
+        method = partial(bipartition_tree, spanning_tree_fn=uniform_spanning_tree)
+    kw = dict(pop_col="population", pop_target=ideal, epsilon=case["eps"], node_repeats=1, method=method)
+    if case.get("region"):
+        kw["region_surcharge"] = {"county": 0.5}
+    chain = MarkovChain(partial(recom, **kw),
+                        [constraints.within_percent_of_ideal_population(part, case["eps"])],
+                        accept.always_accept, part, total_steps=case["steps"] + 1)
+    state = None
+    for state in chain:
+        pass
+    pops = [state["population"][d] for d in sorted(state["population"])]
+    county_splits = 0
+    if case.get("region"):
+        for nodes in state.parts.values():
+            county_splits += len({graph.nodes[v]["county"] for v in nodes}) - 1
+    return len(state["cut_edges"]), pops, county_splits
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    for name, case in CASES.items():
+        with ProcessPoolExecutor(max_workers=os.cpu_count()) as ex:
+            rows = list(ex.map(partial(run_chain, case=case), range(case["chains"])))
+        _, part, plan = _build(case)
+        labels = list(part.graph.nodes)
+        out = os.path.join(GOLDEN, f"ensemble_{name}.npz")
+        np.savez_compressed(
+            out, meta=json.dumps(case), cut_edges=np.array([r[0] for r in rows], dtype=np.int32),
+            population=np.array([r[1] for r in rows], dtype=np.int64),
+            county_splits=np.array([r[2] for r in rows], dtype=np.int32),
+            plan=np.array([plan[v] for v in labels], dtype=np.uint8))
+        print(out, "mean cut edges", np.mean([r[0] for r in rows]))
+
+
+if __name__ == "__main__":
+    main()

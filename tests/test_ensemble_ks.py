@@ -1,0 +1,91 @@
+"""Free-running ensembles against the reference (north star): two-sample KS, alpha = 0.01,
+on the number of cut edges and on the population deviation, sampled ACROSS independent
+chains at a fixed step.  The reference ensembles are tests/golden/ensemble_*.npz, written by
+oracle/make_ensemble_fixtures.py from the unmodified reference (384 chains each).
+
+CPU: the oracle port's free-running mode vs the reference (pins the counter-based RNG
+schedule statistically).  GPU: the CUDA engine vs the reference."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy.stats import ks_2samp
+
+from gerrychain_b200 import _abi, synthetic
+from gerrychain_b200.config import EngineConfig, cut_policy_for
+from gerrychain_b200.csr import csr_from_networkx
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ALPHA = 0.01
+CASES = ["grid20_mst", "grid20_wilson", "grid12_region"]
+
+
+def _case(name, n_chains, seed):
+    z = np.load(os.path.join(GOLDEN, f"ensemble_{name}.npz"))
+    meta = json.loads(str(z["meta"]))
+    m, n = meta["dims"]
+    g = synthetic.grid_graph(m, n)
+    regions = None
+    if meta.get("region"):
+        for (i, j) in g.nodes:
+            g.nodes[(i, j)]["county"] = (i // (m // 3)) * 3 + j // (n // 3)
+        regions = {"county": 0.5}
+    csr = csr_from_networkx(g, "population", regions)
+    k = int(z["plan"].max()) + 1
+    ideal = float(csr.pop.sum()) / k
+    eps = meta["eps"]
+    tree_kind = _abi.RC_TREE_WILSON if meta["tree"] == "wilson" else _abi.RC_TREE_MST
+    cfg = EngineConfig(n_districts=k, n_chains=n_chains, pop_target=ideal, epsilon=eps,
+                       pop_lower=(1 - eps) * ideal, pop_upper=(1 + eps) * ideal, seed=seed,
+                       tree_kind=tree_kind, cut_policy=cut_policy_for(regions, tree_kind))
+    return z, meta, g, csr, cfg, ideal
+
+
+def _county_splits(g, csr, assign, k):
+    county = np.array([g.nodes[v]["county"] for v in csr.node_labels])
+    out = np.zeros(assign.shape[0], dtype=np.int64)
+    for d in range(k):
+        for c in range(assign.shape[0]):
+            out[c] += len(np.unique(county[assign[c] == d])) - 1
+    return out
+
+
+def _compare(z, meta, g, csr, cfg, ideal, cut_count, tally, assign):
+    ref_cut = z["cut_edges"]
+    ref_dev = np.abs(z["population"] - ideal).max(axis=1) / ideal
+    our_dev = np.abs(tally - ideal).max(axis=1) / ideal
+    p_cut = ks_2samp(ref_cut, cut_count).pvalue
+    p_dev = ks_2samp(ref_dev, our_dev).pvalue
+    p_pool = ks_2samp((z["population"].ravel() - ideal) / ideal, (tally.ravel() - ideal) / ideal).pvalue
+    assert p_cut > ALPHA, ("cut edges", p_cut, ref_cut.mean(), cut_count.mean())
+    assert p_dev > ALPHA, ("max |deviation|", p_dev)
+    assert p_pool > ALPHA, ("pooled deviation", p_pool)
+    if meta.get("region"):
+        ours = _county_splits(g, csr, assign, cfg.n_districts)
+        p_split = ks_2samp(z["county_splits"], ours).pvalue
+        assert p_split > ALPHA, ("county splits", p_split, z["county_splits"].mean(), ours.mean())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_ensemble_matches_reference(name):
+    from oracle import oracle
+
+    z, meta, g, csr, cfg, ideal = _case(name, 1536, seed=11)
+    ora = oracle.OracleChains(csr, cfg, z["plan"]).run(meta["steps"], n_threads=os.cpu_count() or 1)
+    assert (ora.status == 0).all()
+    _compare(z, meta, g, csr, cfg, ideal, ora.cut_count, ora.tally, ora.assignments())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_engine_ensemble_matches_reference(name):
+    from gerrychain_b200.engine import Engine
+
+    z, meta, g, csr, cfg, ideal = _case(name, 4096, seed=12)
+    eng = Engine(csr, cfg, z["plan"])
+    eng.run(meta["steps"]).synchronize()
+    eng.check_status()
+    _compare(z, meta, g, csr, cfg, ideal, eng.cut_count.cpu().numpy(), eng.tally.cpu().numpy(),
+             eng.assignments())
