@@ -125,7 +125,7 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   if (cap_nodes > N) cap_nodes = N;
   if (cap_nodes > rc::kMaxLocal) cap_nodes = rc::kMaxLocal;
   int cap_edges = cfg->cap_edges > 0 ? cfg->cap_edges
-                                     : (int)(1.1 * cap_nodes * ((double)E / N)) + 64;
+                                     : (int)(1.02 * cap_nodes * ((double)E / N)) + 64;
   if (cap_edges > E) cap_edges = E;
   if (cap_edges > 65535) cap_edges = 65535;
   cap_nodes = (cap_nodes + 7) & ~7;

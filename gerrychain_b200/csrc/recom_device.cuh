@@ -76,6 +76,8 @@ struct Smem {
   uint32_t* best;    // [CN] minimum key over the live edges of a component
   uint32_t* bpos;    // [CN] (local edge << 16 | live-list position) of that minimum
   lid_t* hook;       // [CN] component merge forest
+  lid_t* vlA;        // [CN/2+2] live components, ping
+  lid_t* vlB;        // [CN/2+2] live components, pong
   // Euler-tour phase (aliases the spanning-tree phase)
   lid_t* te;         // [CN] local edge index of tree edge t (ascending)
   uint32_t* head;    // [CN] first out-arc of a node (linked adjacency)
@@ -119,6 +121,8 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
   size_t o_best = take(wilson ? 0 : size_t(CN) * 4);
   size_t o_bpos = take(wilson ? 0 : size_t(CN) * 4);
   size_t o_hook = take(wilson ? 0 : size_t(CN) * 2);
+  size_t o_vlA = take(wilson ? 0 : size_t(CN / 2 + 2) * 2);
+  size_t o_vlB = take(wilson ? 0 : size_t(CN / 2 + 2) * 2);
   size_t o_wtmp = take(wilson ? size_t(CN) * 4 : 0);
   size_t o_wcnt = take(wilson ? size_t(CN) * 2 : 0);
   size_t o_wsl = take(wilson ? size_t(CN) * 2 : 0);
@@ -165,6 +169,8 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
     s->best = (uint32_t*)(base + o_best);
     s->bpos = (uint32_t*)(base + o_bpos);
     s->hook = (lid_t*)(base + o_hook);
+    s->vlA = (lid_t*)(base + o_vlA);
+    s->vlB = (lid_t*)(base + o_vlB);
     s->te = (lid_t*)(base + o_te);
     s->head = (uint32_t*)(base + o_head);
     s->nxt = (lid_t*)(base + o_nxt);
@@ -182,7 +188,7 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
 
 // misc[] slots
 enum { M_WSUM = 0 /* 0..63: two alternating banks of 32 warp sums */,
-       M_ERR = 65, M_PICK, M_CNT, M_TOT, M_NINT, M_SUBSET, M_DELTA, M_TSTAR, M_NLIVE, M_NBAL, M_TAILLEN,
+       M_ERR = 65, M_PICK, M_CNT, M_TOT, M_NINT, M_SUBSET, M_DELTA, M_TSTAR, M_NLIVE, M_NBAL, M_TAILLEN, M_NV,
        M_BEST64 = 80 /* 80..81, 8-byte aligned */, M_TICKET = 82 /* 82..85: two 8-byte slots */, M_CTR = 88 /* 88..95 counters */ };
 
 #ifdef __CUDACC__

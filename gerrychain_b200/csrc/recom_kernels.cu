@@ -276,8 +276,11 @@ __device__ int tree_edge_list(Chain& c, const Step& st) {
 
 // ---- P2a: random-weight minimum spanning tree by contracting Boruvka rounds ---------------
 // Unique MST under the total order (key32, local edge index) == Kruskal's tree.  Live edges
-// carry their endpoints as current component ids; edges inside a component are dropped
-// every round, so the work shrinks geometrically.  On return tflag marks the tree edges
+// carry their endpoints as current component ids and are compacted every round (edges inside
+// a component are dropped); the vertex side works on a compacted list of live components,
+// which at least halves every round.  Per round: (A) minimum key per component, (B) lowest
+// edge index among the edges attaining it, (C) hook, (C') compress the hook forest and list
+// the surviving roots, (D) relabel + compact the edges.  On return tflag marks the tree edges
 // and te[0..n-2] lists them in ascending local edge index.
 constexpr int kCompactK = 8;
 
@@ -285,7 +288,7 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
                            const uint32_t* rrank, int* rounds_out) {
   const Params& p = *c.p;
   const Smem& s = c.s;
-  const int tid = threadIdx.x, T = blockDim.x;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
   const int n = st.n, m = st.m;
   // weights: one Philox block per four edges
   if (rrank) {
@@ -303,10 +306,12 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
   for (int j = tid; j < m; j += T) { s.lab[j] = (uint32_t)s.eu[j] | ((uint32_t)s.ev[j] << 16); s.lj[j] = (lid_t)j; }
   for (int i = tid; i < n; i += T) { s.best[i] = 0xffffffffu; s.bpos[i] = 0xffffffffu; s.hook[i] = (lid_t)i; }
   for (int i = tid; i < (m + 31) >> 5; i += T) s.tflag[i] = 0;
-  if (tid == 0) s.misc[M_NLIVE] = 0;
+  if (tid == 0) { s.misc[M_NLIVE] = 0; s.misc[M_NV] = 0; }
   __syncthreads();
-  int nlive = m, rounds = 0;
-  while (nlive > 0) {
+  int nlive = m, nv = n, rounds = 0;
+  const lid_t* vcur = nullptr;  // round 0: every node is a component
+  lid_t* vnext = s.vlA;
+  while (nlive > 0 && nv > 1) {
     ++rounds;
     // A: minimum key per component (native 32-bit shared atomics)
     for (int q = tid; q < nlive; q += T) {
@@ -328,9 +333,10 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     __syncthreads();
     // C: every component hooks onto the other side of its lightest edge; of a mutual pair
     // the smaller id stays a root
-    for (int v = tid; v < n; v += T) {
+    for (int q = tid; q < nv; q += T) {
+      const int v = vcur ? (int)vcur[q] : q;
       const uint32_t bp = s.bpos[v];
-      if (bp == 0xffffffffu) continue;
+      if (bp == 0xffffffffu) continue;  // a finished component (disconnected input)
       const uint32_t ab = s.lab[bp & 0xffffu];
       const int a = ab & 0xffffu, b = ab >> 16;
       const int other = a == v ? b : a;
@@ -340,16 +346,35 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     }
     __syncthreads();
     // C': compress the merge forest (benign race: a reader may see a pointer that is already
-    // compressed - still an ancestor) so that D needs one lookup per endpoint
-    for (int v = tid; v < n; v += T) {
-      if (s.bpos[v] == 0xffffffffu) continue;
-      int r = v, h;
-      while ((h = s.hook[r]) != r) r = h;
-      s.hook[v] = (lid_t)r;
-      s.best[v] = 0xffffffffu;  // ready for the next round (only roots stay live)
-      s.bpos[v] = 0xffffffffu;
+    // compressed - still an ancestor) and list the roots, the live components of the next round
+    for (int q0 = 0; q0 < nv; q0 += T) {
+      const int q = q0 + tid;
+      bool is_root = false;
+      int v = 0;
+      if (q < nv) {
+        v = vcur ? (int)vcur[q] : q;
+        if (s.bpos[v] != 0xffffffffu) {
+          int r = v, h;
+          while ((h = s.hook[r]) != r) r = h;
+          s.hook[v] = (lid_t)r;
+          s.best[v] = 0xffffffffu;
+          s.bpos[v] = 0xffffffffu;
+          is_root = r == v;
+        }
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, is_root);
+      if (bal) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s.misc[M_NV], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (is_root) vnext[base + __popc(bal & ((1u << lane) - 1u))] = (lid_t)v;
+      }
     }
     __syncthreads();
+    nv = s.misc[M_NV];
+    vcur = vnext;
+    vnext = vnext == s.vlA ? s.vlB : s.vlA;
+    if (nv <= 1) break;  // one component left: every remaining edge is inside it
     // D: relabel the live edges to the new roots and drop the ones inside a component;
     // in place: a sweep's reads all precede its writes, and it writes below what it read
     for (int base = 0; base < nlive; base += T * kCompactK) {
@@ -371,7 +396,7 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
       const int incl = warp_incl_scan(cnt);
       __syncthreads();  // every read of this sweep is done
       int wbase = 0;
-      if ((tid & 31) == 31 && incl > 0) wbase = atomicAdd(&s.misc[M_NLIVE], incl);
+      if (lane == 31 && incl > 0) wbase = atomicAdd(&s.misc[M_NLIVE], incl);
       wbase = __shfl_sync(0xffffffffu, wbase, 31);
       int o = wbase + incl - cnt;
 #pragma unroll
@@ -383,7 +408,7 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     __syncthreads();
     nlive = s.misc[M_NLIVE];
     __syncthreads();
-    if (tid == 0) s.misc[M_NLIVE] = 0;
+    if (tid == 0) { s.misc[M_NLIVE] = 0; s.misc[M_NV] = 0; }
   }
   *rounds_out = rounds;
   return tree_edge_list(c, st);
