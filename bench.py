@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config5"])
+    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config4", "config5"])
     ap.add_argument("--chains", type=int, default=1024, help="chains per GPU")
     ap.add_argument("--chain-steps", type=int, default=32, help="ReCom steps per chain per bench step")
     ap.add_argument("--seed", type=int, default=2024)
@@ -61,6 +61,7 @@ WORKLOAD_NAMES = {
     "config1": "Grid 20x20 (400 nodes), 4 districts, eps=0.05, random_spanning_tree ReCom",
     "config2": "Grid 100x100 (10k nodes), 10 districts, eps=0.05, random_spanning_tree ReCom",
     "config3": "Delaunay 9k nodes, 18 districts, eps=0.02, random_spanning_tree ReCom",
+    "config4": "Delaunay 200k nodes, 50 districts, eps=0.05, uniform_spanning_tree (Wilson) ReCom, spill mode",
     "config5": "Delaunay 9k nodes, 18 districts, eps=0.02, region-aware ReCom (67 counties, surcharge 0.5)",
 }
 

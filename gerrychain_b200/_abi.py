@@ -171,6 +171,10 @@ _lib: Optional[C.CDLL] = None
 
 
 def lib_path() -> str:
+    """The in-tree library; RECOM_B200_LIB selects another build of the same ABI (A/B runs)."""
+    override = os.environ.get("RECOM_B200_LIB")
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 

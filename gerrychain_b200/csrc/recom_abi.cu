@@ -42,7 +42,9 @@ struct RcEngine {
   rc::Params p{};
   bool bound = false;
   int grid = 0, threads = 0, ctas_per_sm = 0, n_sms = 0;
-  size_t smem = 0, scratch_bytes = 0, sched_bytes = 0;
+  size_t smem = 0, scratch_bytes = 0, sched_bytes = 0, spill_bytes = 0;
+  bool spill = false;
+  const void* kernel = nullptr;
   int64_t launches = 0;
   // owned device memory
   int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_slot_edge = nullptr, *d_edge_uv = nullptr,
@@ -131,20 +133,31 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   cap_nodes = (cap_nodes + 7) & ~7;
   cap_edges = (cap_edges + 31) & ~31;
   p.cap_nodes = cap_nodes; p.cap_edges = cap_edges;
-  e->smem = rc::smem_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R, cfg->tree_kind == RC_TREE_WILSON);
+  const bool wilson = cfg->tree_kind == RC_TREE_WILSON;  // one kernel instantiation per tree kind
+  size_t split = 0;
+  const size_t total = rc::smem_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R, wilson, nullptr, &split);
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
   e->n_sms = prop.multiProcessorCount;
+  // a merged pair that does not fit an SM's shared memory keeps its working arrays in a
+  // per-CTA global scratch block instead (L2 resident): same code, generic pointers
+  e->spill = total > (size_t)prop.sharedMemPerBlockOptin;
+  e->smem = e->spill ? split : total;
+  e->spill_bytes = e->spill ? ((total - split + 255) & ~size_t(255)) : 0;
   if (e->smem > (size_t)prop.sharedMemPerBlockOptin) {
     rc_engine_destroy(e);
-    return fail(RC_ERR_CAPACITY, "merged pair of %d nodes / %d edges needs %zu B shared memory (> %zu)",
-                cap_nodes, cap_edges, e->smem, (size_t)prop.sharedMemPerBlockOptin);
+    return fail(RC_ERR_CAPACITY, "graph of %d nodes needs %zu B of shared memory for the membership bitmap (> %zu)",
+                N, e->smem, (size_t)prop.sharedMemPerBlockOptin);
   }
-  CUDA_OK(cudaFuncSetAttribute(rc::recom_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  e->threads = cfg->threads_per_cta > 0 ? cfg->threads_per_cta : 512;
-  if (e->threads > 512) e->threads = 512;
-  e->threads = (e->threads + 31) & ~31;
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->ctas_per_sm, rc::recom_step_kernel, e->threads, e->smem));
+  e->threads = 512;
+  if (cfg->threads_per_cta != 0 && cfg->threads_per_cta != 512) {
+    rc_engine_destroy(e);
+    return fail(RC_ERR_INVALID_ARG, "threads_per_cta is fixed at 512 in this build (0 = default)");
+  }
+  e->kernel = wilson ? (e->spill ? (const void*)rc::recom_step_kernel<true, true> : (const void*)rc::recom_step_kernel<true, false>)
+                     : (e->spill ? (const void*)rc::recom_step_kernel<false, true> : (const void*)rc::recom_step_kernel<false, false>);
+  CUDA_OK(cudaFuncSetAttribute(e->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->ctas_per_sm, e->kernel, e->threads, e->smem));
   if (e->ctas_per_sm < 1) { rc_engine_destroy(e); return fail(RC_ERR_CAPACITY, "kernel does not fit an SM"); }
   // persistent grid: every CTA resident, (chain, step) tickets handed out in order
   e->grid = e->ctas_per_sm * e->n_sms;
@@ -155,7 +168,8 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   size_t b_bad = cfg->allow_pair_reselection ? (size_t)e->grid * 2048 * sizeof(uint32_t) : 0;
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
   size_t b_prog = 256 + (size_t)cfg->n_chains * sizeof(int32_t);
-  e->scratch_bytes = al(b_nodes) + al(b_eids) + al(b_bad) + al(b_prog);
+  size_t b_spill = (size_t)e->grid * e->spill_bytes;
+  e->scratch_bytes = al(b_nodes) + al(b_eids) + al(b_bad) + al(b_prog) + al(b_spill);
   CUDA_OK(cudaMalloc(&e->d_scratch, e->scratch_bytes));
   char* base = (char*)e->d_scratch;
   p.nodes = (int32_t*)base; base += al(b_nodes);
@@ -163,6 +177,9 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   p.badpairs = b_bad ? (uint32_t*)base : nullptr; base += al(b_bad);
   p.work_counter = (unsigned long long*)base;
   p.progress = (int32_t*)(base + 256);
+  base += al(b_prog);
+  p.spill = b_spill ? (unsigned char*)base : nullptr;
+  p.spill_stride = (int64_t)e->spill_bytes;
   e->sched_bytes = b_prog;
   CUDA_OK(cudaEventCreate(&e->ev0));
   CUDA_OK(cudaEventCreate(&e->ev1));
@@ -211,7 +228,8 @@ int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   CUDA_OK(cudaEventRecord(e->ev0, s));
   CUDA_OK(cudaMemsetAsync(p.work_counter, 0, e->sched_bytes, s));
-  rc::recom_step_kernel<<<e->grid, e->threads, e->smem, s>>>(p);
+  void* args[] = {(void*)&p};
+  CUDA_OK(cudaLaunchKernel(e->kernel, dim3(e->grid), dim3(e->threads), args, e->smem, s));
   e->launches++;
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(e->ev1, s));
@@ -264,7 +282,8 @@ int rc_engine_replay(RcEngine* e, const RcReplay* rp, void* stream) {
   rc::Params p = e->p;
   p.rp = *rp;
   p.n_steps = rp->n_steps;
-  rc::recom_step_kernel<<<1, e->threads, e->smem, (cudaStream_t)stream>>>(p);
+  void* args[] = {(void*)&p};
+  CUDA_OK(cudaLaunchKernel(e->kernel, dim3(1), dim3(e->threads), args, e->smem, (cudaStream_t)stream));
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return RC_OK;

@@ -43,6 +43,8 @@ struct Params {
   unsigned long long* work_counter;  // persistent scheduling: next (chain, step) ticket
   int32_t* progress;      // [n_chains] steps of this launch completed per chain
   int32_t keep_counters;  // init_state_kernel: leave step/proposal numbers and counters alone
+  unsigned char* spill;   // spill mode: [grid][spill_stride] working arrays in global memory
+  int64_t spill_stride;
 };
 
 // ---- shared-memory carve-up -------------------------------------------------------
@@ -94,15 +96,21 @@ struct Smem {
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
-// N: nodes of the whole graph, CN/CE: caps of a merged pair, R: region columns
+// N: nodes of the whole graph, CN/CE: caps of a merged pair, R: region columns.
+// The first three arrays (misc, membership bitmap, its prefix) always live in shared memory
+// at `base`; the rest follows them there, or - when a merged pair does not fit the 227 KB
+// of an SM (spill mode) - sits in a per-CTA global scratch block at `big` (L2 resident).
+// Returns the total size; *split = size of the always-shared part.
 __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int N, int CN, int CE, int R,
-                                              int wilson) {
+                                              int wilson, unsigned char* big = nullptr, size_t* split_out = nullptr) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return r; };
   const int NW = (N + 31) / 32;
   size_t o_misc = take(128 * 4);
   size_t o_mbits = take(size_t(NW) * 4);
   size_t o_mpref = take(size_t(NW) * 2);
+  const size_t split = o;
+  if (split_out) *split_out = split;
   size_t o_pop = take(size_t(CN) * 4);
   size_t o_eu = take(size_t(CE) * 2);
   size_t o_ev = take(size_t(CE) * 2);
@@ -147,6 +155,7 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
     s->misc = (int32_t*)(base + o_misc);
     s->mbits = (uint32_t*)(base + o_mbits);
     s->mpref = (lid_t*)(base + o_mpref);
+    if (big) base = big - split;  // the offsets below are relative to the start of the layout
     s->pop = (int32_t*)(base + o_pop);
     s->eu = (lid_t*)(base + o_eu);
     s->ev = (lid_t*)(base + o_ev);

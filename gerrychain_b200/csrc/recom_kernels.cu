@@ -144,6 +144,7 @@ __device__ void build_local_adjacency(Chain& c, const Step& st) {
 
 // ---- P1: gather the merged pair into shared memory ---------------------------------------
 // returns RC_OK / RC_ERR_CAPACITY (block uniform)
+template <bool kWilson>
 __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
   const Params& p = *c.p;
   const Smem& s = c.s;
@@ -246,7 +247,7 @@ __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
   st.m = m;
   *d_sub_out = s.misc[M_CNT];
   if (m > p.cap_edges || m > 65535) return RC_ERR_CAPACITY;
-  if (p.cfg.tree_kind == RC_TREE_WILSON) build_local_adjacency(c, st);
+  if (kWilson) build_local_adjacency(c, st);
   return RC_OK;
 }
 
@@ -763,6 +764,7 @@ struct ProposalResult {
 };
 
 // One recom proposal + validity + commit (tree_proposals.py:36-146, chain.py:186-195).
+template <bool kWilson>
 __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep* rs,
                                   int32_t* ctr /* smem counters */) {
   const Params& p = *c.p;
@@ -807,7 +809,7 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
   if (resel && ((bad[(st.a * 256 + st.b) >> 5] >> ((st.a * 256 + st.b) & 31)) & 1)) continue;
   // ---- P1
   int d_sub = 0;
-  res.status = gather_pair(c, st, &d_sub);
+  res.status = gather_pair<kWilson>(c, st, &d_sub);
   if (tid == 0) { ctr[RC_CTR_NODES] += st.n; ctr[RC_CTR_SLOTS] += d_sub; }
   if (res.status) return res;
   const int n = st.n, nt = n - 1;
@@ -825,12 +827,12 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
       return res;
     }
     if (rs && (int)tree_no >= n_rec) { res.status = RC_ERR_REPLAY; return res; }
-    const bool wilson = p.cfg.tree_kind == RC_TREE_WILSON;
+    constexpr bool wilson = kWilson;
     const uint32_t* rrank = (rs && !wilson) ? p.rp.weight_rank + (rs->first_tree + tree_no) * (long long)p.g.E : nullptr;
     // ---- P2
     int rounds = 0;
-    res.status = wilson ? wilson_tree(c, st, tree_no, prop_no, rs ? rs->first_tree + tree_no : 0, ctr)
-                        : boruvka_mst(c, st, tree_no, prop_no, rrank, &rounds);
+    if (wilson) res.status = wilson_tree(c, st, tree_no, prop_no, rs ? rs->first_tree + tree_no : 0, ctr);
+    else res.status = boruvka_mst(c, st, tree_no, prop_no, rrank, &rounds);
     if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_ROUNDS] += rounds; }
     res.trees = (int)tree_no + 1;
     if (res.status) return res;
@@ -874,7 +876,7 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
         root = select_kth(c, n, (int)rc_below(r.v[0], r.v[1], (uint32_t)n_int), internal);
       }
       // ---- P5
-      const int policy = p.cfg.tree_kind == RC_TREE_WILSON ? RC_CUT_UNIFORM : p.cfg.cut_policy;
+      const int policy = kWilson ? RC_CUT_UNIFORM : p.cfg.cut_policy;
       if (rs && rs->cut_edge >= 0) {
         const int want = rs->cut_edge;
         tstar = select_kth(c, nt, 0, [&](int t) { return c.eids[s.te[t]] == want && is_bal(t); });
@@ -970,11 +972,13 @@ __device__ __forceinline__ void st_release(int32_t* p, int v) {
 // retries fall.  Step s of a chain waits (acquire) for step s-1 of the same chain, which an
 // earlier ticket - held by a CTA that is resident by construction - publishes (release).
 // Replay mode (TEST HOOK) is one CTA walking one chain through the record.
+template <bool kWilson, bool kSpill>
 __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Chain c;
   c.p = &p;
-  smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R, p.cfg.tree_kind == RC_TREE_WILSON);
+  smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R, kWilson,
+              kSpill ? p.spill + (size_t)blockIdx.x * p.spill_stride : nullptr);
   const int tid = threadIdx.x;
   c.nodes = p.nodes + (size_t)blockIdx.x * p.cap_nodes;
   c.eids = p.eids + (size_t)blockIdx.x * p.cap_edges;
@@ -1028,7 +1032,7 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
       const RcReplayStep* rs = replay ? p.rp.steps + t : nullptr;
       ProposalResult r = {RC_OK, 0, 0, 0};
       for (int streak = 0; streak < streak_cap; ++streak) {
-        r = propose(c, replay ? (uint32_t)t : prop_no, rs, ctr);
+        r = propose<kWilson>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
         ++prop_no;
         __syncthreads();
         if (r.status || r.accepted || replay) break;

@@ -75,3 +75,12 @@ def config3(n_chains=1024, **kw):
 def config5(n_chains=1024, **kw):
     """configs[4]: config 3 + 67 Voronoi counties, region_surcharge={"county": 0.5}."""
     return delaunay_workload(9000, 18, 0.02, n_chains, counties=67, **kw)
+
+
+def config4(n_chains=1024, **kw):
+    """configs[3]: Delaunay 200k nodes, 50 districts, eps 0.05, uniform_spanning_tree (Wilson).
+    Merged pairs (~8k nodes) exceed an SM's shared memory: the engine runs in spill mode."""
+    from . import _abi
+
+    kw.setdefault("tree_kind", _abi.RC_TREE_WILSON)
+    return delaunay_workload(200000, 50, 0.05, n_chains, pop_range=(20, 200), **kw)

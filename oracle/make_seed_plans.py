@@ -36,6 +36,7 @@ def make(n_nodes, k, eps, pop_range=(500, 2500)):
 
 
 if __name__ == "__main__":
-    make(9000, 18, 0.02)
-    if "--big" in sys.argv:
+    if "--only-big" not in sys.argv:
+        make(9000, 18, 0.02)
+    if "--big" in sys.argv or "--only-big" in sys.argv:
         make(200000, 50, 0.05, pop_range=(20, 200))
