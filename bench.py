@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--threads-per-cta", type=int, default=0)
+    ap.add_argument("--wilson", action="store_true", help="uniform_spanning_tree instead of random_spanning_tree")
+    ap.add_argument("--cap-nodes", type=int, default=0)
+    ap.add_argument("--cap-edges", type=int, default=0)
     return ap.parse_args()
 
 
@@ -73,12 +76,20 @@ def make_workload(args, n_chains, chain_offset=0):
     kw = dict(n_chains=n_chains, seed=args.seed, chain_offset=chain_offset)
     if args.threads_per_cta:
         kw["threads_per_cta"] = args.threads_per_cta
+    if args.wilson:
+        from gerrychain_b200 import _abi
+
+        kw["tree_kind"] = _abi.RC_TREE_WILSON
+    if args.cap_nodes:
+        kw["cap_nodes"] = args.cap_nodes
+    if args.cap_edges:
+        kw["cap_edges"] = args.cap_edges
     return fn(**kw)
 
 
 def config_dict(args, world, extra=None):
     d = {
-        "workload": WORKLOAD_NAMES[args.workload],
+        "workload": WORKLOAD_NAMES[args.workload] + (" [uniform_spanning_tree]" if args.wilson and args.workload != "config4" else ""),
         "chains_per_gpu": args.chains,
         "chains_total": args.chains * world,
         "chain_steps_per_bench_step": args.chain_steps,

@@ -167,7 +167,7 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   size_t b_eids = (size_t)e->grid * cap_edges * sizeof(int32_t);
   size_t b_bad = cfg->allow_pair_reselection ? (size_t)e->grid * 2048 * sizeof(uint32_t) : 0;
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-  size_t b_prog = 256 + (size_t)cfg->n_chains * sizeof(int32_t);
+  size_t b_prog = 512 + (size_t)cfg->n_chains * sizeof(int32_t);  // ticket, phase timers, progress words
   size_t b_spill = (size_t)e->grid * e->spill_bytes;
   e->scratch_bytes = al(b_nodes) + al(b_eids) + al(b_bad) + al(b_prog) + al(b_spill);
   CUDA_OK(cudaMalloc(&e->d_scratch, e->scratch_bytes));
@@ -176,7 +176,8 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   p.eids = (int32_t*)base; base += al(b_eids);
   p.badpairs = b_bad ? (uint32_t*)base : nullptr; base += al(b_bad);
   p.work_counter = (unsigned long long*)base;
-  p.progress = (int32_t*)(base + 256);
+  p.timers = (unsigned long long*)(base + 256);
+  p.progress = (int32_t*)(base + 512);
   base += al(b_prog);
   p.spill = b_spill ? (unsigned char*)base : nullptr;
   p.spill_stride = (int64_t)e->spill_bytes;
@@ -309,6 +310,15 @@ int rc_engine_info(RcEngine* e, RcEngineInfo* out) {
   out->threads_per_cta = e->threads; out->ctas_per_sm = e->ctas_per_sm; out->n_sms = e->n_sms;
   out->grid = e->grid; out->smem_bytes = (int64_t)e->smem; out->scratch_bytes = (int64_t)e->scratch_bytes;
   out->kernel_launches = e->launches;
+  return RC_OK;
+}
+
+/* dev tool (not in the public header): cycles per phase accumulated by an RC_TIMERS build
+ * during the last rc_engine_run */
+int rc_debug_phase_cycles(RcEngine* e, unsigned long long* out16) {
+  if (!e || !out16) return fail(RC_ERR_INVALID_ARG, "null argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaMemcpy(out16, e->p.timers, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return RC_OK;
 }
 

@@ -43,6 +43,7 @@ struct Params {
   unsigned long long* work_counter;  // persistent scheduling: next (chain, step) ticket
   int32_t* progress;      // [n_chains] steps of this launch completed per chain
   int32_t keep_counters;  // init_state_kernel: leave step/proposal numbers and counters alone
+  unsigned long long* timers;  // RC_TIMERS builds: cycles per phase (thread 0 of every CTA)
   unsigned char* spill;   // spill mode: [grid][spill_stride] working arrays in global memory
   int64_t spill_stride;
 };

@@ -423,6 +423,8 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
 // this is the tree - and the per-node draw counts - of the reference's sequential
 // loop-erased walks fed with the same stacks.  Short cycles (<= 4) are found by a local
 // look-ahead; what remains by pointer doubling over the functional graph.
+constexpr int kLook = 2;  // nodes per thread whose look-ahead result is staged in registers
+
 __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t prop_no, long long tree_idx,
                            int32_t* ctr) {
   const Params& p = *c.p;
@@ -473,16 +475,17 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     }
   }
   for (int i = tid; i < (m + 31) >> 5; i += T) s.tflag[i] = 0;
+  for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
   __syncthreads();
   if (s.misc[M_ERR]) return s.misc[M_ERR];
   int walk = 0;
   for (;;) {
     // local look-ahead: u is on a cycle of length <= 4 iff it comes back to itself
     for (;;) {
-      bool on[4];
+      bool on[kLook];
       int popped = 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < kLook; ++k) {
         const int u = tid + k * T;
         on[k] = false;
         if (u < n && u != root) {
@@ -492,20 +495,20 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
           on[k] = hit;
         }
       }
-      for (int u = tid + 4 * T; u < n; u += T) {  // merged pairs larger than 4 T nodes
+      for (int u = tid + kLook * T; u < n; u += T) {  // merged pairs larger than kLook * T nodes
         if (u == root) continue;
         const int v1 = succ_of(u), v2 = succ_of(v1), v3 = succ_of(v2);
         if (v2 == u || v3 == u || succ_of(v3) == u) atomicOr(&s.wmark[u >> 5], 1u << (u & 31));
       }
       __syncthreads();  // every pointer has been read
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < kLook; ++k)
         if (on[k]) { draw(tid + k * T); ++popped; }
-      for (int u = tid + 4 * T; u < n; u += T)
+      for (int u = tid + kLook * T; u < n; u += T)
         if ((s.wmark[u >> 5] >> (u & 31)) & 1u) { draw(u); ++popped; }
       walk += popped;
       const int any = __syncthreads_or(popped);
-      if (n > 4 * T) {
+      if (n > kLook * T) {
         for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
         __syncthreads();
       }
@@ -593,29 +596,34 @@ __device__ void euler_subtree_pops(Chain& c, const Step& st, int root) {
     s.W[a] = ((uint32_t)(a ^ 1) == hx && x != root) ? s.pop[x] : 0;
   }
   __syncthreads();
-  // E5: walk 1 - length and weight of every sublist
+  // E5: walk 1 - length and weight of every sublist.  A walk stops in front of the next
+  // splitter (every kStride-th arc, or the tour head) or at the arc that ends the tour.
   const int S = (L + kStride - 1) >> kStrideLog;
   const bool extra = (first & (kStride - 1)) != 0;  // the tour head is not a regular splitter
   const int S1 = S + (extra ? 1 : 0);
-  auto split_id = [&](int a) { return a == first ? (extra ? S : (a >> kStrideLog)) : ((a & (kStride - 1)) == 0 ? (a >> kStrideLog) : -1); };
   uint32_t* __restrict__ XA = s.spX;
   uint32_t* __restrict__ XB = s.spX + s.spCap;
   int32_t* __restrict__ YA = s.spY;
   int32_t* __restrict__ YB = s.spY + s.spCap;
   for (int k = tid; k < S1; k += T) {
     int a = k < S ? (k << kStrideLog) : first;
-    int len = 0, w = 0, next = k;
+    int len = 0, w = 0, nx;
     for (;;) {
       w += s.W[a];
       ++len;
-      const int nx = s.succ[a];
-      if (nx == a) { next = k; s.misc[M_TAILLEN] = len; len = 0; w = 0; break; }  // terminal sublist
-      const int sid = split_id(nx);
-      if (sid >= 0) { next = sid; break; }
+      nx = s.succ[a];
+      if (((nx & (kStride - 1)) == 0) | (nx == first) | (nx == a)) break;
       a = nx;
     }
-    XA[k] = ((uint32_t)next << 16) | (uint32_t)len;
-    YA[k] = w;
+    if (nx == a) {  // terminal sublist: distance 0 to itself, its length is kept aside
+      s.misc[M_TAILLEN] = len;
+      XA[k] = (uint32_t)k << 16;
+      YA[k] = 0;
+    } else {
+      const int next = (nx == first && extra) ? S : (nx >> kStrideLog);
+      XA[k] = ((uint32_t)next << 16) | (uint32_t)len;
+      YA[k] = w;
+    }
   }
   __syncthreads();
   // E6: rank the sublists (distance / weight from the start of sublist k to the terminal one)
@@ -638,12 +646,12 @@ __device__ void euler_subtree_pops(Chain& c, const Step& st, int root) {
     int w = -YA[k];
     for (;;) {
       const int wa = s.W[a];
+      const int nx = s.succ[a];
       s.P[a] = (lid_t)pos;
       s.W[a] = w;
       ++pos;
       w += wa;
-      const int nx = s.succ[a];
-      if (nx == a || split_id(nx) >= 0) break;
+      if (((nx & (kStride - 1)) == 0) | (nx == first) | (nx == a)) break;
       a = nx;
     }
   }
@@ -756,6 +764,16 @@ __device__ int choose_cut_by_weight(Chain& c, const Step& st, int policy, uint32
   return tstar;
 }
 
+// Phase timers: compiled in with -DRC_TIMERS (scripts/gpu_phases.sh); thread 0 of every CTA
+// adds clock64() deltas per phase to Params.timers (dev tool, not part of the product build).
+#ifdef RC_TIMERS
+#define RC_PH(i) do { if (threadIdx.x == 0) { unsigned long long* a_ = reinterpret_cast<unsigned long long*>(c.s.misc + 96); \
+  const unsigned long long t_ = (unsigned long long)clock64(); a_[i] += t_ - a_[15]; a_[15] = t_; } } while (0)
+#else
+#define RC_PH(i) do { } while (0)
+#endif
+enum { PH_OTHER = 0, PH_PICK, PH_GATHER, PH_TREE, PH_EULER, PH_BALANCE, PH_CHOOSE, PH_COMMIT, PH_N };
+
 struct ProposalResult {
   int status;     // RC_OK or error
   int accepted;   // committed
@@ -799,7 +817,9 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
     e = rs->pair_edge;
     if (e < 0 || e >= p.g.E || !((__ldcg(c.mask + (e >> 5)) >> (e & 31)) & 1)) { res.status = RC_ERR_REPLAY; return res; }
   } else {
+    RC_PH(PH_OTHER);
     e = pick_cut_edge(c, cut_count, prop_no, retry);
+    RC_PH(PH_PICK);
     if (e < 0) { res.status = RC_ERR_NO_CUT_EDGES; return res; }
   }
   {
@@ -810,6 +830,7 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
   // ---- P1
   int d_sub = 0;
   res.status = gather_pair<kWilson>(c, st, &d_sub);
+  RC_PH(PH_GATHER);
   if (tid == 0) { ctr[RC_CTR_NODES] += st.n; ctr[RC_CTR_SLOTS] += d_sub; }
   if (res.status) return res;
   const int n = st.n, nt = n - 1;
@@ -833,6 +854,7 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
     int rounds = 0;
     if (wilson) res.status = wilson_tree(c, st, tree_no, prop_no, rs ? rs->first_tree + tree_no : 0, ctr);
     else res.status = boruvka_mst(c, st, tree_no, prop_no, rrank, &rounds);
+    RC_PH(PH_TREE);
     if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_ROUNDS] += rounds; }
     res.trees = (int)tree_no + 1;
     if (res.status) return res;
@@ -841,6 +863,7 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
     if (n < 3) { res.status = RC_ERR_NO_ROOT; return res; }
     // ---- P3
     euler_subtree_pops(c, st, r0);
+    RC_PH(PH_EULER);
     // ---- P4: balanced tree edges (cur[t] = population below edge t)
     auto is_bal = [&](int t) { return balanced(s.cur[t], st.tot, ideal, thr); };
     {
@@ -853,6 +876,7 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
       __syncthreads();
     }
     const int nbal = s.misc[M_NBAL];
+    RC_PH(PH_BALANCE);
     res.nbal = nbal;
     if (nbal > 0) {
       const bool last_rec = rs && (int)tree_no == n_rec - 1;
@@ -902,6 +926,7 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
   }
   break;
   }  // pair loop
+  RC_PH(PH_CHOOSE);
   // ---- P6: the side holding the reference's root keeps the lower id (tree.py:421, :947-950)
   const int pa = s.P[2 * tstar], pb = s.P[2 * tstar + 1];
   const int pd = min(pa, pb), pu = max(pa, pb);
@@ -953,6 +978,7 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
     if (p.st.d_last_pair) { p.st.d_last_pair[2 * c.chain] = st.a; p.st.d_last_pair[2 * c.chain + 1] = st.b; }
   }
   __syncthreads();
+  RC_PH(PH_COMMIT);
   res.accepted = 1;
   return res;
 }
@@ -983,6 +1009,10 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
   c.nodes = p.nodes + (size_t)blockIdx.x * p.cap_nodes;
   c.eids = p.eids + (size_t)blockIdx.x * p.cap_edges;
   c.par = 0;
+#ifdef RC_TIMERS
+  if (tid < 30) c.s.misc[96 + tid] = 0;  // misc[96..127]: per-CTA phase cycles (+ last stamp), flushed at exit
+  if (tid == 0) reinterpret_cast<unsigned long long*>(c.s.misc + 96)[15] = (unsigned long long)clock64();
+#endif
   int32_t* ctr = c.s.misc + M_CTR;  // [RC_N_COUNTERS]
   if (tid < RC_N_COUNTERS) ctr[tid] = 0;
   __syncthreads();
@@ -1062,6 +1092,10 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
     if (!replay && tid == 0) st_release(p.progress + chain, seg + 1);
     if (replay && status != RC_OK) break;
   }
+#ifdef RC_TIMERS
+  __syncthreads();
+  if (tid < PH_N) atomicAdd(p.timers + tid, reinterpret_cast<unsigned long long*>(c.s.misc + 96)[tid]);
+#endif
 }
 
 // ---- state kernels -----------------------------------------------------------------------

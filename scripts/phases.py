@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Dev tool: per-phase cycle breakdown of the chain-step kernel from an RC_TIMERS build.
+
+    nvcc ... -DRC_TIMERS -o variants/lib_timers.so   (scripts/build_timers.sh)
+    RECOM_B200_LIB=variants/lib_timers.so python scripts/phases.py --workload config2
+"""
+import argparse, ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from gerrychain_b200 import workloads, _abi
+from gerrychain_b200.engine import Engine
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="config2")
+ap.add_argument("--chains", type=int, default=1024)
+ap.add_argument("--chain-steps", type=int, default=8)
+ap.add_argument("--cap-nodes", type=int, default=0)
+ap.add_argument("--cap-edges", type=int, default=0)
+ap.add_argument("--wilson", action="store_true")
+a = ap.parse_args()
+kw = dict(n_chains=a.chains, seed=5, cap_nodes=a.cap_nodes, cap_edges=a.cap_edges)
+if a.wilson:
+    kw["tree_kind"] = _abi.RC_TREE_WILSON
+csr, plan, cfg = getattr(workloads, a.workload)(**kw)
+eng = Engine(csr, cfg, plan)
+eng.run(4).synchronize()
+eng.run(a.chain_steps).synchronize()
+ms = eng.last_run_ms()
+out = (C.c_ulonglong * 16)()
+eng.lib.rc_debug_phase_cycles.argtypes = [C.c_void_p, C.c_void_p]
+eng.lib.rc_debug_phase_cycles(eng._handle, out)
+names = ["other/handoff", "pick", "gather", "tree", "euler", "balance", "choose", "commit"]
+tot = sum(out[:8]) or 1
+info = eng.info()
+steps = a.chains * a.chain_steps
+ctr = eng.counters.sum(0).cpu().numpy()
+print(f"{a.workload} wilson={a.wilson} chains={a.chains} steps/chain={a.chain_steps}: {ms:.2f} ms, "
+      f"{steps / ms * 1e3:.0f} steps/s, smem {info.smem_bytes} B, ctas/sm {info.ctas_per_sm}, grid {info.grid}")
+for n, v in zip(names, out[:8]):
+    print(f"  {n:14s} {100 * v / tot:5.1f}%  {v / steps:12.0f} cycles/step (thread 0 of one CTA)")
