@@ -40,8 +40,10 @@ struct Params {
   int32_t* nodes;     // [grid][cap_nodes] local -> global node
   int32_t* eids;      // [grid][cap_edges] local edge -> global edge id
   uint32_t* badpairs; // [grid][2048] bitset of (a*256+b), pair reselection only
-  unsigned long long* work_counter;  // persistent scheduling: next (chain, step) ticket
+  unsigned long long* work_counter;  // [2] persistent scheduling: pop index, push index
   int32_t* progress;      // [n_chains] steps of this launch completed per chain
+  int32_t* ring;          // [ring_cap] ready chains (chain id + 1; 0 = empty)
+  int32_t ring_cap;
   int32_t keep_counters;  // init_state_kernel: leave step/proposal numbers and counters alone
   unsigned long long* timers;  // RC_TIMERS builds: cycles per phase (thread 0 of every CTA)
   unsigned char* spill;   // spill mode: [grid][spill_stride] working arrays in global memory

@@ -424,6 +424,7 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
 // loop-erased walks fed with the same stacks.  Short cycles (<= 4) are found by a local
 // look-ahead; what remains by pointer doubling over the functional graph.
 constexpr int kLook = 2;  // nodes per thread whose look-ahead result is staged in registers
+constexpr int kSeqThreshold = 24;  // fewer busy threads than this: finish sequentially
 
 __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t prop_no, long long tree_idx,
                            int32_t* ctr) {
@@ -478,68 +479,95 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
   for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
   __syncthreads();
   if (s.misc[M_ERR]) return s.misc[M_ERR];
-  int walk = 0;
+  int walk = 0, passes = 0;
+  // Phase 1 - while many cycles exist, pop them in parallel: u is on a cycle of length <= 4
+  // iff following the pointers brings it back to itself.  (Early on about a third of all
+  // nodes sit on such a cycle; the yield decays quickly.)
   for (;;) {
-    // local look-ahead: u is on a cycle of length <= 4 iff it comes back to itself
-    for (;;) {
-      bool on[kLook];
-      int popped = 0;
-#pragma unroll
-      for (int k = 0; k < kLook; ++k) {
-        const int u = tid + k * T;
-        on[k] = false;
-        if (u < n && u != root) {
-          const int v1 = succ_of(u), v2 = succ_of(v1);
-          bool hit = v2 == u;
-          if (!hit) { const int v3 = succ_of(v2); hit = v3 == u || succ_of(v3) == u; }
-          on[k] = hit;
-        }
-      }
-      for (int u = tid + kLook * T; u < n; u += T) {  // merged pairs larger than kLook * T nodes
-        if (u == root) continue;
-        const int v1 = succ_of(u), v2 = succ_of(v1), v3 = succ_of(v2);
-        if (v2 == u || v3 == u || succ_of(v3) == u) atomicOr(&s.wmark[u >> 5], 1u << (u & 31));
-      }
-      __syncthreads();  // every pointer has been read
-#pragma unroll
-      for (int k = 0; k < kLook; ++k)
-        if (on[k]) { draw(tid + k * T); ++popped; }
-      for (int u = tid + kLook * T; u < n; u += T)
-        if ((s.wmark[u >> 5] >> (u & 31)) & 1u) { draw(u); ++popped; }
-      walk += popped;
-      const int any = __syncthreads_or(popped);
-      if (n > kLook * T) {
-        for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
-        __syncthreads();
-      }
-      if (!any) break;
-    }
-    // global detection: after >= n steps of the functional graph every node sits on a cycle
-    // or at the root, and every cycle node is somebody's landing point
-    for (int u = tid; u < n; u += T) s.wgA[u] = (lid_t)succ_of(u);
-    for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
-    __syncthreads();
-    lid_t* __restrict__ A = s.wgA;
-    lid_t* __restrict__ B = s.wgB;
-    for (int span = 1; span < n; span <<= 1) {
-      for (int u = tid; u < n; u += T) B[u] = A[A[u]];
-      __syncthreads();
-      lid_t* tmp = A; A = B; B = tmp;
-    }
-    for (int u = tid; u < n; u += T) {
-      const int v = A[u];
-      if (v != root) atomicOr(&s.wmark[v >> 5], 1u << (v & 31));
-    }
-    __syncthreads();
+    bool on[kLook];
     int popped = 0;
-    for (int u = tid; u < n; u += T)
+#pragma unroll
+    for (int k = 0; k < kLook; ++k) {
+      const int u = tid + k * T;
+      on[k] = false;
+      if (u < n && u != root) {
+        const int v1 = succ_of(u), v2 = succ_of(v1);
+        bool hit = v2 == u;
+        if (!hit) { const int v3 = succ_of(v2); hit = v3 == u || succ_of(v3) == u; }
+        on[k] = hit;
+      }
+    }
+    for (int u = tid + kLook * T; u < n; u += T) {  // merged pairs larger than kLook * T nodes
+      if (u == root) continue;
+      const int v1 = succ_of(u), v2 = succ_of(v1), v3 = succ_of(v2);
+      if (v2 == u || v3 == u || succ_of(v3) == u) atomicOr(&s.wmark[u >> 5], 1u << (u & 31));
+    }
+    __syncthreads();  // every pointer has been read
+#pragma unroll
+    for (int k = 0; k < kLook; ++k)
+      if (on[k]) { draw(tid + k * T); ++popped; }
+    for (int u = tid + kLook * T; u < n; u += T)
       if ((s.wmark[u >> 5] >> (u & 31)) & 1u) { draw(u); ++popped; }
     walk += popped;
-    const int any = __syncthreads_or(popped);
-    for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
-    __syncthreads();
-    if (!any) break;
+    const int busy = __syncthreads_count(popped > 0);
+    if (n > kLook * T) {
+      for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
+      __syncthreads();
+    }
+    if (busy < kSeqThreshold || ++passes > 64) break;
   }
+  // Phase 2 - which nodes already lead to the root?  After >= n steps of the functional
+  // graph every node sits on a cycle or at the root.
+  for (int u = tid; u < n; u += T) s.wgA[u] = (lid_t)succ_of(u);
+  for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
+  __syncthreads();
+  lid_t* __restrict__ A = s.wgA;
+  lid_t* __restrict__ B = s.wgB;
+  for (int span = 1; span < n; span <<= 1) {
+    for (int u = tid; u < n; u += T) B[u] = A[A[u]];
+    __syncthreads();
+    lid_t* tmp = A; A = B; B = tmp;
+  }
+  for (int u = tid; u < n; u += T) {
+    if ((int)A[u] == root) atomicOr(&s.wmark[u >> 5], 1u << (u & 31));  // wmark: in the tree
+    B[u] = 0;                                                              // B: walk stamps
+  }
+  __syncthreads();
+  // Phase 3 - the remaining cycles hang on a handful of components that pop one after the
+  // other (the long tail of Wilson's algorithm is sequential): one thread finishes them as
+  // loop-erased walks over the current pointers, drawing only where a loop closes.
+  if (tid == 0) {
+    lid_t* stamp = B;
+    auto in_tree = [&](int u) { return (s.wmark[u >> 5] >> (u & 31)) & 1u; };
+    // a connected pair needs ~10-20 draws per node; a walk that cannot reach the root
+    // (disconnected input plan) is cut off instead of spinning for ever
+    const long long budget = 2048ll * n + 65536;
+    long long spent = 0;
+    for (int node = 0; node < n && spent <= budget; ++node) {
+      if (in_tree(node)) continue;
+      const lid_t id = (lid_t)(node + 1);
+      int u = node;
+      while (!in_tree(u) && spent <= budget) {
+        if (stamp[u] == id) {  // the walk closed a loop at u: pop it
+          int v = u;
+          do {
+            const int w = succ_of(v);
+            draw(v);
+            stamp[v] = 0;
+            ++walk;
+            v = w;
+          } while (v != u);
+        }
+        stamp[u] = id;
+        u = succ_of(u);
+        ++spent;
+      }
+      if (spent > budget) break;
+      for (u = node; !in_tree(u); u = succ_of(u)) s.wmark[u >> 5] |= 1u << (u & 31);
+    }
+    if (spent > budget && !s.misc[M_ERR]) s.misc[M_ERR] = RC_ERR_DISCONNECTED;
+  }
+  __syncthreads();
   if (s.misc[M_ERR]) return s.misc[M_ERR];
   // the tree: edge (u, successor of u) for every node but the root
   for (int u = tid; u < n; u += T) {
@@ -772,7 +800,7 @@ __device__ int choose_cut_by_weight(Chain& c, const Step& st, int policy, uint32
 #else
 #define RC_PH(i) do { } while (0)
 #endif
-enum { PH_OTHER = 0, PH_PICK, PH_GATHER, PH_TREE, PH_EULER, PH_BALANCE, PH_CHOOSE, PH_COMMIT, PH_N };
+enum { PH_OTHER = 0, PH_PICK, PH_GATHER, PH_TREE, PH_EULER, PH_BALANCE, PH_CHOOSE, PH_COMMIT, PH_FLUSH, PH_TICKET, PH_STATE, PH_N };
 
 struct ProposalResult {
   int status;     // RC_OK or error
@@ -1021,35 +1049,45 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
   const unsigned long long total =
       replay ? (unsigned long long)p.rp.n_steps : (unsigned long long)n_chains * (unsigned long long)p.n_steps;
   const int streak_cap = p.cfg.max_invalid_streak > 0 ? p.cfg.max_invalid_streak : 1000;
-  // ticket hand-out: thread 0 fetches the NEXT ticket while the current step runs, waits for
-  // that chain's previous step, and publishes the ticket through one of two alternating
-  // shared slots - one barrier per step on this path
-  unsigned long long* slots = reinterpret_cast<unsigned long long*>(&c.s.misc[M_TICKET]);
+  // Work queue of READY chains (free-running mode).  Pop index h < n_chains takes chain h;
+  // later pops take ring slot h - n_chains, which the CTA that finished a step of some chain
+  // fills (release) once that chain's state is in L2.  A chain is in the ring at most once,
+  // so a slow step (many retries) delays only its own chain: no CTA ever waits while another
+  // chain is ready.
+  int32_t* tslot = &c.s.misc[M_TICKET];
   unsigned long long rt = 0;  // replay: steps are taken in order
-  unsigned long long pre = 0;  // thread 0: prefetched ticket
+  const unsigned long long cap = (unsigned long long)p.ring_cap;
   int flip = 0;
-  if (!replay && tid == 0) pre = atomicAdd(p.work_counter, 1ull);
   for (;;) {
     unsigned long long t;
+    int chain;
     if (replay) {
       t = rt++;
+      chain = p.rp.chain;
     } else {
       if (tid == 0) {
-        if (pre < total) {
-          const int ch = (int)(pre % (unsigned long long)n_chains);
-          const int sg = (int)(pre / (unsigned long long)n_chains);
-          while (ld_acquire(p.progress + ch) < sg) __nanosleep(32);
+        const unsigned long long h = atomicAdd(p.work_counter, 1ull);
+        int ch = -1;
+        if (h < total) {
+          if (h < (unsigned long long)n_chains) {
+            ch = (int)h;
+          } else {
+            int32_t* slot = p.ring + (h - (unsigned long long)n_chains) % cap;
+            int v;
+            while ((v = ld_acquire(slot)) == 0) __nanosleep(32);
+            st_release(slot, 0);  // the slot may be refilled cap pushes later
+            ch = v - 1;
+          }
         }
-        slots[flip] = pre;
+        tslot[flip] = ch;
       }
       __syncthreads();
-      t = slots[flip];
+      chain = tslot[flip];
       flip ^= 1;
-      if (tid == 0 && t < total) pre = atomicAdd(p.work_counter, 1ull);  // in flight during the step
+      RC_PH(PH_TICKET);
+      t = chain < 0 ? total : 0;
     }
     if (t >= total) break;
-    const int chain = replay ? p.rp.chain : (int)(t % (unsigned long long)n_chains);
-    const int seg = replay ? 0 : (int)(t / (unsigned long long)n_chains);
     c.chain = chain;
     c.gchain = (uint32_t)(chain + p.cfg.chain_offset);
     c.assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
@@ -1059,6 +1097,7 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
     if (status == RC_OK) {
       // one accepted step (chain.py:185-195): propose until valid, accept always
       uint32_t prop_no = __ldcg(p.st.d_proposal_no + chain);
+      RC_PH(PH_STATE);
       const RcReplayStep* rs = replay ? p.rp.steps + t : nullptr;
       ProposalResult r = {RC_OK, 0, 0, 0};
       for (int streak = 0; streak < streak_cap; ++streak) {
@@ -1089,7 +1128,17 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
     }
     __threadfence();
     __syncthreads();
-    if (!replay && tid == 0) st_release(p.progress + chain, seg + 1);
+    RC_PH(PH_FLUSH);
+    if (!replay && tid == 0) {
+      const int done = p.progress[chain] + 1;  // this CTA owns the chain until it is pushed back
+      p.progress[chain] = done;
+      if (done < p.n_steps) {
+        const unsigned long long q = atomicAdd(p.work_counter + 1, 1ull);
+        int32_t* slot = p.ring + q % cap;
+        while (ld_acquire(slot) != 0) __nanosleep(32);  // its previous content has been taken
+        st_release(slot, chain + 1);
+      }
+    }
     if (replay && status != RC_OK) break;
   }
 #ifdef RC_TIMERS
