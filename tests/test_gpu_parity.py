@@ -222,6 +222,52 @@ def test_config4_wilson_200k_nodes():
     _free_run_vs_oracle(csr, plan, cfg, 3)
 
 
+def test_edge_cases_status_words():
+    """Inputs the reference rejects or chokes on map to status words, never to a hang:
+    a plan whose district is disconnected (merged pair not connected), a merged pair larger
+    than the engine's caps, a plan with a single district (no cut edges), out-of-range ids."""
+    from gerrychain_b200.engine import Engine, EngineError
+
+    csr, plan, cfg = workloads.config1(n_chains=4, seed=1)
+    # (1) district 0 split into two far-apart blobs: every pair containing it is disconnected
+    bad = plan.copy().reshape(20, 20)
+    bad[:, :] = 1
+    bad[0:2, 0:2] = 0
+    bad[18:20, 18:20] = 0
+    bad[10:20, 0:10] = 2
+    bad[0:10, 10:20] = 3
+    for tree_kind in (_abi.RC_TREE_MST, _abi.RC_TREE_WILSON):
+        cfg2 = workloads.config1(n_chains=4, seed=1, tree_kind=tree_kind, cap_nodes=400, cap_edges=760)[2]
+        cfg2.pop_lower, cfg2.pop_upper = 1.0, 0.0  # no bounds: the plan is unbalanced on purpose
+        cfg2.epsilon = 0.9
+        eng = Engine(csr, cfg2, bad.reshape(-1))
+        eng.run(30).synchronize()
+        st = eng.status.cpu().numpy()
+        assert set(st.tolist()) <= {_abi.RC_OK, _abi.RC_ERR_DISCONNECTED}
+        assert (st == _abi.RC_ERR_DISCONNECTED).any()
+    # (2) caps smaller than a merged pair
+    cfg3 = workloads.config1(n_chains=2, seed=1, cap_nodes=64, cap_edges=128)[2]
+    eng = Engine(csr, cfg3, plan)
+    eng.run(1).synchronize()
+    assert (eng.status.cpu().numpy() == _abi.RC_ERR_CAPACITY).all()
+    with pytest.raises(EngineError):
+        eng.check_status()
+    # (3) one district only: no cut edges to pick from (random.choice(()) in the reference)
+    cfg4 = workloads.config1(n_chains=2, seed=1)[2]
+    eng = Engine(csr, cfg4, np.zeros(csr.n_nodes, dtype=np.uint8))
+    eng.run(1).synchronize()
+    assert (eng.status.cpu().numpy() == _abi.RC_ERR_NO_CUT_EDGES).all()
+    # (4) ids outside [0, k)
+    with pytest.raises(ValueError):
+        Engine(csr, cfg4, np.full(csr.n_nodes, 9, dtype=np.uint8))
+    # (5) single chain, many districts (k = 100 on a 20x20 grid: 4-node districts, pairs of 8 nodes)
+    k = 100
+    tiny = (np.arange(400).reshape(20, 20) // 40 * 10 + np.arange(400).reshape(20, 20) % 20 // 2).astype(np.uint8)
+    from gerrychain_b200.config import EngineConfig
+    cfg5 = EngineConfig(n_districts=k, n_chains=3, pop_target=4.0, epsilon=0.3, seed=3)
+    _free_run_vs_oracle(csr, tiny.reshape(-1), cfg5, 40)
+
+
 def test_histograms():
     csr, plan, cfg = workloads.config1(n_chains=128, seed=2)
     eng = _engine(csr, cfg, plan)
