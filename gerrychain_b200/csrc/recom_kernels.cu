@@ -251,6 +251,16 @@ __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
   return RC_OK;
 }
 
+// Phase timers: compiled in with -DRC_TIMERS (scripts/gpu_phases.sh); thread 0 of every CTA
+// adds clock64() deltas per phase to Params.timers (dev tool, not part of the product build).
+#ifdef RC_TIMERS
+#define RC_PH(i) do { if (threadIdx.x == 0) { unsigned long long* a_ = reinterpret_cast<unsigned long long*>(c.s.misc + 96); \
+  const unsigned long long t_ = (unsigned long long)clock64(); a_[i] += t_ - a_[15]; a_[15] = t_; } } while (0)
+#else
+#define RC_PH(i) do { } while (0)
+#endif
+enum { PH_OTHER = 0, PH_PICK, PH_GATHER, PH_TREE, PH_EULER, PH_BALANCE, PH_CHOOSE, PH_COMMIT, PH_FLUSH, PH_TICKET, PH_STATE, PH_W1, PH_W2, PH_W3, PH_N };
+
 // te[0..n-2] = the tree edges flagged in tflag, ascending local edge index (8 edges per
 // thread step); RC_ERR_DISCONNECTED unless there are exactly n - 1
 __device__ int tree_edge_list(Chain& c, const Step& st) {
@@ -425,6 +435,7 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
 // look-ahead; what remains by pointer doubling over the functional graph.
 constexpr int kLook = 2;  // nodes per thread whose look-ahead result is staged in registers
 constexpr int kSeqThreshold = 24;  // fewer busy threads than this: finish sequentially
+constexpr int kTab = 8;  // draws per node precomputed for the sequential finish
 
 __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t prop_no, long long tree_idx,
                            int32_t* ctr) {
@@ -460,18 +471,22 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
       }
       if (slot < 0) { s.misc[M_ERR] = RC_ERR_REPLAY; slot = r0; }
       s.wsl[u] = (lid_t)slot;
+      s.wnx[u] = s.ladj[slot];
     } else {
       const RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WALK, (uint32_t)u, tree_no, prop_no, j >> 2);
-      s.wsl[u] = (lid_t)(r0 + (int)rc_below32(r.v[j & 3u], (uint32_t)d));
+      const int slot = r0 + (int)rc_below32(r.v[j & 3u], (uint32_t)d);
+      s.wsl[u] = (lid_t)slot;
+      s.wnx[u] = s.ladj[slot];
     }
   };
-  auto succ_of = [&](int u) { return u == root ? u : (int)s.ladj[s.wsl[u]]; };
+  auto succ_of = [&](int u) { return (int)s.wnx[u]; };  // wnx[root] == root
   if (tid == 0) s.misc[M_ERR] = 0;
   for (int u = tid; u < n; u += T) {
     s.wcnt[u] = 0;
     if (u != root) {
       if (s.loff[u + 1] == s.loff[u]) s.misc[M_ERR] = RC_ERR_DISCONNECTED; else draw(u);
     } else {
+      s.wnx[u] = (lid_t)u;
       s.wsl[u] = 0;
     }
   }
@@ -516,6 +531,7 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     }
     if (busy < kSeqThreshold || ++passes > 64) break;
   }
+  RC_PH(PH_W1);
   // Phase 2 - which nodes already lead to the root?  After >= n steps of the functional
   // graph every node sits on a cycle or at the root.
   for (int u = tid; u < n; u += T) s.wgA[u] = (lid_t)succ_of(u);
@@ -528,17 +544,43 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     __syncthreads();
     lid_t* tmp = A; A = B; B = tmp;
   }
+  // ... and, for the sequential part, the next kTab draws of every node computed by all
+  // threads (a draw is a pure function of (node, draw number)): slot offsets within the row
   for (int u = tid; u < n; u += T) {
     if ((int)A[u] == root) atomicOr(&s.wmark[u >> 5], 1u << (u & 31));  // wmark: in the tree
     B[u] = 0;                                                              // B: walk stamps
+    const uint32_t j0 = s.wcnt[u];
+    s.wbase[u] = (lid_t)j0;
+    if (!replay && u != root) {
+      const uint32_t d = (uint32_t)(s.loff[u + 1] - s.loff[u]);
+      RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WALK, (uint32_t)u, tree_no, prop_no, j0 >> 2);
+#pragma unroll
+      for (int q = 0; q < kTab; ++q) {
+        const uint32_t j = j0 + q;
+        if (q && (j & 3u) == 0) r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WALK, (uint32_t)u, tree_no, prop_no, j >> 2);
+        s.wtab[u * kTab + q] = (uint8_t)rc_below32(r.v[j & 3u], d);
+      }
+    }
   }
   __syncthreads();
+  RC_PH(PH_W2);
   // Phase 3 - the remaining cycles hang on a handful of components that pop one after the
   // other (the long tail of Wilson's algorithm is sequential): one thread finishes them as
   // loop-erased walks over the current pointers, drawing only where a loop closes.
   if (tid == 0) {
     lid_t* stamp = B;
     auto in_tree = [&](int u) { return (s.wmark[u >> 5] >> (u & 31)) & 1u; };
+    auto pop = [&](int v) {  // node v takes its next draw
+      const uint32_t q = (uint32_t)s.wcnt[v] - (uint32_t)s.wbase[v];
+      if (!replay && q < (uint32_t)kTab && s.loff[v + 1] - s.loff[v] <= 256) {
+        const int slot = s.loff[v] + (int)s.wtab[v * kTab + q];
+        s.wcnt[v] = (lid_t)(s.wcnt[v] + 1);
+        s.wsl[v] = (lid_t)slot;
+        s.wnx[v] = s.ladj[slot];
+      } else {
+        draw(v);
+      }
+    };
     // a connected pair needs ~10-20 draws per node; a walk that cannot reach the root
     // (disconnected input plan) is cut off instead of spinning for ever
     const long long budget = 2048ll * n + 65536;
@@ -551,22 +593,23 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
         if (stamp[u] == id) {  // the walk closed a loop at u: pop it
           int v = u;
           do {
-            const int w = succ_of(v);
-            draw(v);
+            const int w = s.wnx[v];
+            pop(v);
             stamp[v] = 0;
             ++walk;
             v = w;
           } while (v != u);
         }
         stamp[u] = id;
-        u = succ_of(u);
+        u = s.wnx[u];
         ++spent;
       }
       if (spent > budget) break;
-      for (u = node; !in_tree(u); u = succ_of(u)) s.wmark[u >> 5] |= 1u << (u & 31);
+      for (u = node; !in_tree(u); u = s.wnx[u]) s.wmark[u >> 5] |= 1u << (u & 31);
     }
     if (spent > budget && !s.misc[M_ERR]) s.misc[M_ERR] = RC_ERR_DISCONNECTED;
   }
+  RC_PH(PH_W3);
   __syncthreads();
   if (s.misc[M_ERR]) return s.misc[M_ERR];
   // the tree: edge (u, successor of u) for every node but the root
@@ -791,16 +834,6 @@ __device__ int choose_cut_by_weight(Chain& c, const Step& st, int policy, uint32
   __syncthreads();
   return tstar;
 }
-
-// Phase timers: compiled in with -DRC_TIMERS (scripts/gpu_phases.sh); thread 0 of every CTA
-// adds clock64() deltas per phase to Params.timers (dev tool, not part of the product build).
-#ifdef RC_TIMERS
-#define RC_PH(i) do { if (threadIdx.x == 0) { unsigned long long* a_ = reinterpret_cast<unsigned long long*>(c.s.misc + 96); \
-  const unsigned long long t_ = (unsigned long long)clock64(); a_[i] += t_ - a_[15]; a_[15] = t_; } } while (0)
-#else
-#define RC_PH(i) do { } while (0)
-#endif
-enum { PH_OTHER = 0, PH_PICK, PH_GATHER, PH_TREE, PH_EULER, PH_BALANCE, PH_CHOOSE, PH_COMMIT, PH_FLUSH, PH_TICKET, PH_STATE, PH_N };
 
 struct ProposalResult {
   int status;     // RC_OK or error

@@ -1,8 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/gpu_tests_16.log
-rm -f gpurun_out/ab.log gpurun_out/ab.err
-bash scripts/gpu_ab.sh o r
-{
-RECOM_B200_LIB=$PWD/variants/lib_timers.so python scripts/phases.py --workload config2 --chain-steps 32
-RECOM_B200_LIB=$PWD/variants/lib_timers.so python scripts/phases.py --workload config3 --chain-steps 32
-} > gpurun_out/phases.log 2>&1
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/gpu_tests_21.log
+python bench.py --workload config3 --wilson --chain-steps 16 --steps 10 --warmup 2 --no-cpu-baseline > gpurun_out/bench_c3w3.json 2> gpurun_out/bench_c3w3.err
+timeout 500 python bench.py --workload config4 --chains 1024 --chain-steps 4 --steps 4 --warmup 2 --no-cpu-baseline > gpurun_out/bench_c4c.json 2>> gpurun_out/bench_c3w3.err
+python bench.py --workload config1 --wilson --no-cpu-baseline --steps 20 > gpurun_out/bench_c1w2.json 2>> gpurun_out/bench_c3w3.err
