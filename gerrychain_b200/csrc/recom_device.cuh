@@ -79,8 +79,8 @@ struct Smem {
   lid_t* wgB;        // [CN] pointer doubling, pong
   uint32_t* wmark;   // [CN/32] nodes found on a cycle; later: nodes in the tree
   lid_t* wnx;        // [CN] current successor of u (== ladj[wsl[u]]; the root points at itself)
-  lid_t* wbase;      // [CN] draw number the table of u starts at
-  uint8_t* wtab;     // [CN][8] next draws of u as offsets into its adjacency row
+  unsigned long long* wst;  // [CN] sequential finish: successor | stamp | draws | table base
+  lid_t* wtab;       // [CN][8] the next 8 successors of u (draws base .. base + 7)
   uint32_t* best;    // [CN] minimum key over the live edges of a component
   uint32_t* bpos;    // [CN] (local edge << 16 | live-list position) of that minimum
   lid_t* hook;       // [CN] component merge forest
@@ -144,8 +144,8 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
   size_t o_wgB = take(wilson ? size_t(CN) * 2 : 0);
   size_t o_wmark = take(wilson ? size_t((CN + 31) / 32) * 4 : 0);
   size_t o_wnx = take(wilson ? size_t(CN) * 2 : 0);
-  size_t o_wbase = take(wilson ? size_t(CN) * 2 : 0);
-  size_t o_wtab = take(wilson ? size_t(CN) * 8 : 0);
+  size_t o_wst = take(wilson ? size_t(CN) * 8 : 0);
+  size_t o_wtab = take(wilson ? size_t(CN) * 16 : 0);
   size_t end_a = o;
   // Euler phase
   o = phase;
@@ -182,8 +182,8 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
     s->wgB = (lid_t*)(base + o_wgB);
     s->wmark = (uint32_t*)(base + o_wmark);
     s->wnx = (lid_t*)(base + o_wnx);
-    s->wbase = (lid_t*)(base + o_wbase);
-    s->wtab = (uint8_t*)(base + o_wtab);
+    s->wst = (unsigned long long*)(base + o_wst);
+    s->wtab = (lid_t*)(base + o_wtab);
     s->key = (uint32_t*)(base + o_key);
     s->lab = (uint32_t*)(base + o_lab);
     s->lj = (lid_t*)(base + o_lj);

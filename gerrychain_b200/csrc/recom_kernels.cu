@@ -436,6 +436,7 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
 constexpr int kLook = 2;  // nodes per thread whose look-ahead result is staged in registers
 constexpr int kSeqThreshold = 24;  // fewer busy threads than this: finish sequentially
 constexpr int kTab = 8;  // draws per node precomputed for the sequential finish
+constexpr uint32_t kInTree = 0xffffu;  // walk stamp of a node that leads to the root
 
 __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t prop_no, long long tree_idx,
                            int32_t* ctr) {
@@ -535,7 +536,6 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
   // Phase 2 - which nodes already lead to the root?  After >= n steps of the functional
   // graph every node sits on a cycle or at the root.
   for (int u = tid; u < n; u += T) s.wgA[u] = (lid_t)succ_of(u);
-  for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
   __syncthreads();
   lid_t* __restrict__ A = s.wgA;
   lid_t* __restrict__ B = s.wgB;
@@ -544,21 +544,25 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     __syncthreads();
     lid_t* tmp = A; A = B; B = tmp;
   }
-  // ... and, for the sequential part, the next kTab draws of every node computed by all
-  // threads (a draw is a pure function of (node, draw number)): slot offsets within the row
+  // ... and, for the sequential part, one packed state word per node - successor, walk
+  // stamp (kInTree: leads to the root), draws consumed, first tabulated draw - plus the next
+  // kTab successors of every node, computed by all threads (a draw is a pure function of
+  // (node, draw number)).  One 64-bit load per walk step, one 128-bit load per pop.
+  unsigned long long* __restrict__ wst = s.wst;
   for (int u = tid; u < n; u += T) {
-    if ((int)A[u] == root) atomicOr(&s.wmark[u >> 5], 1u << (u & 31));  // wmark: in the tree
-    B[u] = 0;                                                              // B: walk stamps
     const uint32_t j0 = s.wcnt[u];
-    s.wbase[u] = (lid_t)j0;
+    const uint32_t stamp = (int)A[u] == root ? kInTree : 0u;
+    wst[u] = (unsigned long long)s.wnx[u] | ((unsigned long long)stamp << 16) |
+             ((unsigned long long)j0 << 32) | ((unsigned long long)j0 << 48);
     if (!replay && u != root) {
-      const uint32_t d = (uint32_t)(s.loff[u + 1] - s.loff[u]);
+      const int r0 = s.loff[u];
+      const uint32_t d = (uint32_t)(s.loff[u + 1] - r0);
       RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WALK, (uint32_t)u, tree_no, prop_no, j0 >> 2);
 #pragma unroll
       for (int q = 0; q < kTab; ++q) {
         const uint32_t j = j0 + q;
         if (q && (j & 3u) == 0) r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WALK, (uint32_t)u, tree_no, prop_no, j >> 2);
-        s.wtab[u * kTab + q] = (uint8_t)rc_below32(r.v[j & 3u], d);
+        s.wtab[u * kTab + q] = s.ladj[r0 + (int)rc_below32(r.v[j & 3u], d)];
       }
     }
   }
@@ -568,56 +572,72 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
   // other (the long tail of Wilson's algorithm is sequential): one thread finishes them as
   // loop-erased walks over the current pointers, drawing only where a loop closes.
   if (tid == 0) {
-    lid_t* stamp = B;
-    auto in_tree = [&](int u) { return (s.wmark[u >> 5] >> (u & 31)) & 1u; };
-    auto pop = [&](int v) {  // node v takes its next draw
-      const uint32_t q = (uint32_t)s.wcnt[v] - (uint32_t)s.wbase[v];
-      if (!replay && q < (uint32_t)kTab && s.loff[v + 1] - s.loff[v] <= 256) {
-        const int slot = s.loff[v] + (int)s.wtab[v * kTab + q];
-        s.wcnt[v] = (lid_t)(s.wcnt[v] + 1);
-        s.wsl[v] = (lid_t)slot;
-        s.wnx[v] = s.ladj[slot];
+    auto nx_of = [](unsigned long long w) { return (int)(w & 0xffffu); };
+    auto stamp_of = [](unsigned long long w) { return (uint32_t)(w >> 16) & 0xffffu; };
+    auto pop = [&](int v, unsigned long long w) {  // node v takes its next draw; returns new word
+      const uint32_t cnt = (uint32_t)(w >> 32) & 0xffffu, base = (uint32_t)(w >> 48);
+      const uint32_t q = cnt - base;
+      int nn;
+      if (!replay && q < (uint32_t)kTab) {
+        nn = s.wtab[v * kTab + q];
       } else {
+        s.wcnt[v] = (lid_t)cnt;
         draw(v);
+        nn = s.wnx[v];
       }
+      return (unsigned long long)nn | ((unsigned long long)((cnt + 1) & 0xffffu) << 32) |
+             ((unsigned long long)base << 48);  // stamp cleared
     };
     // a connected pair needs ~10-20 draws per node; a walk that cannot reach the root
     // (disconnected input plan) is cut off instead of spinning for ever
     const long long budget = 2048ll * n + 65536;
     long long spent = 0;
     for (int node = 0; node < n && spent <= budget; ++node) {
-      if (in_tree(node)) continue;
-      const lid_t id = (lid_t)(node + 1);
+      if (stamp_of(wst[node]) == kInTree) continue;
+      const uint32_t id = (uint32_t)(node % 0xfffe) + 1u;  // 1..0xfffe, never kInTree
       int u = node;
-      while (!in_tree(u) && spent <= budget) {
-        if (stamp[u] == id) {  // the walk closed a loop at u: pop it
+      for (;;) {
+        unsigned long long w = wst[u];
+        const uint32_t sp_ = stamp_of(w);
+        if (sp_ == kInTree || spent > budget) break;
+        if (sp_ == id) {  // the walk closed a loop at u: pop it
           int v = u;
           do {
-            const int w = s.wnx[v];
-            pop(v);
-            stamp[v] = 0;
+            const unsigned long long wv = wst[v];
+            wst[v] = pop(v, wv);
             ++walk;
-            v = w;
+            v = nx_of(wv);
           } while (v != u);
+          w = wst[u];
         }
-        stamp[u] = id;
-        u = s.wnx[u];
+        wst[u] = (w & ~0xffff0000ull) | ((unsigned long long)id << 16);
+        u = nx_of(w);
         ++spent;
       }
       if (spent > budget) break;
-      for (u = node; !in_tree(u); u = s.wnx[u]) s.wmark[u >> 5] |= 1u << (u & 31);
+      for (u = node;;) {
+        const unsigned long long w = wst[u];
+        if (stamp_of(w) == kInTree) break;
+        wst[u] = w | 0xffff0000ull;
+        u = nx_of(w);
+      }
     }
     if (spent > budget && !s.misc[M_ERR]) s.misc[M_ERR] = RC_ERR_DISCONNECTED;
   }
   RC_PH(PH_W3);
   __syncthreads();
   if (s.misc[M_ERR]) return s.misc[M_ERR];
-  // the tree: edge (u, successor of u) for every node but the root
+  // the tree: edge (u, successor of u) for every node but the root; the slot of the
+  // successor in u's row gives the edge
   for (int u = tid; u < n; u += T) {
     walk += (u != root);  // the first draw of every node
     if (u == root) continue;
-    const int j = s.ladje[s.wsl[u]];
-    atomicOr(&s.tflag[j >> 5], 1u << (j & 31));
+    const unsigned long long w = wst[u];
+    const int nn = (int)(w & 0xffffu);
+    int j = -1;
+    for (int q = s.loff[u]; q < s.loff[u + 1]; ++q)
+      if (s.ladj[q] == nn) { j = s.ladje[q]; break; }
+    if (j >= 0) atomicOr(&s.tflag[j >> 5], 1u << (j & 31));  // else: tree_edge_list reports it
   }
   walk = warp_sum(walk);
   if ((tid & 31) == 0 && walk) atomicAdd(&ctr[RC_CTR_WALK], walk);
