@@ -21,6 +21,8 @@ RC_ERR_NO_CUT_EDGES = 7
 RC_ERR_REPLAY = 8
 RC_ERR_NO_ROOT = 9
 RC_ERR_INVALID_STREAK = 10
+RC_ERR_BALANCE = 11
+RC_SEED_REMAINING = 255
 
 STATUS_NAMES = {
     0: "RC_OK",
@@ -34,6 +36,7 @@ STATUS_NAMES = {
     8: "RC_ERR_REPLAY",
     9: "RC_ERR_NO_ROOT",
     10: "RC_ERR_INVALID_STREAK",
+    11: "RC_ERR_BALANCE",
 }
 
 RC_FLAG_WARNED = 1
@@ -160,6 +163,8 @@ EXPORTS = (
     "rc_engine_init_state",
     "rc_engine_run",
     "rc_engine_step_host",
+    "rc_engine_seed",
+    "rc_engine_seed_replay",
     "rc_engine_replay",
     "rc_engine_histograms",
     "rc_engine_info",
@@ -204,6 +209,8 @@ def load() -> C.CDLL:
     lib.rc_engine_step_host.argtypes = [
         C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p]
+    lib.rc_engine_seed.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.rc_engine_seed_replay.argtypes = [C.c_void_p, C.c_int32, C.POINTER(RcReplay), C.c_void_p]
     lib.rc_engine_replay.argtypes = [C.c_void_p, C.POINTER(RcReplay), C.c_void_p]
     lib.rc_engine_histograms.argtypes = [
         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]

@@ -275,6 +275,36 @@ int rc_engine_step_host(RcEngine* e, const uint8_t* h_assignment, int64_t h_stri
   return RC_OK;
 }
 
+static int seed_impl(RcEngine* e, int32_t max_attempts, const RcReplay* rp, void* stream) {
+  if (!e || !e->bound) return fail(RC_ERR_INVALID_ARG, "engine has no bound state");
+  if (e->p.cap_nodes < e->p.g.N || e->p.cap_edges < e->p.g.E)
+    return fail(RC_ERR_CAPACITY, "seed plans split the whole graph: create the engine with cap_nodes = %d, cap_edges = %d",
+                e->p.g.N, e->p.g.E);
+  if (e->p.cfg.n_districts > 254) return fail(RC_ERR_INVALID_ARG, "seed plans need n_districts <= 254");
+  if (e->p.g.R > 0) return fail(RC_ERR_INVALID_ARG, "seed plans are drawn without region surcharges");
+  if (rp && (rp->n_steps != e->p.cfg.n_districts - 1 || !rp->steps || !rp->weight_rank ||
+             rp->chain < 0 || rp->chain >= e->p.cfg.n_chains))
+    return fail(RC_ERR_INVALID_ARG, "seed replay needs n_districts - 1 recorded splits with weight ranks");
+  CUDA_OK(cudaSetDevice(e->device));
+  rc::Params p = e->p;
+  p.rp = rp ? *rp : RcReplay{};
+  p.seed_max_attempts = max_attempts;
+  const void* kern = e->spill ? (const void*)rc::seed_kernel<true> : (const void*)rc::seed_kernel<false>;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  void* args[] = {(void*)&p};
+  CUDA_OK(cudaLaunchKernel(kern, dim3(rp ? 1 : e->grid), dim3(e->threads), args, e->smem, (cudaStream_t)stream));
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return init_state_impl(e, stream, 2);
+}
+
+int rc_engine_seed(RcEngine* e, int32_t max_attempts, void* stream) { return seed_impl(e, max_attempts, nullptr, stream); }
+
+int rc_engine_seed_replay(RcEngine* e, int32_t max_attempts, const RcReplay* rp, void* stream) {
+  if (!rp) return fail(RC_ERR_INVALID_ARG, "null replay");
+  return seed_impl(e, max_attempts, rp, stream);
+}
+
 int rc_engine_replay(RcEngine* e, const RcReplay* rp, void* stream) {
   if (!e || !e->bound || !rp) return fail(RC_ERR_INVALID_ARG, "engine has no bound state / null replay");
   if (rp->n_steps <= 0 || !rp->steps) return fail(RC_ERR_INVALID_ARG, "empty replay");

@@ -44,7 +44,9 @@ struct Params {
   int32_t* progress;      // [n_chains] steps of this launch completed per chain
   int32_t* ring;          // [ring_cap] ready chains (chain id + 1; 0 = empty)
   int32_t ring_cap;
-  int32_t keep_counters;  // init_state_kernel: leave step/proposal numbers and counters alone
+  int32_t keep_counters;  // init_state_kernel: 1 = leave step/proposal numbers and counters
+                          // alone; 2 = after seeding: also keep a failed chain's status
+  int32_t seed_max_attempts;
   unsigned long long* timers;  // RC_TIMERS builds: cycles per phase (thread 0 of every CTA)
   unsigned char* spill;   // spill mode: [grid][spill_stride] working arrays in global memory
   int64_t spill_stride;

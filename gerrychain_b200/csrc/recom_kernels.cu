@@ -1200,6 +1200,167 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
 #endif
 }
 
+// =========================================================================================
+// Seed plans: recursive_tree_part (tree.py:971-1085) with method = bipartition_tree on
+// random_spanning_tree, node_repeats = 1.  One CTA builds one plan: k - 2 one-sided splits
+// of the shrinking remainder (label RC_SEED_REMAINING) with the debt-tightened target
+// (tree.py:1021-1050), then one two-sided split (tree.py:1054-1061).  The merged "pair" is
+// the whole remainder, so the engine must have been created with caps covering the graph
+// (the working arrays then usually live in the global scratch: spill mode).
+template <bool kSpill>
+__global__ void __launch_bounds__(512, 2) seed_kernel(const Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Chain c;
+  c.p = &p;
+  smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R, false,
+              kSpill ? p.spill + (size_t)blockIdx.x * p.spill_stride : nullptr);
+  const Smem& s = c.s;
+  const int tid = threadIdx.x, T = blockDim.x;
+  c.nodes = p.nodes + (size_t)blockIdx.x * p.cap_nodes;
+  c.eids = p.eids + (size_t)blockIdx.x * p.cap_edges;
+  c.par = 0;
+  int32_t* ctr = s.misc + M_CTR;
+  const bool replay = p.rp.n_steps > 0;
+  const int k = p.cfg.n_districts;
+  const double pt = p.cfg.pop_target, eps = p.cfg.epsilon;
+  const double lb_pop = __dmul_rn(pt, __dsub_rn(1.0, eps)), ub_pop = __dmul_rn(pt, __dadd_rn(1.0, eps));
+  const long long max_attempts = p.seed_max_attempts > 0 ? p.seed_max_attempts : 0x7fffffffffffffffLL;
+  for (int chain = replay ? p.rp.chain : (int)blockIdx.x; chain < p.cfg.n_chains; chain += gridDim.x) {
+    c.chain = chain;
+    c.gchain = (uint32_t)(chain + p.cfg.chain_offset);
+    c.assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
+    c.mask = p.st.d_cut_mask + (size_t)chain * p.st.mask_stride;
+    c.tally = p.st.d_tally + (size_t)chain * k;
+    if (tid < RC_N_COUNTERS) ctr[tid] = 0;
+    for (int i = tid; i < (int)p.st.assign_stride; i += T) c.assign[i] = RC_SEED_REMAINING;
+    for (int d = tid; d < k; d += T) c.tally[d] = 0;
+    __syncthreads();
+    int status = RC_OK;
+    double debt = 0.0;
+    for (int part = 0; part < k - 1 && status == RC_OK; ++part) {
+      const bool last = part == k - 2;
+      double ideal = pt, e1 = eps;
+      if (!last) {  // tree.py:1021-1023
+        const double min_pop = fmax(lb_pop, __dsub_rn(lb_pop, debt));
+        const double max_pop = fmin(ub_pop, __dsub_rn(ub_pop, debt));
+        ideal = __ddiv_rn(__dadd_rn(min_pop, max_pop), 2.0);
+        e1 = __ddiv_rn(__dsub_rn(max_pop, min_pop), __dmul_rn(2.0, ideal));
+      }
+      const double thr = __dmul_rn(ideal, e1);
+      const uint32_t prop_no = RC_SEED_PROPOSAL | (uint32_t)part;
+      const RcReplayStep* rs = replay ? p.rp.steps + part : nullptr;
+      const int n_rec = rs ? rs->n_trees : 0;
+      Step st;
+      st.a = st.b = RC_SEED_REMAINING;
+      int d_sub = 0;
+      status = gather_pair<false>(c, st, &d_sub);
+      if (tid == 0) { ctr[RC_CTR_NODES] += st.n; ctr[RC_CTR_SLOTS] += d_sub; }
+      if (status) break;
+      const int n = st.n, nt = n - 1;
+      if (n < 3) { status = RC_ERR_NO_ROOT; break; }
+      for (uint32_t tree_no = 0;; ++tree_no) {
+        if ((long long)tree_no >= max_attempts) { status = RC_ERR_MAX_ATTEMPTS; break; }
+        if (rs && (int)tree_no >= n_rec) { status = RC_ERR_REPLAY; break; }
+        const uint32_t* rrank = rs ? p.rp.weight_rank + (rs->first_tree + tree_no) * (long long)p.g.E : nullptr;
+        int rounds = 0;
+        status = boruvka_mst(c, st, tree_no, prop_no, rrank, &rounds);
+        if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_ROUNDS] += rounds; }
+        if (status) break;
+        const int r0 = 0;
+        euler_subtree_pops(c, st, r0);
+        // the reference's root (tree.py:377): uniform over tree nodes of degree > 1
+        auto internal = [&](int i) { return s.nxt[s.head[i]] != kNone; };
+        int root;
+        const bool last_rec = rs && (int)tree_no == n_rec - 1;
+        if (last_rec) {
+          const int gr = rs->root;
+          root = (gr >= 0 && gr < p.g.N && is_member(s, gr)) ? local_id(s, gr) : -1;
+          if (root < 0 || !internal(root)) { status = RC_ERR_REPLAY; break; }
+        } else {
+          if (tid == 0) s.misc[M_NINT] = 0;
+          __syncthreads();
+          int cnt = 0;
+          for (int i = tid; i < n; i += T) cnt += internal(i) ? 1 : 0;
+          cnt = warp_sum(cnt);
+          if ((tid & 31) == 0 && cnt) atomicAdd(&s.misc[M_NINT], cnt);
+          __syncthreads();
+          const int n_int = s.misc[M_NINT];
+          RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_ROOT, 0, tree_no, prop_no, 0);
+          root = select_kth(c, n, (int)rc_below(r.v[0], r.v[1], (uint32_t)n_int), internal);
+        }
+        // population below edge t as seen from the reference's root
+        const int ent_root = s.ent[root];
+        auto below_pop = [&](int t) {
+          const int pa = s.P[2 * t], pb = s.P[2 * t + 1];
+          const bool root_in_child = ent_root != 0xffff && ent_root >= min(pa, pb) && ent_root <= max(pa, pb);
+          return root_in_child ? st.tot - s.cur[t] : s.cur[t];
+        };
+        auto fits = [&](int pop) { return fabs(__dsub_rn((double)pop, ideal)) <= thr; };
+        auto is_cut = [&](int t) {  // tree.py:386-424
+          const int pb = below_pop(t);
+          return last ? (fits(pb) && fits(st.tot - pb)) : (fits(pb) || fits(st.tot - pb));
+        };
+        if (tid == 0) s.misc[M_NBAL] = 0;
+        __syncthreads();
+        {
+          int cnt = 0;
+          for (int t = tid; t < nt; t += T) cnt += is_cut(t) ? 1 : 0;
+          cnt = warp_sum(cnt);
+          if ((tid & 31) == 0 && cnt) atomicAdd(&s.misc[M_NBAL], cnt);
+        }
+        __syncthreads();
+        const int nbal = s.misc[M_NBAL];
+        if (nbal == 0) continue;
+        if (rs && !last_rec) { status = RC_ERR_REPLAY; break; }
+        int tstar;
+        if (rs && rs->cut_edge >= 0) {
+          const int want = rs->cut_edge;
+          tstar = select_kth(c, nt, 0, [&](int t) { return c.eids[s.te[t]] == want && is_cut(t); });
+          if (tstar < 0) { status = RC_ERR_REPLAY; break; }
+        } else {
+          RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_CUT, 0, tree_no, prop_no, 0);
+          tstar = select_kth(c, nt, (int)rc_below(r.v[0], r.v[1], (uint32_t)nbal), is_cut);
+        }
+        if (tid == 0) ctr[RC_CTR_ATTEMPTS] += (int)tree_no + 1;
+        // labels: `below` = the side of the cut that does not hold the reference's root
+        const int pa = s.P[2 * tstar], pb = s.P[2 * tstar + 1];
+        const int pd = min(pa, pb), pu = max(pa, pb);
+        auto child_side = [&](int i) { const int en = s.ent[i]; return en != 0xffff && en >= pd && en <= pu; };
+        const bool root_cs = child_side(root);
+        const int pop_below = below_pop(tstar);
+        long long part_pop;
+        if (!last) {
+          const bool take_below = fits(pop_below);  // tree.py:388 first, :399 otherwise
+          part_pop = take_below ? pop_below : st.tot - pop_below;
+          for (int i = tid; i < n; i += T) {
+            const bool below = child_side(i) != root_cs;
+            if (below == take_below) c.assign[c.nodes[i]] = (uint8_t)part;
+          }
+          if (tid == 0) c.tally[part] = part_pop;
+          if (!(lb_pop <= (double)part_pop && (double)part_pop <= ub_pop)) status = RC_ERR_BALANCE;
+          debt = __dadd_rn(debt, __dsub_rn((double)part_pop, pt));
+        } else {  // root side -> parts[-2], the rest -> parts[-1] (tree.py:1054-1075)
+          for (int i = tid; i < n; i += T)
+            c.assign[c.nodes[i]] = (uint8_t)((child_side(i) != root_cs) ? k - 1 : k - 2);
+          const long long p_hi = pop_below, p_lo = (long long)st.tot - pop_below;
+          if (tid == 0) { c.tally[k - 1] = p_hi; c.tally[k - 2] = p_lo; }
+          if (!(lb_pop <= (double)p_hi && (double)p_hi <= ub_pop && lb_pop <= (double)p_lo && (double)p_lo <= ub_pop))
+            status = RC_ERR_BALANCE;
+        }
+        break;
+      }
+      __syncthreads();  // the labels written above are read by the next gather
+    }
+    __syncthreads();
+    if (tid == 0) {
+      p.st.d_status[chain] = status;
+      for (int i = 0; i < RC_N_COUNTERS; ++i) p.st.d_counters[(size_t)chain * RC_N_COUNTERS + i] = ctr[i];
+    }
+    __syncthreads();
+    if (replay) break;
+  }
+}
+
 // ---- state kernels -----------------------------------------------------------------------
 // Tally._initialize_tally (updaters/tally.py:118-141) + first cut_edges scan
 // (updaters/cut_edges.py:110-114); one CTA per chain.
@@ -1243,8 +1404,11 @@ __global__ void init_state_kernel(const Params p) {
       for (int i = 0; i < RC_N_COUNTERS; ++i) p.st.d_counters[(size_t)chain * RC_N_COUNTERS + i] = 0;
     }
   }
-  if (__syncthreads_or(bad) && tid == 0) p.st.d_status[chain] = RC_ERR_INVALID_ARG;
-  else if (tid == 0) p.st.d_status[chain] = RC_OK;
+  const bool any_bad = __syncthreads_or(bad);
+  if (tid == 0) {
+    if (p.keep_counters == 2 && p.st.d_status[chain] != RC_OK) { /* seed plan failed: keep why */ }
+    else p.st.d_status[chain] = any_bad ? RC_ERR_INVALID_ARG : RC_OK;
+  }
 }
 
 // Ensemble histograms (one thread per chain).

@@ -153,6 +153,32 @@ class Engine:
             ptr(h_cut_count), ptr(h_status), self._stream()))
         return self
 
+    def seed(self, max_attempts: int = 10000):
+        """Random seed plans for every chain (``rc_engine_seed``: the reference's
+        ``recursive_tree_part``); the engine must cover the whole graph
+        (``cap_nodes = N, cap_edges = E``).  Asynchronous."""
+        _check(self.lib, self.lib.rc_engine_seed(self._handle, int(max_attempts or 0), self._stream()))
+        return self
+
+    def seed_replay(self, rec, chain: int = 0, max_attempts: int = 10000):
+        """TEST HOOK: recursive_tree_part with recorded reference randomness."""
+        t = self.torch
+        keep = []
+
+        def up(arr):
+            x = t.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(self.device)
+            keep.append(x)
+            return x.data_ptr()
+
+        rp = _abi.RcReplay()
+        rp.n_steps = len(rec.steps)
+        rp.chain = chain
+        rp.steps = up(rec.steps)
+        rp.weight_rank = up(rec.weight_rank)
+        _check(self.lib, self.lib.rc_engine_seed_replay(self._handle, int(max_attempts or 0), C.byref(rp), self._stream()))
+        t.cuda.synchronize(self.device)
+        return self
+
     def last_run_ms(self) -> float:
         ms = C.c_float()
         _check(self.lib, self.lib.rc_engine_last_run_ms(self._handle, C.byref(ms)))

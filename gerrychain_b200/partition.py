@@ -187,11 +187,19 @@ class Partition:
     @classmethod
     def from_random_assignment(cls, graph, n_parts, epsilon, pop_col, updaters=None,
                                use_default_updaters=True, flips=None, method=None):
-        """partition.py:67-120.  Seed-plan generation (recursive_tree_part) is the row
-        *before* the hot path and is not on the device yet."""
-        raise NotImplementedError(
-            "seed plans (recursive_tree_part) are outside the accelerated path; build the "
-            "initial assignment with GerryChain or gerrychain_b200.synthetic and pass it in")
+        """partition.py:67-120: a partition from a random seed plan drawn by
+        ``recursive_tree_part`` (tree.py:971-1085) - here by ``rc_engine_seed``."""
+        from .seed import recursive_tree_part
+
+        ctx = context_of(graph)
+        total_pop = int(ctx.column(pop_col).sum())
+        ideal_pop = total_pop / n_parts
+        if method is None:
+            assignment = recursive_tree_part(graph, range(n_parts), ideal_pop, pop_col, epsilon)
+        else:
+            assignment = method(graph=graph, parts=range(n_parts), pop_target=ideal_pop, pop_col=pop_col,
+                                epsilon=epsilon)
+        return cls(graph, assignment, updaters, use_default_updaters=use_default_updaters)
 
     # -- reference surface -------------------------------------------------------------
     def __repr__(self):

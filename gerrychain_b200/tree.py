@@ -58,3 +58,10 @@ def bipartition_tree(graph=None, pop_col=None, pop_target=None, epsilon=None, no
 ENGINE_KWARGS = dict(spanning_tree_fn=random_spanning_tree, max_attempts=100000, warn_attempts=1000,
                      allow_pair_reselection=False, cut_choice=_region_preferred_max_weight_choice,
                      balance_edge_fn=find_balanced_edge_cuts_memoization, one_sided_cut=False)
+
+
+def recursive_tree_part(graph, parts, pop_target, pop_col, epsilon, node_repeats=1, method=None):
+    """tree.py:971-1085 on the device (see gerrychain_b200.seed)."""
+    from .seed import recursive_tree_part as _impl
+
+    return _impl(graph, parts, pop_target, pop_col, epsilon, node_repeats=node_repeats, method=method)

@@ -43,8 +43,14 @@ enum {
   RC_ERR_NO_CUT_EDGES = 7,  /* tree_proposals.py:106 random.choice(()) -> IndexError  */
   RC_ERR_REPLAY = 8,        /* replay record inconsistent with the state              */
   RC_ERR_NO_ROOT = 9,       /* tree.py:377 choice([]) : no tree node of degree > 1    */
-  RC_ERR_INVALID_STREAK = 10 /* proposals kept failing the population Bounds           */
+  RC_ERR_INVALID_STREAK = 10, /* proposals kept failing the population Bounds          */
+  RC_ERR_BALANCE = 11       /* tree.py:1441-1446 BalanceError / PopulationBalanceError (seed plans) */
 };
+
+/* seed plans (tree.py:971-1085): label of nodes not yet assigned, and the proposal-number
+ * space of the seed splits in the random-draw schedule */
+#define RC_SEED_REMAINING 255
+#define RC_SEED_PROPOSAL 0x40000000u
 
 /* per-chain flag bits (RcState.d_flags), sticky */
 enum {
@@ -195,6 +201,20 @@ int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream);
 int rc_engine_step_host(RcEngine* e, const uint8_t* h_assignment, int64_t h_stride,
                         int64_t n_steps, uint8_t* h_assignment_out, int64_t* h_tally_out,
                         int32_t* h_cut_count_out, int32_t* h_status_out, void* stream);
+
+/* Random seed plans for every chain: recursive_tree_part (tree.py:971-1085) with
+ * method = partial(bipartition_tree, max_attempts=max_attempts) (the reference's default is
+ * 10000) - k - 2 one-sided splits with a debt-tightened target, then a two-sided one -
+ * followed by rc_engine_init_state.  Replaces Partition.from_random_assignment
+ * (partition/partition.py:67-120).  The engine must have been created with cap_nodes >=
+ * n_nodes and cap_edges >= n_edges (every split works on the whole remainder).  A chain
+ * whose plan could not be completed carries the status word (RC_ERR_MAX_ATTEMPTS,
+ * RC_ERR_BALANCE, ...). */
+int rc_engine_seed(RcEngine* e, int32_t max_attempts, void* stream);
+
+/* TEST HOOK: the same for chain rp->chain with recorded reference randomness, one
+ * RcReplayStep per split (pair_edge unused). */
+int rc_engine_seed_replay(RcEngine* e, int32_t max_attempts, const RcReplay* rp, void* stream);
 
 /* TEST HOOK: apply recorded reference steps to one chain (device pointers inside). */
 int rc_engine_replay(RcEngine* e, const RcReplay* d_replay_host_struct, void* stream);

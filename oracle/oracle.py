@@ -44,6 +44,9 @@ def load():
         _lib.rco_balanced_cuts_of_tree.argtypes = [
             C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_void_p]
         _lib.rco_mst_of_graph.argtypes = [C.POINTER(_abi.RcGraph), C.c_void_p, C.c_void_p]
+        _lib.rco_seed_plan.argtypes = [
+            C.POINTER(_abi.RcGraph), C.POINTER(_abi.RcConfig), C.c_void_p, C.c_uint32, C.c_int32,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.RcReplay)]
         _lib.rco_philox.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.rco_philox.restype = None
     return _lib
@@ -73,6 +76,33 @@ def mst_of_graph(csr, weights):
     if nt < 0:
         raise RuntimeError(_abi.STATUS_NAMES[-nt])
     return np.sort(out[:nt])
+
+
+def seed_plans(csr, cfg: EngineConfig, n_plans=1, max_attempts=10000, rec=None):
+    """recursive_tree_part on the CPU: (status [n], plans [n][N] uint8, tally [n][k]).
+    rec: tests/_golden.ReplayArrays of recorded reference randomness (one plan)."""
+    lib = load()
+    g = _abi.graph_struct(csr)
+    c = cfg.to_struct()
+    plans = np.zeros((n_plans, csr.n_nodes), dtype=np.uint8)
+    tally = np.zeros((n_plans, cfg.n_districts), dtype=np.int64)
+    status = np.zeros(n_plans, dtype=np.int32)
+    counters = np.zeros((n_plans, _abi.RC_N_COUNTERS), dtype=np.int64)
+    rp = None
+    if rec is not None:
+        rp = _abi.RcReplay()
+        rp.n_steps = len(rec.steps)
+        rp.steps = rec.steps.ctypes.data
+        rp.weights = rec.weights.ctypes.data
+    w = lib.rco_work_create(C.byref(g))
+    try:
+        for i in range(n_plans):
+            status[i] = lib.rco_seed_plan(C.byref(g), C.byref(c), w, cfg.chain_offset + i, max_attempts,
+                                          plans[i].ctypes.data, tally[i].ctypes.data,
+                                          counters[i].ctypes.data, C.byref(rp) if rp is not None else None)
+    finally:
+        lib.rco_work_destroy(w)
+    return status, plans, tally, counters
 
 
 class OracleChains:

@@ -629,6 +629,122 @@ int rco_replay(const RcGraph* g, const RcConfig* c, RcoWork* w, const RcReplay* 
   return RC_OK;
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* Seed plans: tree.py:971-1085 recursive_tree_part with method = bipartition_tree
+ * (random_spanning_tree, node_repeats = 1): k - 2 one-sided splits of the shrinking
+ * remainder with a debt-tightened target (tree.py:1021-1050), then one two-sided split
+ * (tree.py:1054-1061).  Nodes not yet assigned carry RC_SEED_REMAINING.  One-sided cuts
+ * (tree.py:386-409): the subtree below a node if ITS population fits, else everything but
+ * the subtree if THAT fits.  rp (optional): recorded reference randomness, one
+ * RcReplayStep per split (pair_edge unused). */
+int rco_seed_plan(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t chain,
+                  int32_t seed_max_attempts, uint8_t* assign, int64_t* tally,
+                  int64_t* counters, const RcReplay* rp) {
+  const int k = c->n_districts;
+  const double pt = c->pop_target, eps = c->epsilon;
+  const double lb_pop = pt * (1 - eps), ub_pop = pt * (1 + eps);
+  const int64_t max_attempts = seed_max_attempts > 0 ? seed_max_attempts : INT64_MAX;
+  for (int v = 0; v < g->n_nodes; ++v) assign[v] = RC_SEED_REMAINING;
+  for (int d = 0; d < k; ++d) tally[d] = 0;
+  double debt = 0;
+  for (int part = 0; part < k - 2; ++part) {
+    double min_pop = fmax(pt * (1 - eps), pt * (1 - eps) - debt);
+    double max_pop = fmin(pt * (1 + eps), pt * (1 + eps) - debt);
+    double ideal = (min_pop + max_pop) / 2;
+    double e1 = (max_pop - min_pop) / (2 * ideal);
+    const uint32_t prop_no = RC_SEED_PROPOSAL | (uint32_t)part;
+    const RcReplayStep* rs = rp ? &rp->steps[part] : NULL;
+    rco_gather(g, w, assign, RC_SEED_REMAINING, RC_SEED_REMAINING);
+    int done = 0;
+    for (uint32_t t = 0; !done; ++t) {
+      if ((int64_t)t >= max_attempts) { rco_ungather(w); return RC_ERR_MAX_ATTEMPTS; }
+      if (rs && (int)t >= rs->n_trees) { rco_ungather(w); return RC_ERR_REPLAY; }
+      if (rp) {
+        const double* rw = rp->weights + (rs->first_tree + t) * (int64_t)g->n_edges;
+        for (int j = 0; j < w->m; ++j) w->w[j] = rw[w->eid[j]];
+      } else {
+        rco_random_weights(g, c, w, chain, t, prop_no);
+      }
+      int rc = rco_kruskal(w);
+      if (rc) { rco_ungather(w); return rc; }
+      counters[RC_CTR_TREES]++;
+      build_tree_adj(w);
+      int root = -1;
+      if (rs && (int)t == rs->n_trees - 1) {
+        root = w->g2l[rs->root];
+        if (root < 0 || w->toff[root + 1] - w->toff[root] < 2) { rco_ungather(w); return RC_ERR_REPLAY; }
+      } else {
+        int n_int = 0;
+        for (int i = 0; i < w->n; ++i) n_int += (w->toff[i + 1] - w->toff[i]) > 1;
+        if (!n_int) { rco_ungather(w); return RC_ERR_NO_ROOT; }
+        RcPhilox p = rc_draw(c->seed, chain, RC_DRAW_ROOT, 0, t, prop_no, 0);
+        int kth = (int)rc_below(p.v[0], p.v[1], (uint32_t)n_int);
+        for (int i = 0; i < w->n; ++i)
+          if ((w->toff[i + 1] - w->toff[i]) > 1 && kth-- == 0) { root = i; break; }
+      }
+      rco_bfs(w, root);
+      rco_subtree_pops(g, w);
+      /* one-sided cuts, canonical order: ascending edge id; bal_child < 0 encodes "ABOVE" */
+      int nb = 0;
+      for (int v = 0; v < w->n; ++v) {
+        if (v == root) continue;
+        int64_t p = w->subpop[v];
+        if (fabs((double)p - ideal) <= ideal * e1) w->bal_t[nb++] = w->parent_t[v];
+        else if (fabs((double)(w->totpop - p) - ideal) <= ideal * e1) w->bal_t[nb++] = w->parent_t[v];
+      }
+      if (!nb) continue;
+      if (rs && (int)t != rs->n_trees - 1) { rco_ungather(w); return RC_ERR_REPLAY; }
+      t_sort_ctx = w;
+      qsort(w->bal_t, (size_t)nb, sizeof(int32_t), cmp_bal);
+      int pick = -1;
+      if (rs && rs->cut_edge >= 0) {
+        for (int q = 0; q < nb; ++q) if (w->tw_eid[w->bal_t[q]] == rs->cut_edge) pick = q;
+        if (pick < 0) { rco_ungather(w); return RC_ERR_REPLAY; }
+      } else {
+        RcPhilox p = rc_draw(c->seed, chain, RC_DRAW_CUT, 0, t, prop_no, 0);
+        pick = (int)rc_below(p.v[0], p.v[1], (uint32_t)nb);
+      }
+      int te = w->bal_t[pick];
+      int child = (w->parent[w->tu[te]] == w->tv[te] && w->parent_t[w->tu[te]] == te) ? w->tu[te] : w->tv[te];
+      int64_t below = w->subpop[child];
+      int take_below = fabs((double)below - ideal) <= ideal * e1;
+      mark_subtree(w, child);
+      int64_t part_pop = take_below ? below : w->totpop - below;
+      for (int i = 0; i < w->n; ++i)
+        if ((w->side[i] != 0) == (take_below != 0)) assign[w->nodes[i]] = (uint8_t)part;
+      tally[part] = part_pop;
+      counters[RC_CTR_ATTEMPTS] += (int64_t)t + 1;
+      if (!(lb_pop <= (double)part_pop && (double)part_pop <= ub_pop)) { rco_ungather(w); return RC_ERR_BALANCE; }
+      debt += (double)part_pop - pt;
+      done = 1;
+    }
+    rco_ungather(w);
+  }
+  /* the last two districts: a two-sided split of what remains (tree.py:1054-1061) */
+  {
+    RcConfig c2 = *c;
+    c2.max_attempts = seed_max_attempts;
+    c2.allow_pair_reselection = 0;
+    c2.node_repeats = 1;
+    c2.tree_kind = RC_TREE_MST;
+    c2.cut_policy = RC_CUT_UNIFORM;
+    const uint32_t prop_no = RC_SEED_PROPOSAL | (uint32_t)(k - 2);
+    const RcReplayStep* rs = rp ? &rp->steps[k - 2] : NULL;
+    rco_gather(g, w, assign, RC_SEED_REMAINING, RC_SEED_REMAINING);
+    int64_t child_pop = 0;
+    uint32_t flags = 0;
+    int rc = rco_bipartition(g, &c2, w, chain, prop_no, rp, rs, counters, &flags, &child_pop, NULL);
+    if (rc) { rco_ungather(w); return rc == -1 ? RC_ERR_MAX_ATTEMPTS : rc; }
+    for (int i = 0; i < w->n; ++i) assign[w->nodes[i]] = (uint8_t)(w->side[i] ? k - 1 : k - 2);
+    tally[k - 1] = child_pop;
+    tally[k - 2] = w->totpop - child_pop;
+    rco_ungather(w);
+    for (int d = k - 2; d < k; ++d)
+      if (!(lb_pop <= (double)tally[d] && (double)tally[d] <= ub_pop)) return RC_ERR_BALANCE;
+  }
+  return RC_OK;
+}
+
 /* Known-answer entry (reference tests/test_tree.py:354-385): balanced cut edges of a GIVEN
  * tree.  tree_uv [n-1][2] node indices, pops [n]; returns count, fills out_uv [..][2]
  * with (child, parent) pairs in ascending (min,max) order. */

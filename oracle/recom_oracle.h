@@ -26,6 +26,9 @@ int rco_step(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t global_ch
 int rco_replay(const RcGraph* g, const RcConfig* c, RcoWork* w, const RcReplay* rp,
                uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
                int64_t* counters, uint32_t* flags);
+int rco_seed_plan(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t chain,
+                  int32_t seed_max_attempts, uint8_t* assign, int64_t* tally,
+                  int64_t* counters, const RcReplay* rp);
 int rco_balanced_cuts_of_tree(int32_t n, const int32_t* tree_uv, const int32_t* pops,
                               double ideal, double eps, int32_t root, int32_t* out_uv);
 int rco_mst_of_graph(const RcGraph* g, const double* weights, int32_t* out_eids);

@@ -109,3 +109,35 @@ def load(name, inject_cut=True) -> Golden:
         rec.stack_val = z["ws_val"].astype(np.int32)
     return Golden(name, meta, csr, cfg, z["init_assignment"], rec, z["assignment"],
                   z["n_cut_edges"], z["population"], z["balanced_ptr"], z["balanced"], tree_ptr)
+
+
+def seedplan_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "seedplan_*.npz")))
+
+
+def load_seedplan(name):
+    """Recorded reference recursive_tree_part (oracle/record_seed_plans.py):
+    (csr, cfg, ReplayArrays, reference plan, cuts per split)."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    csr = csr_from_edges(int(z["pop"].shape[0]), z["edge_uv"], z["pop"])
+    cfg = EngineConfig(n_districts=meta["k"], n_chains=1, pop_target=meta["pop_target"],
+                       epsilon=meta["epsilon"], seed=0)
+    tree_ptr = z["tree_ptr"]
+    S = len(tree_ptr) - 1
+    steps = np.zeros(S, dtype=STEP_DTYPE)
+    steps["pair_edge"] = -1
+    steps["n_trees"] = np.diff(tree_ptr)
+    steps["first_tree"] = tree_ptr[:-1]
+    steps["root"] = z["root"]
+    steps["cut_edge"] = z["cut_edge"]
+    T = int(tree_ptr[-1])
+    w = np.full((T, csr.n_edges), np.nan, dtype=np.float64)
+    wp = z["w_ptr"]
+    t_of = np.repeat(np.arange(T), np.diff(wp))
+    w[t_of, z["w_eid"]] = z["w_val"]
+    order = np.argsort(w, axis=1, kind="stable")
+    rank = np.empty_like(order)
+    np.put_along_axis(rank, order, np.broadcast_to(np.arange(csr.n_edges), order.shape), axis=1)
+    rec = ReplayArrays(steps=steps, weights=w, weight_rank=rank.astype(np.uint32))
+    return csr, cfg, rec, z["plan"], z["n_cuts"]

@@ -190,3 +190,27 @@ def test_batched_markov_chain_matches_oracle_and_api():
     assert np.array_equal(runner2.run_to_end().assignment.cpu().numpy(), ora.assignments())
     with pytest.raises(TypeError):
         BatchedMarkovChain(p, cons, lambda s: True, grid, 10, 4)
+
+
+def test_from_random_assignment_and_recursive_tree_part():
+    random.seed(11)
+    g = networkx.grid_2d_graph(12, 12)
+    for n in g.nodes:
+        g.nodes[n]["population"] = 1
+    part = Partition.from_random_assignment(g, 6, 0.1, "population", updaters={"population": Tally("population")})
+    assert len(part) == 6 and _contiguous(part)
+    assert all(abs(p - 24) <= 2.4 for p in part["population"].values())
+    plan = gc.tree.recursive_tree_part(g, ["a", "b", "c"], 48, "population", 0.1)
+    assert set(plan.values()) == {"a", "b", "c"} and set(plan) == set(g.nodes)
+    from gerrychain_b200.seed import random_plans
+
+    plans = random_plans(g, 4, 0.1, "population", n_plans=32, seed=3)
+    assert plans.shape == (32, 144) and len({p.tobytes() for p in plans}) > 16
+    # seed plans feed the batched runner
+    ideal = 36
+    p = functools.partial(recom, pop_col="population", pop_target=ideal, epsilon=0.1)
+    init = Partition(g, {n: int(plans[0][i]) for i, n in enumerate(g.nodes)}, {"population": Tally("population")})
+    runner = gc.BatchedMarkovChain(p, [within_percent_of_ideal_population(init, 0.1)], always_accept, init,
+                                   total_steps=11, n_chains=32, seed=1, initial_assignments=plans)
+    last = runner.run_to_end()
+    assert (np.abs(last.population() - ideal) <= 3.6).all()

@@ -268,6 +268,66 @@ def test_edge_cases_status_words():
     _free_run_vs_oracle(csr, tiny.reshape(-1), cfg5, 40)
 
 
+@pytest.mark.parametrize("name", _golden.seedplan_names())
+def test_seed_plan_replay_bit_exact_with_reference(name):
+    """recursive_tree_part (tree.py:971-1085): the reference's recorded weights, roots and cut
+    choices replayed on the device give the reference's seed plan."""
+    from gerrychain_b200.engine import Engine
+
+    csr, cfg, rec, plan, _ = _golden.load_seedplan(name)
+    cfg.cap_nodes, cfg.cap_edges = csr.n_nodes, csr.n_edges
+    eng = Engine(csr, cfg, np.zeros(csr.n_nodes, dtype=np.uint8))
+    eng.seed_replay(rec)
+    assert int(eng.status.cpu().numpy()[0]) == 0, _abi.STATUS_NAMES.get(int(eng.status.cpu().numpy()[0]))
+    assert np.array_equal(eng.assignments()[0], plan)
+    _naive_check(csr, cfg.n_districts, eng.assignments(), eng.tally.cpu().numpy(),
+                 eng.cut_mask.cpu().numpy(), eng.cut_count.cpu().numpy())
+
+
+def test_seed_plans_free_running_bit_exact_with_oracle():
+    from oracle import oracle
+    from gerrychain_b200.engine import Engine
+
+    for name, n_plans in (("seedplan_grid20_k8", 24), ("seedplan_delaunay600_k5", 16)):
+        csr, cfg, _, _, _ = _golden.load_seedplan(name)
+        cfg.n_chains, cfg.seed = n_plans, 5150
+        cfg.cap_nodes, cfg.cap_edges = csr.n_nodes, csr.n_edges
+        eng = Engine(csr, cfg, np.zeros(csr.n_nodes, dtype=np.uint8))
+        eng.seed(10000).synchronize()
+        status, plans, tally, counters = oracle.seed_plans(csr, cfg, n_plans=n_plans)
+        assert np.array_equal(eng.status.cpu().numpy(), status) and (status == 0).all()
+        assert np.array_equal(eng.assignments(), plans)
+        assert np.array_equal(eng.tally.cpu().numpy(), tally)
+        assert np.array_equal(eng.counters.cpu().numpy()[:, _abi.RC_CTR_TREES], counters[:, _abi.RC_CTR_TREES])
+        _naive_check(csr, cfg.n_districts, eng.assignments(), eng.tally.cpu().numpy(),
+                     eng.cut_mask.cpu().numpy(), eng.cut_count.cpu().numpy())
+        # a seeded engine is ready to run chains from its own plans
+        cfg2 = cfg
+        eng.run(5).synchronize()
+        assert (eng.status.cpu().numpy() == 0).all()
+
+
+def test_seed_plans_config3_scale_spill_mode():
+    """9k-node Delaunay graph, 18 districts: every split works on the whole remainder, so
+    the seed kernel runs in spill mode; plans must be balanced and contiguous."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from gerrychain_b200.engine import Engine
+
+    csr, _, cfg = workloads.config3(n_chains=8, seed=8)
+    cfg.cap_nodes, cfg.cap_edges = csr.n_nodes, csr.n_edges
+    eng = Engine(csr, cfg, np.zeros(csr.n_nodes, dtype=np.uint8))
+    eng.seed(10000).synchronize()
+    assert (eng.status.cpu().numpy() == 0).all()
+    tally = eng.tally.cpu().numpy()
+    assert (tally >= cfg.pop_lower).all() and (tally <= cfg.pop_upper).all()
+    uv = csr.edge_uv
+    for pl in eng.assignments():
+        same = pl[uv[:, 0]] == pl[uv[:, 1]]
+        m = coo_matrix((np.ones(same.sum()), (uv[same, 0], uv[same, 1])), shape=(csr.n_nodes,) * 2)
+        assert connected_components(m, directed=False)[0] == cfg.n_districts
+
+
 def test_histograms():
     csr, plan, cfg = workloads.config1(n_chains=128, seed=2)
     eng = _engine(csr, cfg, plan)

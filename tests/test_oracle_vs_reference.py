@@ -85,3 +85,33 @@ def test_region_cut_policy_matches_reference(oracle_lib, name):
     rc, trace, info = ch.replay(g.rec)
     assert rc == 0
     assert np.array_equal(trace, g.assignment)
+
+
+@pytest.mark.parametrize("name", _golden.seedplan_names())
+def test_oracle_seed_plan_replays_reference_recursive_tree_part(name):
+    """tree.py:971-1085: fed the reference's recorded weights / roots / cut choices, the
+    oracle's recursive_tree_part returns the reference's plan, split by split."""
+    csr, cfg, rec, plan, _ = _golden.load_seedplan(name)
+    status, plans, tally, _ = oracle.seed_plans(csr, cfg, rec=rec)
+    assert status[0] == 0, _abi.STATUS_NAMES.get(int(status[0]))
+    assert np.array_equal(plans[0], plan)
+    assert np.array_equal(tally[0], np.bincount(plan, weights=csr.pop, minlength=cfg.n_districts).astype(np.int64))
+
+
+def test_oracle_seed_plans_free_running_are_valid():
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+
+    csr, cfg, _, _, _ = _golden.load_seedplan("seedplan_grid20_k8")
+    cfg.seed = 77
+    status, plans, tally, _ = oracle.seed_plans(csr, cfg, n_plans=20)
+    assert (status == 0).all()
+    lo, hi = cfg.pop_target * (1 - cfg.epsilon), cfg.pop_target * (1 + cfg.epsilon)
+    assert (tally >= lo).all() and (tally <= hi).all()
+    uv = csr.edge_uv
+    for pl in plans:
+        assert set(pl.tolist()) == set(range(cfg.n_districts))
+        same = pl[uv[:, 0]] == pl[uv[:, 1]]
+        m = coo_matrix((np.ones(same.sum()), (uv[same, 0], uv[same, 1])), shape=(csr.n_nodes,) * 2)
+        assert connected_components(m, directed=False)[0] == cfg.n_districts
+    assert len({pl.tobytes() for pl in plans}) == 20
