@@ -15,6 +15,7 @@ from . import accept, constraints, proposals, tree, updaters  # noqa: F401
 from .accept import always_accept
 from .chain import BatchedMarkovChain, ChainBatch, MarkovChain
 from .constraints import Bounds, Validator, within_percent_of_ideal_population
+from .graph import Graph
 from .grid import Grid
 from .partition import Assignment, GeographicPartition, Partition
 from .proposals import MetagraphError, ReCom, recom
@@ -23,7 +24,7 @@ from .updaters import Tally, cut_edges
 
 __all__ = [
     "MarkovChain", "BatchedMarkovChain", "ChainBatch", "Partition", "GeographicPartition", "Assignment",
-    "Grid", "recom", "ReCom", "MetagraphError", "BipartitionWarning", "bipartition_tree",
+    "Grid", "Graph", "recom", "ReCom", "MetagraphError", "BipartitionWarning", "bipartition_tree",
     "within_percent_of_ideal_population", "Validator", "Bounds", "Tally", "cut_edges",
     "always_accept", "accept", "constraints", "proposals", "tree", "updaters",
 ]

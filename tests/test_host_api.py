@@ -177,3 +177,32 @@ def test_histogram_all_reduce_over_gloo_world_size_2(tmp_path):
         capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "rank0_ok" in out.stdout and "rank1_ok" in out.stdout
+
+
+def test_graph_json_round_trip_feeds_the_csr_builder(tmp_path):
+    """Graph.from_json / to_json (reference graph/graph.py:76-119): networkx adjacency JSON
+    -> Graph -> canonical CSR, node order and attributes preserved."""
+    import networkx
+    import numpy as np
+
+    from gerrychain_b200.csr import csr_from_networkx
+
+    g = networkx.grid_2d_graph(3, 4)
+    g = networkx.relabel_nodes(g, {n: f"v{n[0]}{n[1]}" for n in g.nodes})
+    for i, n in enumerate(g.nodes):
+        g.nodes[n].update(TOTPOP=10 + i, county="A" if i < 6 else None)
+    path = tmp_path / "dual.json"
+    gc.Graph.from_networkx(g).to_json(str(path))
+    loaded = gc.Graph.from_json(str(path))
+    assert repr(loaded) == "<Graph [12 nodes, 17 edges]>"
+    assert list(loaded.nodes) == list(g.nodes) and loaded.lookup("v00", "TOTPOP") == 10
+    a = csr_from_networkx(g, "TOTPOP", {"county": 0.5})
+    b = csr_from_networkx(loaded, "TOTPOP", {"county": 0.5})
+    for f in ("row_ptr", "col_idx", "slot_edge", "edge_uv", "pop", "region_ids"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert (b.region_ids[0] == -1).sum() == 6  # None -> -1: always surcharged (tree.py:84-85)
+    island = networkx.Graph()
+    island.add_nodes_from([0, 1, 2])
+    island.add_edge(0, 1)
+    with pytest.warns(UserWarning, match="islands"):
+        gc.Graph.from_networkx(island).issue_warnings()
