@@ -1,16 +1,20 @@
-"""``Grid``: a partition of an m x n lattice with unit populations.
+"""``Grid``: a partition of an m x n lattice with unit populations - the synthetic input of
+BASELINE.json configs[0] and [1].
 
-Reference: /root/reference/gerrychain/grid.py:32-288 - same nodes ``(i, j)``, attributes
-(``population = 1``, ``area = 1``, ``shared_perim``), default quadrant plan
-(``color_quadrants``) and ``as_list_of_lists``.  It is the synthetic input of BASELINE.json
-configs[0] and [1].  The geometric default updaters of the reference's Grid (perimeter,
-boundaries, polsby_popper) are downstream statistics outside the accelerated path.
+API of the reference's ``Grid`` (/root/reference/gerrychain/grid.py:32-288): nodes are
+``(i, j)`` tuples with ``population = 1`` / ``area = 1``, edges carry ``shared_perim``, the
+default plan is the four quadrants, ``as_list_of_lists()`` / ``str()`` render the plan.  The
+lattice itself comes from ``gerrychain_b200.synthetic.grid_graph``; rendering reads the dense
+district vector the engine works on instead of walking a dict.  The reference's geometric
+default updaters (perimeter, boundaries, polsby_popper) are downstream statistics outside the
+accelerated path; ``population``, ``area``, ``cut_edges`` and ``cut_edges_by_part`` are kept.
 """
 
 from __future__ import annotations
 
-import math
 from typing import Callable, Dict, Optional, Tuple
+
+import numpy as np
 
 from . import synthetic
 from .partition import Partition
@@ -18,18 +22,18 @@ from .updaters import Tally, cut_edges, cut_edges_by_part
 
 
 def create_grid_graph(dimensions: Tuple[int, int], with_diagonals: bool = False):
-    """grid.py:142-181."""
-    if len(dimensions) != 2:
-        raise ValueError("Expected two dimensions.")
-    return synthetic.grid_graph(dimensions[0], dimensions[1], with_diagonals)
+    """m x n lattice graph with the node / edge attributes of grid.py:142-181."""
+    try:
+        m, n = dimensions
+    except (TypeError, ValueError):
+        raise ValueError("Expected two dimensions.") from None
+    return synthetic.grid_graph(int(m), int(n), with_diagonals)
 
 
 def color_quadrants(node: Tuple[int, int], thresholds: Tuple[int, int]) -> int:
-    """grid.py:267-288."""
-    x, y = node
-    x_color = 0 if x < thresholds[0] else 1
-    y_color = 0 if y < thresholds[1] else 2
-    return x_color + y_color
+    """Quadrant index of a lattice node: bit 0 = right of the column threshold... in the
+    reference's convention 0/1 by the first coordinate, +2 by the second (grid.py:267-288)."""
+    return int(node[0] >= thresholds[0]) + 2 * int(node[1] >= thresholds[1])
 
 
 class Grid(Partition):
@@ -43,31 +47,31 @@ class Grid(Partition):
     def __init__(self, dimensions: Optional[Tuple[int, int]] = None, with_diagonals: bool = False,
                  assignment: Optional[Dict] = None, updaters: Optional[Dict[str, Callable]] = None,
                  parent: Optional["Grid"] = None, flips: Optional[Dict] = None) -> None:
-        if dimensions:
-            self.dimensions = dimensions
-            graph = create_grid_graph(dimensions, with_diagonals)
-            if not assignment:
-                thresholds = tuple(math.floor(n / 2) for n in self.dimensions)
-                assignment = {node: color_quadrants(node, thresholds) for node in graph.nodes}
-            if not updaters:
-                updaters = dict()
-            updaters.update(self.default_updaters)
-            super().__init__(graph, assignment, updaters)
-        elif parent:
-            super().__init__(parent=parent, flips=flips)
-        else:
+        if parent is not None and not dimensions:
+            Partition.__init__(self, parent=parent, flips=flips)  # dimensions travel with _inherit
+            return
+        if not dimensions:
             raise Exception("Not a good way to create a Partition")
-
-    def __str__(self):
-        rows = self.as_list_of_lists()
-        return "\n".join(["".join([str(x) for x in row]) for row in rows]) + "\n"
-
-    def __repr__(self):
-        dims = "x".join(str(d) for d in self.dimensions)
-        number_of_parts = len(self.parts)
-        s = "s" if number_of_parts > 1 else ""
-        return "{} Grid\nPartitioned into {} part{}".format(dims, number_of_parts, s)
+        self.dimensions = tuple(dimensions)
+        lattice = create_grid_graph(self.dimensions, with_diagonals)
+        if not assignment:
+            half = (self.dimensions[0] // 2, self.dimensions[1] // 2)
+            assignment = {cell: color_quadrants(cell, half) for cell in lattice.nodes}
+        merged = dict(updaters or {})
+        merged.update(self.default_updaters)  # the defaults win, as in the reference
+        Partition.__init__(self, lattice, assignment, merged)
 
     def as_list_of_lists(self):
+        """Row j of the result lists the districts of cells (0, j) .. (m-1, j)."""
         m, n = self.dimensions
-        return [[self.assignment.mapping[(i, j)] for i in range(m)] for j in range(n)]
+        labels = np.array(self._district_labels, dtype=object)
+        cells = labels[self._vec.reshape(m, n)]  # node (i, j) has index i * n + j
+        return [list(cells[:, j]) for j in range(n)]
+
+    def __str__(self):
+        return "".join("".join(str(d) for d in row) + "\n" for row in self.as_list_of_lists())
+
+    def __repr__(self):
+        k = len(self)
+        return "{}x{} Grid\nPartitioned into {} part{}".format(self.dimensions[0], self.dimensions[1], k,
+                                                              "" if k == 1 else "s")
