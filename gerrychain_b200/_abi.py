@@ -44,6 +44,9 @@ RC_FLAG_WARNED = 1
 RC_TREE_MST = 0
 RC_TREE_WILSON = 1
 
+RC_ACCEPT_ALWAYS = 0
+RC_ACCEPT_CUT_EDGE = 1
+
 RC_CUT_UNIFORM = 0
 RC_CUT_REGION_PREF = 1
 RC_CUT_MAX_WEIGHT = 2
@@ -94,6 +97,7 @@ class RcConfig(C.Structure):
         ("cap_edges", C.c_int32),
         ("threads_per_cta", C.c_int32),
         ("max_invalid_streak", C.c_int32),
+        ("accept_rule", C.c_int32),
     ]
 
 

@@ -175,8 +175,15 @@ class BatchedMarkovChain:
     def __init__(self, proposal, constraints, accept, initial_state: Partition, total_steps: int,
                  n_chains: int, seed: Optional[int] = None, chain_offset: int = 0, device=None,
                  yield_every: int = 1, initial_assignments=None, **engine_options):
-        if accept is not always_accept:
-            raise TypeError("BatchedMarkovChain implements accept=always_accept on the device")
+        from .accept import cut_edge_accept
+
+        if accept is always_accept:
+            accept_rule = _abi.RC_ACCEPT_ALWAYS
+        elif accept is cut_edge_accept:
+            accept_rule = _abi.RC_ACCEPT_CUT_EDGE
+        else:
+            raise TypeError("BatchedMarkovChain implements accept=always_accept and accept=cut_edge_accept "
+                            "on the device; other acceptance functions need the host loop (MarkovChain)")
         (self.pop_col, pop_target, epsilon, node_repeats, self.region_surcharge,
          method) = _recom_arguments(proposal)
         cons, lower, upper = _device_bounds(constraints, self.pop_col)
@@ -197,6 +204,7 @@ class BatchedMarkovChain:
             self._ekw.update(pop_lower=float(lower), pop_upper=float(upper))
         self._ekw["seed"] = random.getrandbits(64) if seed is None else int(seed)
         self._ekw["chain_offset"] = int(chain_offset)
+        self._ekw["accept_rule"] = accept_rule
         self._device = device
         self._plans = initial_assignments
         self.engine = None

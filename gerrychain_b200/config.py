@@ -33,6 +33,7 @@ class EngineConfig:
     cap_edges: int = 0
     threads_per_cta: int = 0
     max_invalid_streak: int = 0
+    accept_rule: int = _abi.RC_ACCEPT_ALWAYS
 
     def to_struct(self) -> _abi.RcConfig:
         c = _abi.RcConfig()
@@ -54,6 +55,7 @@ class EngineConfig:
         c.cap_edges = int(self.cap_edges)
         c.threads_per_cta = int(self.threads_per_cta)
         c.max_invalid_streak = int(self.max_invalid_streak)
+        c.accept_rule = int(self.accept_rule)
         return c
 
 

@@ -1027,6 +1027,35 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
   }
   // side(i): node i is cut away from the root's side and takes the higher id b
   auto side = [&](int i) { return below(i) != root_below; };
+  if (p.cfg.accept_rule == RC_ACCEPT_CUT_EDGE) {
+    // accept.py:19-35: the number of cut edges the proposal WOULD have, before anything is
+    // written; a rejected proposal leaves the state alone but still counts as a step
+    if (tid == 0) s.misc[M_DELTA] = 0;
+    for (int i0 = 0; i0 < st.n; i0 += T) {
+      const int i = i0 + tid;
+      const uint32_t bal = __ballot_sync(0xffffffffu, i < st.n && side(i));
+      if (i < st.n && (tid & 31) == 0) s.newb[i >> 5] = bal;
+    }
+    __syncthreads();
+    int d = 0;
+    for (int j = tid; j < st.m; j += T) {
+      const int u = s.eu[j], v = s.ev[j];
+      const int was = ((s.oldb[u >> 5] >> (u & 31)) ^ (s.oldb[v >> 5] >> (v & 31))) & 1u;
+      const int now = ((s.newb[u >> 5] >> (u & 31)) ^ (s.newb[v >> 5] >> (v & 31))) & 1u;
+      d += now - was;
+    }
+    d = warp_sum(d);
+    if ((tid & 31) == 0 && d) atomicAdd(&s.misc[M_DELTA], d);
+    __syncthreads();
+    const int new_count = cut_count + s.misc[M_DELTA];
+    __syncthreads();
+    const double ratio = __ddiv_rn((double)cut_count, (double)new_count);
+    const RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_ACCEPT, 0, 0, prop_no, 0);
+    if (!(rc_unit_double(r.v[0], r.v[1]) < (ratio < 1.0 ? ratio : 1.0))) {
+      res.accepted = 1;  // step consumed, old state kept
+      return res;
+    }
+  }
   if (tid == 0) s.misc[M_DELTA] = 0;
   for (int i0 = 0; i0 < st.n; i0 += T) {  // partition/assignment.py:76-86
     const int i = i0 + tid;

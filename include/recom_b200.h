@@ -60,6 +60,11 @@ enum {
 enum { RC_TREE_MST = 0,   /* tree.py:60-94  random_spanning_tree (+ networkx Kruskal) */
        RC_TREE_WILSON = 1 /* tree.py:97-132 uniform_spanning_tree                     */ };
 
+enum { RC_ACCEPT_ALWAYS = 0,   /* accept.py:15 always_accept                            */
+       RC_ACCEPT_CUT_EDGE = 1  /* accept.py:19-35 cut_edge_accept: a valid proposal is taken
+                                  with probability min(1, #cut edges before / after); a
+                                  rejected one still counts as a step (chain.py:191-195)  */ };
+
 enum { RC_CUT_UNIFORM = 0,      /* tree.py:540-545 random.choice(cuts)                 */
        RC_CUT_REGION_PREF = 1,  /* tree.py:548-578 power-set preference, then max weight */
        RC_CUT_MAX_WEIGHT = 2    /* tree.py:446-480 _max_weight_choice                  */ };
@@ -98,6 +103,7 @@ typedef struct RcConfig {
   int32_t cap_edges;          /* max undirected edges of a merged pair (0: picks)      */
   int32_t threads_per_cta;    /* 0: engine picks                                       */
   int32_t max_invalid_streak; /* consecutive invalid proposals before RC_ERR_INVALID_STREAK (0: 1000) */
+  int32_t accept_rule;        /* RC_ACCEPT_*: MarkovChain(accept=)  chain.py:192        */
 } RcConfig;
 
 /* ---- chain state, resident in HBM, owned by the caller --------------------------- */

@@ -31,6 +31,7 @@ enum {
   RC_DRAW_ROOT = 3,   /* BFS root among tree nodes of degree > 1 (tree.py:377)          */
   RC_DRAW_CUT = 4,    /* random.choice(cuts) (tree.py:545)                              */
   RC_DRAW_WROOT = 5,  /* Wilson root (tree.py:112)                                      */
+  RC_DRAW_ACCEPT = 7, /* accept.py:35 random.random() of cut_edge_accept                 */
   RC_DRAW_WALK = 6    /* Wilson successor draw j at node u (tree.py:119): index = rank of u
                          among the nodes of the merged pair (ascending node index),
                          sub = j >> 2, word j & 3; the value picks among u's neighbours

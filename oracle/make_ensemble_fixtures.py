@@ -36,6 +36,8 @@ CASES = {
     "grid20_mst": dict(dims=(20, 20), eps=0.05, tree="mst", steps=60, chains=384),
     "grid20_wilson": dict(dims=(20, 20), eps=0.05, tree="wilson", steps=60, chains=384),
     "grid12_region": dict(dims=(12, 12), eps=0.1, tree="mst", steps=60, chains=384, region=True),
+    # Metropolis acceptance on the number of cut edges (accept.py:19-35)
+    "grid20_cutaccept": dict(dims=(20, 20), eps=0.05, tree="mst", steps=60, chains=384, accept="cut_edge"),
 }
 
 
@@ -73,7 +75,8 @@ def run_chain(seed, case):
         kw["region_surcharge"] = {"county": 0.5}
     chain = MarkovChain(partial(recom, **kw),
                         [constraints.within_percent_of_ideal_population(part, case["eps"])],
-                        accept.always_accept, part, total_steps=case["steps"] + 1)
+                        accept.cut_edge_accept if case.get("accept") == "cut_edge" else accept.always_accept,
+                        part, total_steps=case["steps"] + 1)
     state = None
     for state in chain:
         pass
@@ -87,7 +90,10 @@ def run_chain(seed, case):
 
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         with ProcessPoolExecutor(max_workers=os.cpu_count()) as ex:
             rows = list(ex.map(partial(run_chain, case=case), range(case["chains"])))
         _, part, plan = _build(case)

@@ -577,6 +577,22 @@ static int rco_propose(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t
     double lo = (double)(pop_a < pop_b ? pop_a : pop_b), hi = (double)(pop_a < pop_b ? pop_b : pop_a);
     valid = (c->pop_lower <= lo) && (hi <= c->pop_upper);
   }
+  if (valid && c->accept_rule == RC_ACCEPT_CUT_EDGE) {      /* accept.py:19-35 */
+    int delta = 0;
+    for (int j = 0; j < w->m; ++j) {
+      int e = w->eid[j];
+      int was = mask[e >> 5] >> (e & 31) & 1;
+      int now = w->side[w->eu[j]] != w->side[w->ev[j]];
+      delta += now - was;
+    }
+    double ratio = (double)*cut_count / (double)(*cut_count + delta);
+    RcPhilox p = rc_draw(c->seed, chain, RC_DRAW_ACCEPT, 0, 0, prop_no, 0);
+    if (!(rc_unit_double(p.v[0], p.v[1]) < (ratio < 1.0 ? ratio : 1.0))) {
+      *accepted = 1;                                         /* chain.py:191-195: counts, state kept */
+      rco_ungather(w);
+      return RC_OK;
+    }
+  }
   if (valid) {
     for (int i = 0; i < w->n; ++i) assign[w->nodes[i]] = (uint8_t)(w->side[i] ? b : a);
     tally[a] = pop_a; tally[b] = pop_b;                   /* updaters/tally.py:162-165 */

@@ -19,7 +19,7 @@ from gerrychain_b200.csr import csr_from_networkx
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ALPHA = 0.01
-CASES = ["grid20_mst", "grid20_wilson", "grid12_region"]
+CASES = ["grid20_mst", "grid20_wilson", "grid12_region", "grid20_cutaccept"]
 
 
 def _case(name, n_chains, seed):
@@ -39,7 +39,8 @@ def _case(name, n_chains, seed):
     tree_kind = _abi.RC_TREE_WILSON if meta["tree"] == "wilson" else _abi.RC_TREE_MST
     cfg = EngineConfig(n_districts=k, n_chains=n_chains, pop_target=ideal, epsilon=eps,
                        pop_lower=(1 - eps) * ideal, pop_upper=(1 + eps) * ideal, seed=seed,
-                       tree_kind=tree_kind, cut_policy=cut_policy_for(regions, tree_kind))
+                       tree_kind=tree_kind, cut_policy=cut_policy_for(regions, tree_kind),
+                       accept_rule=_abi.RC_ACCEPT_CUT_EDGE if meta.get("accept") == "cut_edge" else _abi.RC_ACCEPT_ALWAYS)
     return z, meta, g, csr, cfg, ideal
 
 

@@ -171,6 +171,17 @@ def test_max_attempts_status():
         eng.check_status()
 
 
+def test_cut_edge_accept_bit_exact_with_oracle():
+    """accept.py:19-35 on the device: rejected proposals leave the state alone and count."""
+    csr, plan, cfg = workloads.config1(n_chains=32, seed=6, accept_rule=_abi.RC_ACCEPT_CUT_EDGE)
+    eng = _free_run_vs_oracle(csr, plan, cfg, 80)
+    # some proposals were rejected: fewer distinct states than steps on at least one chain
+    csr, plan, cfg0 = workloads.config1(n_chains=32, seed=6)
+    eng0 = _engine(csr, cfg0, plan)
+    eng0.run(80).synchronize()
+    assert not np.array_equal(eng.assignments(), eng0.assignments())
+
+
 def test_pair_reselection():
     csr, plan, cfg = workloads.config1(n_chains=8, seed=5, max_attempts=2, allow_pair_reselection=True)
     _free_run_vs_oracle(csr, plan, cfg, 60)
