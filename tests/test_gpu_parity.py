@@ -145,6 +145,26 @@ def test_free_run_config5_region_aware():
     _free_run_vs_oracle(csr, plan, cfg, 15)
 
 
+def test_free_run_config2_full_batch_many_steps():
+    """BASELINE's full batch (1024 chains, so that chains migrate between CTAs through the
+    ready ring and every SM works on several chains) for 40 steps, in several launches of
+    different length: still bit-exact with the sequential oracle."""
+    from oracle import oracle
+
+    csr, plan, cfg = workloads.config2(n_chains=1024, seed=2024)
+    eng = _engine(csr, cfg, plan)
+    for n in (1, 7, 32):
+        eng.run(n)
+    eng.synchronize()
+    ora = oracle.OracleChains(csr, cfg, plan).run(40, n_threads=16)
+    assert (ora.status == 0).all()
+    assert np.array_equal(eng.assignments(), ora.assignments())
+    assert np.array_equal(eng.tally.cpu().numpy(), ora.tally)
+    assert np.array_equal(eng.cut_mask.cpu().numpy().view(np.uint32), ora.cut_mask)
+    assert np.array_equal(eng.proposal_no.cpu().numpy().view(np.uint32), ora.proposal_no)
+    assert np.array_equal(eng.counters.cpu().numpy()[:, :5], ora.counters[:, :5])
+
+
 def test_node_repeats_and_tight_bounds():
     # percent != epsilon: proposals can be invalid and must not count as steps
     csr, plan, cfg = workloads.config1(n_chains=16, seed=3, node_repeats=2)
