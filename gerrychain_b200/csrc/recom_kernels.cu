@@ -434,7 +434,9 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
 // loop-erased walks fed with the same stacks.  Short cycles (<= 4) are found by a local
 // look-ahead; what remains by pointer doubling over the functional graph.
 constexpr int kLook = 2;  // nodes per thread whose look-ahead result is staged in registers
-constexpr int kSeqThreshold = 24;  // fewer busy threads than this: finish sequentially
+constexpr int kLocalThreshold = 4;  // a local pass with fewer busy threads: try a global detection
+constexpr int kFullThreshold = 8;   // a global detection with fewer busy threads: finish sequentially
+constexpr int kMaxPasses = 4096;    // safety (disconnected input plans): then phase 3's budget applies
 constexpr int kTab = 8;  // draws per node precomputed for the sequential finish
 constexpr uint32_t kInTree = 0xffffu;  // walk stamp of a node that leads to the root
 
@@ -496,41 +498,70 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
   __syncthreads();
   if (s.misc[M_ERR]) return s.misc[M_ERR];
   int walk = 0, passes = 0;
-  // Phase 1 - while many cycles exist, pop them in parallel: u is on a cycle of length <= 4
-  // iff following the pointers brings it back to itself.  (Early on about a third of all
-  // nodes sit on such a cycle; the yield decays quickly.)
+  // Phase 1 - while cycles are plentiful, pop them in parallel.  Local passes: u is on a
+  // cycle of length <= 4 iff following the pointers brings it back to itself (early on about
+  // a third of all nodes sits on such a cycle).  When a local pass finds almost nothing, one
+  // global detection (pointer doubling: after >= n steps every node sits on a cycle or at the
+  // root, and every cycle node is somebody's landing point) pops the longer cycles as well.
+  // The loop ends when even that yields little: what is left is Wilson's sequential tail.
   for (;;) {
-    bool on[kLook];
-    int popped = 0;
+    for (;;) {
+      bool on[kLook];
+      int popped = 0;
 #pragma unroll
-    for (int k = 0; k < kLook; ++k) {
-      const int u = tid + k * T;
-      on[k] = false;
-      if (u < n && u != root) {
-        const int v1 = succ_of(u), v2 = succ_of(v1);
-        bool hit = v2 == u;
-        if (!hit) { const int v3 = succ_of(v2); hit = v3 == u || succ_of(v3) == u; }
-        on[k] = hit;
+      for (int k = 0; k < kLook; ++k) {
+        const int u = tid + k * T;
+        on[k] = false;
+        if (u < n && u != root) {
+          const int v1 = succ_of(u), v2 = succ_of(v1);
+          bool hit = v2 == u;
+          if (!hit) { const int v3 = succ_of(v2); hit = v3 == u || succ_of(v3) == u; }
+          on[k] = hit;
+        }
       }
-    }
-    for (int u = tid + kLook * T; u < n; u += T) {  // merged pairs larger than kLook * T nodes
-      if (u == root) continue;
-      const int v1 = succ_of(u), v2 = succ_of(v1), v3 = succ_of(v2);
-      if (v2 == u || v3 == u || succ_of(v3) == u) atomicOr(&s.wmark[u >> 5], 1u << (u & 31));
-    }
-    __syncthreads();  // every pointer has been read
+      for (int u = tid + kLook * T; u < n; u += T) {  // merged pairs larger than kLook * T nodes
+        if (u == root) continue;
+        const int v1 = succ_of(u), v2 = succ_of(v1), v3 = succ_of(v2);
+        if (v2 == u || v3 == u || succ_of(v3) == u) atomicOr(&s.wmark[u >> 5], 1u << (u & 31));
+      }
+      __syncthreads();  // every pointer has been read
 #pragma unroll
-    for (int k = 0; k < kLook; ++k)
-      if (on[k]) { draw(tid + k * T); ++popped; }
-    for (int u = tid + kLook * T; u < n; u += T)
+      for (int k = 0; k < kLook; ++k)
+        if (on[k]) { draw(tid + k * T); ++popped; }
+      for (int u = tid + kLook * T; u < n; u += T)
+        if ((s.wmark[u >> 5] >> (u & 31)) & 1u) { draw(u); ++popped; }
+      walk += popped;
+      const int busy = __syncthreads_count(popped > 0);
+      if (n > kLook * T) {
+        for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
+        __syncthreads();
+      }
+      if (busy < kLocalThreshold || ++passes > kMaxPasses) break;
+    }
+    if (passes > kMaxPasses) break;
+    // global detection
+    for (int u = tid; u < n; u += T) s.wgA[u] = (lid_t)succ_of(u);
+    __syncthreads();
+    lid_t* __restrict__ A = s.wgA;
+    lid_t* __restrict__ B = s.wgB;
+    for (int span = 1; span < n; span <<= 1) {
+      for (int u = tid; u < n; u += T) B[u] = A[A[u]];
+      __syncthreads();
+      lid_t* tmp = A; A = B; B = tmp;
+    }
+    for (int u = tid; u < n; u += T) {
+      const int v = A[u];
+      if (v != root) atomicOr(&s.wmark[v >> 5], 1u << (v & 31));
+    }
+    __syncthreads();
+    int popped = 0;
+    for (int u = tid; u < n; u += T)
       if ((s.wmark[u >> 5] >> (u & 31)) & 1u) { draw(u); ++popped; }
     walk += popped;
     const int busy = __syncthreads_count(popped > 0);
-    if (n > kLook * T) {
-      for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
-      __syncthreads();
-    }
-    if (busy < kSeqThreshold || ++passes > 64) break;
+    for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
+    __syncthreads();
+    if (busy < kFullThreshold || ++passes > kMaxPasses) break;
   }
   RC_PH(PH_W1);
   // Phase 2 - which nodes already lead to the root?  After >= n steps of the functional
