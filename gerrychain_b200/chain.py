@@ -146,6 +146,12 @@ class ChainBatch:
         """int64 [n_chains, k]: ``partition["population"]`` values, columns in sorted district order."""
         return self._r.engine.tally.cpu().numpy().copy()
 
+    def tally(self, field) -> np.ndarray:
+        """int64 [n_chains, k]: ``Tally(field)`` for every chain (any integer node attribute
+        or list of attributes, e.g. vote counts), computed on the device from the resident plans."""
+        col = self._r.initial_state._ctx.column(field)
+        return self._r.engine.tally_column(col).cpu().numpy()
+
     @property
     def district_labels(self):
         return list(self._r.initial_state._district_labels)

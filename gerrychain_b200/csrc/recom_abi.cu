@@ -337,6 +337,16 @@ int rc_engine_histograms(RcEngine* e, int64_t* d_cut_hist, int32_t n_cut_bins, i
   return RC_OK;
 }
 
+int rc_engine_tally(RcEngine* e, const int32_t* d_column, int64_t* d_out, void* stream) {
+  if (!e || !e->bound) return fail(RC_ERR_INVALID_ARG, "engine has no bound state");
+  if (!d_column || !d_out) return fail(RC_ERR_INVALID_ARG, "null argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  rc::tally_column_kernel<<<e->p.cfg.n_chains, 256, 0, (cudaStream_t)stream>>>(e->p, d_column, (long long*)d_out);
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return RC_OK;
+}
+
 int rc_engine_info(RcEngine* e, RcEngineInfo* out) {
   if (!e || !out) return fail(RC_ERR_INVALID_ARG, "null argument");
   out->cap_nodes = e->p.cap_nodes; out->cap_edges = e->p.cap_edges;

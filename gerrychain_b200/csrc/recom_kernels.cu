@@ -1471,6 +1471,33 @@ __global__ void init_state_kernel(const Params p) {
   }
 }
 
+// Tally of an arbitrary integer node column for every chain (updaters/tally.py:69-170 for
+// columns other than the population the proposal balances - e.g. the vote counts of an
+// Election updater): out[chain][d] = sum of column[v] over nodes v of district d.  One CTA
+// per chain, shared-memory bins, 128-bit loads of the assignment row.
+__global__ void tally_column_kernel(const Params p, const int32_t* __restrict__ column, long long* __restrict__ out) {
+  __shared__ unsigned long long bins[256];
+  const int chain = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const int k = p.cfg.n_districts, N = p.g.N;
+  const uint8_t* assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
+  for (int d = tid; d < 256; d += T) bins[d] = 0;
+  __syncthreads();
+  for (int v0 = tid * 16; v0 < N; v0 += T * 16) {
+    const uint4 q = __ldcg(reinterpret_cast<const uint4*>(assign + v0));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int v = v0 + i;
+      if (v < N) {
+        const uint32_t d = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+        atomicAdd(&bins[d], (unsigned long long)(long long)__ldg(column + v));
+      }
+    }
+  }
+  __syncthreads();
+  for (int d = tid; d < k; d += T) out[(size_t)chain * k + d] = (long long)bins[d];
+}
+
 // Ensemble histograms (one thread per chain).
 __global__ void histogram_kernel(const Params p, unsigned long long* cut_hist, int n_cut_bins,
                                  unsigned long long* dev_hist, int n_dev_bins, double dev_bin_width) {

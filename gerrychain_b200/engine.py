@@ -198,6 +198,17 @@ class Engine:
             float(dev_bin_width), self._stream()))
         return cut, dev
 
+    def tally_column(self, column):
+        """int64 [n_chains, k]: per-district sums of an integer node column (``rc_engine_tally``)."""
+        t = self.torch
+        col = t.as_tensor(np.ascontiguousarray(column, dtype=np.int32)).to(self.device)
+        if col.numel() != self.csr.n_nodes:
+            raise ValueError("column must have one entry per node")
+        out = t.empty((self.cfg.n_chains, self.cfg.n_districts), dtype=t.int64, device=self.device)
+        _check(self.lib, self.lib.rc_engine_tally(self._handle, col.data_ptr(), out.data_ptr(), self._stream()))
+        self.synchronize()  # `col` must outlive the kernel
+        return out
+
     def replay(self, rec, chain: int = 0):
         """TEST HOOK: apply recorded reference steps (tests/_golden.ReplayArrays)."""
         t = self.torch

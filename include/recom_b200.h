@@ -233,6 +233,12 @@ int rc_engine_histograms(RcEngine* e, int64_t* d_cut_hist, int32_t n_cut_bins,
                          int64_t* d_dev_hist, int32_t n_dev_bins, double dev_bin_width,
                          void* stream);
 
+/* Per-district sums of an arbitrary integer node column for every chain:
+ * d_out[chain][d] = sum of d_column[v] over the nodes v of district d (int64).  Replaces
+ * Tally (updaters/tally.py:69-170) for columns other than the balanced population, e.g. the
+ * vote totals of an Election updater (updaters/election.py). */
+int rc_engine_tally(RcEngine* e, const int32_t* d_column, int64_t* d_out, void* stream);
+
 /* Introspection: caps chosen, shared memory per CTA, resident CTAs per SM, grid. */
 typedef struct RcEngineInfo {
   int32_t cap_nodes, cap_edges, threads_per_cta, ctas_per_sm, n_sms, grid;

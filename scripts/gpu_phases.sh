@@ -1,5 +1,6 @@
 mkdir -p gpurun_out
 {
-RECOM_B200_LIB=$PWD/variants/lib_timers.so python scripts/phases.py --workload config3 --wilson --chain-steps 16
-RECOM_B200_LIB=$PWD/variants/lib_timers.so python scripts/phases.py --workload config1 --wilson --chain-steps 32
-} > gpurun_out/phases.log 2>&1
+echo "MST build: slots 11-14 = boruvka weights+init | A+B | C+C' | D"
+RECOM_B200_LIB=$PWD/variants/lib_timers_b.so python scripts/phases.py --workload config2 --chain-steps 64
+RECOM_B200_LIB=$PWD/variants/lib_timers_b.so python scripts/phases.py --workload config3 --chain-steps 64 --chains 1024
+} > gpurun_out/phases_b.log 2>&1

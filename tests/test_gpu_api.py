@@ -183,6 +183,13 @@ def test_batched_markov_chain_matches_oracle_and_api():
     assert part["cut_edges"] == _naive_cut_edges(part)
     assert part["population"] == _naive_tally(part, "population")
     assert len(part["cut_edges"]) == int(ora.cut_count[5])
+    votes = {n: (i * 7) % 13 for i, n in enumerate(grid.graph.nodes)}
+    networkx.set_node_attributes(grid.graph, votes, "votes")
+    got = last.tally("votes")
+    a = last.assignment.cpu().numpy()
+    col = np.array([votes[n] for n in grid.graph.nodes])
+    want = np.stack([np.bincount(a[c], weights=col, minlength=4) for c in range(48)]).astype(np.int64)
+    assert np.array_equal(got, want)
     cut, dev = last.histograms(256, 64, 0.001)
     assert int(cut.sum()) == 48 and int(dev.sum()) == 48
     # run_to_end from a fresh iterator gives the same ensemble in one launch
