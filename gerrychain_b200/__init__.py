@@ -18,13 +18,13 @@ from .constraints import Bounds, Validator, within_percent_of_ideal_population
 from .graph import Graph
 from .grid import Grid
 from .partition import Assignment, GeographicPartition, Partition
-from .proposals import MetagraphError, ReCom, recom
+from .proposals import MetagraphError, ReCom, ReversibilityError, recom, reversible_recom
 from .tree import BipartitionWarning, bipartition_tree
 from .updaters import Tally, cut_edges
 
 __all__ = [
     "MarkovChain", "BatchedMarkovChain", "ChainBatch", "Partition", "GeographicPartition", "Assignment",
-    "Grid", "Graph", "recom", "ReCom", "MetagraphError", "BipartitionWarning", "bipartition_tree",
+    "Grid", "Graph", "recom", "reversible_recom", "ReversibilityError", "ReCom", "MetagraphError", "BipartitionWarning", "bipartition_tree",
     "within_percent_of_ideal_population", "Validator", "Bounds", "Tally", "cut_edges",
     "always_accept", "accept", "constraints", "proposals", "tree", "updaters",
 ]

@@ -22,6 +22,9 @@ RC_ERR_REPLAY = 8
 RC_ERR_NO_ROOT = 9
 RC_ERR_INVALID_STREAK = 10
 RC_ERR_BALANCE = 11
+RC_ERR_REVERSIBILITY = 12
+RC_PROPOSAL_RECOM = 0
+RC_PROPOSAL_REVERSIBLE = 1
 RC_SEED_REMAINING = 255
 
 STATUS_NAMES = {
@@ -37,6 +40,7 @@ STATUS_NAMES = {
     9: "RC_ERR_NO_ROOT",
     10: "RC_ERR_INVALID_STREAK",
     11: "RC_ERR_BALANCE",
+    12: "RC_ERR_REVERSIBILITY",
 }
 
 RC_FLAG_WARNED = 1
@@ -98,6 +102,9 @@ class RcConfig(C.Structure):
         ("threads_per_cta", C.c_int32),
         ("max_invalid_streak", C.c_int32),
         ("accept_rule", C.c_int32),
+        ("proposal_kind", C.c_int32),
+        ("rev_M", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 

@@ -29,7 +29,8 @@ from .accept import always_accept
 from .config import EngineConfig
 from .constraints import Bounds, Validator
 from .partition import Partition
-from .proposals import ReCom, _WARNING_TEXT, engine_kwargs, raise_for_status, recom
+from .proposals import (ReCom, _WARNING_TEXT, engine_kwargs, raise_for_status, recom, reversible_engine_kwargs,
+                        reversible_recom)
 from .tree import BipartitionWarning, bipartition_tree
 
 
@@ -101,6 +102,13 @@ def _recom_arguments(proposal):
     proposal object, or TypeError."""
     if isinstance(proposal, ReCom):
         return proposal.pop_col, proposal.ideal_pop, proposal.epsilon, 1, None, proposal.method
+    if isinstance(proposal, functools.partial) and proposal.func is reversible_recom and not proposal.args:
+        kw = proposal.keywords
+        try:
+            return (kw["pop_col"], kw["pop_target"], kw["epsilon"], 1, None,
+                    ("reversible", kw.get("M", 1), kw.get("repeat_until_valid", False)))
+        except KeyError as e:
+            raise TypeError(f"reversible_recom partial is missing the keyword {e}") from None
     if isinstance(proposal, functools.partial) and proposal.func is recom and not proposal.args:
         kw = proposal.keywords
         try:
@@ -204,7 +212,10 @@ class BatchedMarkovChain:
         self.total_steps = int(total_steps)
         self.n_chains = int(n_chains)
         self.yield_every = max(1, int(yield_every))
-        self._ekw = engine_kwargs(pop_target, epsilon, node_repeats, self.region_surcharge, method)
+        if isinstance(method, tuple) and method[0] == "reversible":
+            self._ekw = reversible_engine_kwargs(pop_target, epsilon, method[1], method[2])
+        else:
+            self._ekw = engine_kwargs(pop_target, epsilon, node_repeats, self.region_surcharge, method)
         self._ekw.update(engine_options)
         if np.isfinite(lower) and np.isfinite(upper):
             self._ekw.update(pop_lower=float(lower), pop_upper=float(upper))

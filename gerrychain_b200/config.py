@@ -34,6 +34,8 @@ class EngineConfig:
     threads_per_cta: int = 0
     max_invalid_streak: int = 0
     accept_rule: int = _abi.RC_ACCEPT_ALWAYS
+    proposal_kind: int = _abi.RC_PROPOSAL_RECOM
+    rev_M: int = 1
 
     def to_struct(self) -> _abi.RcConfig:
         c = _abi.RcConfig()
@@ -56,6 +58,8 @@ class EngineConfig:
         c.threads_per_cta = int(self.threads_per_cta)
         c.max_invalid_streak = int(self.max_invalid_streak)
         c.accept_rule = int(self.accept_rule)
+        c.proposal_kind = int(self.proposal_kind)
+        c.rev_M = int(self.rev_M)
         return c
 
 

@@ -89,6 +89,8 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
     return fail(RC_ERR_INVALID_ARG, "at most 8 region columns");
   if (cfg->tree_kind != RC_TREE_MST && cfg->tree_kind != RC_TREE_WILSON)
     return fail(RC_ERR_INVALID_ARG, "tree_kind %d is neither RC_TREE_MST nor RC_TREE_WILSON", cfg->tree_kind);
+  if (cfg->proposal_kind == RC_PROPOSAL_REVERSIBLE && cfg->tree_kind != RC_TREE_WILSON)
+    return fail(RC_ERR_INVALID_ARG, "reversible_recom draws uniform spanning trees: set tree_kind = RC_TREE_WILSON");
   if (!(cfg->epsilon > 0.0) || !(cfg->pop_target > 0.0))
     return fail(RC_ERR_INVALID_ARG, "epsilon and pop_target must be positive");
   CUDA_OK(cudaSetDevice(device));

@@ -1124,6 +1124,156 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
   return res;
 }
 
+// ---- reversible ReCom (proposals/tree_proposals.py:149-267) ------------------------------
+// An ordered pair of districts uniformly out of k^2; no shared edge -> self-loop.  One
+// uniform spanning tree of the merged pair (no retries), all balanced cuts; more than M ->
+// ReversibilityError, none -> self-loop.  The proposal (uniform cut, root side takes the
+// label of the picked edge's first endpoint) is taken with probability
+// #cuts / (M * seam length of the proposal).  Every call counts as a chain step.
+__device__ ProposalResult propose_reversible(Chain& c, uint32_t prop_no, int32_t* ctr) {
+  const Params& p = *c.p;
+  const Smem& s = c.s;
+  const int tid = threadIdx.x, T = blockDim.x;
+  ProposalResult res = {RC_OK, 1, 0, 0};  // accepted = 1: self-loops count as steps
+  const int k = p.cfg.n_districts;
+  const int M = p.cfg.rev_M > 0 ? p.cfg.rev_M : 1;
+  const RcPhilox rp = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_PAIR, 0, 0, prop_no, 0);
+  const int pr = (int)rc_below(rp.v[0], rp.v[1], (uint32_t)(k * k));
+  const int d_out = pr / k, d_in = pr % k;
+  if (d_out == d_in) return res;  // tree_proposals.py:227
+  // the cut edges between the two districts, ascending edge id
+  auto joins = [&](int e) {
+    const int la = __ldcg(c.assign + p.g.edge_uv[2 * e]), lb = __ldcg(c.assign + p.g.edge_uv[2 * e + 1]);
+    return (la == d_out && lb == d_in) || (la == d_in && lb == d_out);
+  };
+  const int words = (p.g.E + 31) >> 5;
+  const int per = odd_chunk(words);
+  const int lo = min(tid * per, words), hi = min(lo + per, words);
+  int cnt = 0;
+  for (int i = lo; i < hi; ++i) {
+    uint32_t x = __ldcg(c.mask + i);
+    while (x) { const int e = i * 32 + (__ffs(x) - 1); x &= x - 1; cnt += joins(e) ? 1 : 0; }
+  }
+  if (tid == 0) s.misc[M_PICK] = -1;
+  int n_pair;
+  const int excl = block_excl_scan(cnt, &n_pair, s.misc, c.par);
+  if (n_pair == 0) { __syncthreads(); return res; }  // not adjacent: self-loop
+  const int kth = (int)rc_below(rp.v[2], rp.v[3], (uint32_t)n_pair);
+  if (kth >= excl && kth < excl + cnt) {
+    int q = kth - excl;
+    for (int i = lo; i < hi && q >= 0; ++i) {
+      uint32_t x = __ldcg(c.mask + i);
+      while (x) {
+        const int e = i * 32 + (__ffs(x) - 1);
+        x &= x - 1;
+        if (joins(e) && q-- == 0) { s.misc[M_PICK] = e; break; }
+      }
+    }
+  }
+  __syncthreads();
+  const int e = s.misc[M_PICK];
+  __syncthreads();
+  const int lab_root = __ldcg(c.assign + p.g.edge_uv[2 * e]);       // parts_to_merge[0]
+  const int lab_other = __ldcg(c.assign + p.g.edge_uv[2 * e + 1]);  // parts_to_merge[1]
+  Step st;
+  st.a = min(lab_root, lab_other);
+  st.b = max(lab_root, lab_other);
+  int d_sub = 0;
+  res.status = gather_pair<true>(c, st, &d_sub);
+  if (tid == 0) { ctr[RC_CTR_NODES] += st.n; ctr[RC_CTR_SLOTS] += d_sub; }
+  if (res.status) return res;
+  const int n = st.n, nt = n - 1;
+  if (n < 3) { res.status = RC_ERR_NO_ROOT; return res; }
+  res.status = wilson_tree(c, st, 0, prop_no, 0, ctr);
+  if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_ATTEMPTS] += 1; }
+  res.trees = 1;
+  if (res.status) return res;
+  euler_subtree_pops(c, st, 0);
+  const double ideal = p.cfg.pop_target;
+  const double thr = __dmul_rn(ideal, p.cfg.epsilon);
+  auto is_bal = [&](int t) { return balanced(s.cur[t], st.tot, ideal, thr); };
+  if (tid == 0) { s.misc[M_NBAL] = 0; s.misc[M_NINT] = 0; }
+  __syncthreads();
+  auto internal = [&](int i) { return s.nxt[s.head[i]] != kNone; };
+  {
+    int cb = 0, ci = 0;
+    for (int t = tid; t < nt; t += T) cb += is_bal(t) ? 1 : 0;
+    for (int i = tid; i < n; i += T) ci += internal(i) ? 1 : 0;
+    cb = warp_sum(cb);
+    ci = warp_sum(ci);
+    if ((tid & 31) == 0) { if (cb) atomicAdd(&s.misc[M_NBAL], cb); if (ci) atomicAdd(&s.misc[M_NINT], ci); }
+  }
+  __syncthreads();
+  const int nbal = s.misc[M_NBAL], n_int = s.misc[M_NINT];
+  res.nbal = nbal;
+  if (nbal > M) { res.status = RC_ERR_REVERSIBILITY; return res; }  // tree_proposals.py:205-209
+  if (nbal == 0) return res;                                           // self-loop: no balance edge
+  const RcPhilox rr = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_ROOT, 0, 0, prop_no, 0);
+  const int root = select_kth(c, n, (int)rc_below(rr.v[0], rr.v[1], (uint32_t)n_int), internal);
+  const RcPhilox rc_ = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_CUT, 0, 0, prop_no, 0);
+  const int tstar = select_kth(c, nt, (int)rc_below(rc_.v[0], rc_.v[1], (uint32_t)nbal), is_bal);
+  const int pa = s.P[2 * tstar], pb = s.P[2 * tstar + 1];
+  const int pd = min(pa, pb), pu = max(pa, pb);
+  auto below = [&](int i) { const int en = s.ent[i]; return en != 0xffff && en >= pd && en <= pu; };
+  const bool root_below = below(root);
+  const int child_pop = s.cur[tstar];
+  const long long pop_root = root_below ? (long long)child_pop : (long long)st.tot - child_pop;
+  const long long pop_other = (long long)st.tot - pop_root;
+  // new side bitmap: bit = node carries st.b afterwards
+  const bool root_is_b = lab_root == st.b;
+  auto new_is_b = [&](int i) { return (below(i) != root_below) != root_is_b; };  // cut-away side takes lab_other
+  if (tid == 0) { s.misc[M_DELTA] = 0; s.misc[M_CNT] = 0; }
+  for (int i0 = 0; i0 < n; i0 += T) {
+    const int i = i0 + tid;
+    const uint32_t bal = __ballot_sync(0xffffffffu, i < n && new_is_b(i));
+    if (i < n && (tid & 31) == 0) s.newb[i >> 5] = bal;
+  }
+  __syncthreads();
+  int seam = 0, delta = 0;
+  for (int j = tid; j < st.m; j += T) {
+    const int u = s.eu[j], v = s.ev[j];
+    const int was = ((s.oldb[u >> 5] >> (u & 31)) ^ (s.oldb[v >> 5] >> (v & 31))) & 1u;
+    const int now = ((s.newb[u >> 5] >> (u & 31)) ^ (s.newb[v >> 5] >> (v & 31))) & 1u;
+    seam += now;
+    delta += now - was;
+  }
+  seam = warp_sum(seam);
+  delta = warp_sum(delta);
+  if ((tid & 31) == 0) { if (seam) atomicAdd(&s.misc[M_CNT], seam); if (delta) atomicAdd(&s.misc[M_DELTA], delta); }
+  __syncthreads();
+  const int seam_len = s.misc[M_CNT], dcut = s.misc[M_DELTA];
+  const double prob = __ddiv_rn((double)nbal, (double)((long long)M * seam_len));  // tree_proposals.py:256
+  if (prob > 1.0) { res.status = RC_ERR_REVERSIBILITY; return res; }
+  const RcPhilox ra = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_ACCEPT, 0, 0, prop_no, 0);
+  if (!(rc_unit_double(ra.v[0], ra.v[1]) < prob)) return res;  // self-loop
+  if (p.cfg.pop_lower <= p.cfg.pop_upper) {  // the chain's Bounds (constraints/bounds.py:25-28)
+    const double lo2 = (double)min(pop_root, pop_other), hi2 = (double)max(pop_root, pop_other);
+    if (!(p.cfg.pop_lower <= lo2 && hi2 <= p.cfg.pop_upper)) {
+      if (tid == 0) ctr[RC_CTR_INVALID] += 1;
+      res.accepted = 0;
+      return res;
+    }
+  }
+  for (int i = tid; i < n; i += T) {
+    const bool nb = (s.newb[i >> 5] >> (i & 31)) & 1u, ob = (s.oldb[i >> 5] >> (i & 31)) & 1u;
+    if (nb != ob) c.assign[c.nodes[i]] = (uint8_t)(nb ? st.b : st.a);
+  }
+  for (int j = tid; j < st.m; j += T) {
+    const int u = s.eu[j], v = s.ev[j];
+    const int was = ((s.oldb[u >> 5] >> (u & 31)) ^ (s.oldb[v >> 5] >> (v & 31))) & 1u;
+    const int now = ((s.newb[u >> 5] >> (u & 31)) ^ (s.newb[v >> 5] >> (v & 31))) & 1u;
+    if (now != was) { const int eid = c.eids[j]; atomicXor(c.mask + (eid >> 5), 1u << (eid & 31)); }
+  }
+  if (tid == 0) {
+    c.tally[lab_root] = pop_root;
+    c.tally[lab_other] = pop_other;
+    p.st.d_cut_count[c.chain] = __ldcg(p.st.d_cut_count + c.chain) + dcut;
+    if (p.st.d_last_pair) { p.st.d_last_pair[2 * c.chain] = st.a; p.st.d_last_pair[2 * c.chain + 1] = st.b; }
+  }
+  __syncthreads();
+  return res;
+}
+
 // =========================================================================================
 __device__ __forceinline__ int ld_acquire(const int32_t* p) {
   int v;
@@ -1214,7 +1364,12 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
       const RcReplayStep* rs = replay ? p.rp.steps + t : nullptr;
       ProposalResult r = {RC_OK, 0, 0, 0};
       for (int streak = 0; streak < streak_cap; ++streak) {
-        r = propose<kWilson>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
+        if constexpr (kWilson) {
+          if (p.cfg.proposal_kind == RC_PROPOSAL_REVERSIBLE && !replay) r = propose_reversible(c, prop_no, ctr);
+          else r = propose<kWilson>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
+        } else {
+          r = propose<kWilson>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
+        }
         ++prop_no;
         __syncthreads();
         if (r.status || r.accepted || replay) break;

@@ -104,6 +104,8 @@ def raise_for_status(code: int, max_attempts, n_pairs=None):
         raise MetagraphError(
             f"Bipartitioning failed for all {n_pairs} district pairs."
             f"Consider rerunning the chain with a different random seed.")
+    if code == _abi.RC_ERR_REVERSIBILITY:  # tree_proposals.py:205-209, :257-261
+        raise ReversibilityError("Found more balance edges than the upper bound M allows.")
     if code in (_abi.RC_ERR_NO_CUT_EDGES, _abi.RC_ERR_NO_ROOT):  # random.choice of an empty sequence
         raise IndexError("Cannot choose from an empty sequence")
     from .engine import EngineError
@@ -129,6 +131,27 @@ def recom(partition, pop_col: str, pop_target: Union[int, float], epsilon: float
     rkey = tuple(region_surcharge.items()) if region_surcharge else ()
     key = ("recom", rkey) + tuple(sorted((kk, vv) for kk, vv in ekw.items()))
     eng = ctx.engine(key, pop_col, k, region_surcharge, **ekw)  # Bounds are checked by the caller's Validator
+    h_assign, h_tally, h_cut = _run_one_step(partition, pop_col, eng, ekw["max_attempts"])
+    if not eng._api_warned and int(eng.flags[0].item()) & _abi.RC_FLAG_WARNED:  # tree.py:703-710
+        eng._api_warned = True
+        warnings.warn(_WARNING_TEXT.format(ekw["warn_attempts"]), BipartitionWarning)
+    return partition.__class__._from_device(
+        partition, h_assign[0].numpy().copy(), (pop_col,), h_tally[0].numpy().copy(), int(h_cut[0]),
+        eng.cut_mask[0].cpu().numpy().view(np.uint32).copy(), eng.last_pair[0].cpu().numpy())
+
+
+def reversible_engine_kwargs(pop_target, epsilon, M, repeat_until_valid=False) -> Dict:
+    """RcConfig fields of a reversible_recom configuration."""
+    if repeat_until_valid:
+        raise NotImplementedError("reversible_recom(repeat_until_valid=True) has no device path")
+    return dict(pop_target=float(pop_target), epsilon=float(epsilon), node_repeats=1, max_attempts=1,
+                tree_kind=_abi.RC_TREE_WILSON, cut_policy=_abi.RC_CUT_UNIFORM,
+                proposal_kind=_abi.RC_PROPOSAL_REVERSIBLE, rev_M=int(M))
+
+
+def _run_one_step(partition, pop_col, eng, max_attempts):
+    """Host plan in, one device step, host plan out; shared by recom and reversible_recom."""
+    k = len(partition)
     bufs = getattr(eng, "_api_bufs", None)
     if bufs is None:
         bufs = eng._api_bufs = eng.host_buffers()
@@ -136,12 +159,30 @@ def recom(partition, pop_col: str, pop_target: Union[int, float], epsilon: float
     h_assign, h_tally, h_cut, h_status = bufs
     h_assign[0].numpy()[:] = partition._vec
     eng.step_host(h_assign, 1, h_assign, h_tally, h_cut, h_status)
-    raise_for_status(int(h_status[0]), ekw["max_attempts"], k * (k - 1) / 2)
-    if not eng._api_warned and int(eng.flags[0].item()) & _abi.RC_FLAG_WARNED:  # tree.py:703-710
-        eng._api_warned = True
-        warnings.warn(_WARNING_TEXT.format(ekw["warn_attempts"]), BipartitionWarning)
+    raise_for_status(int(h_status[0]), max_attempts, k * (k - 1) / 2)
+    return h_assign, h_tally, h_cut
+
+
+def reversible_recom(partition, pop_col: str, pop_target: Union[int, float], epsilon: float,
+                     balance_edge_fn: Callable = tree.find_balanced_edge_cuts_memoization, M: int = 1,
+                     repeat_until_valid: bool = False, choice: Callable = None):
+    """Reversible ReCom (tree_proposals.py:149-267) as one chain-step kernel launch: uniform
+    ordered district pair, one uniform spanning tree, all balanced cuts (more than ``M``:
+    ``ReversibilityError``), acceptance with probability ``#cuts / (M * seam length)``.
+    Returns ``partition`` itself on a self-loop, like the reference."""
+    if balance_edge_fn is not tree.find_balanced_edge_cuts_memoization or choice is not None:
+        raise NotImplementedError("reversible_recom hooks (balance_edge_fn, choice) have no device path")
+    ctx = partition._ctx
+    k = len(partition)
+    ekw = reversible_engine_kwargs(pop_target, epsilon, M, repeat_until_valid)
+    key = ("reversible",) + tuple(sorted(ekw.items()))
+    eng = ctx.engine(key, pop_col, k, None, **ekw)
+    h_assign, h_tally, h_cut = _run_one_step(partition, pop_col, eng, 1)
+    new_vec = h_assign[0].numpy()
+    if np.array_equal(new_vec, partition._vec):
+        return partition  # self-loop (no adjacency, no balance edge, or rejected)
     return partition.__class__._from_device(
-        partition, h_assign[0].numpy().copy(), (pop_col,), h_tally[0].numpy().copy(), int(h_cut[0]),
+        partition, new_vec.copy(), (pop_col,), h_tally[0].numpy().copy(), int(h_cut[0]),
         eng.cut_mask[0].cpu().numpy().view(np.uint32).copy(), eng.last_pair[0].cpu().numpy())
 
 

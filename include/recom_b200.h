@@ -44,7 +44,8 @@ enum {
   RC_ERR_REPLAY = 8,        /* replay record inconsistent with the state              */
   RC_ERR_NO_ROOT = 9,       /* tree.py:377 choice([]) : no tree node of degree > 1    */
   RC_ERR_INVALID_STREAK = 10, /* proposals kept failing the population Bounds          */
-  RC_ERR_BALANCE = 11       /* tree.py:1441-1446 BalanceError / PopulationBalanceError (seed plans) */
+  RC_ERR_BALANCE = 11,      /* tree.py:1441-1446 BalanceError / PopulationBalanceError (seed plans) */
+  RC_ERR_REVERSIBILITY = 12 /* tree_proposals.py:205-209, :257-261 ReversibilityError   */
 };
 
 /* seed plans (tree.py:971-1085): label of nodes not yet assigned, and the proposal-number
@@ -59,6 +60,10 @@ enum {
 
 enum { RC_TREE_MST = 0,   /* tree.py:60-94  random_spanning_tree (+ networkx Kruskal) */
        RC_TREE_WILSON = 1 /* tree.py:97-132 uniform_spanning_tree                     */ };
+
+enum { RC_PROPOSAL_RECOM = 0,      /* proposals/tree_proposals.py:36-146  recom              */
+       RC_PROPOSAL_REVERSIBLE = 1  /* proposals/tree_proposals.py:149-267 reversible_recom
+                                      (needs tree_kind = RC_TREE_WILSON)                  */ };
 
 enum { RC_ACCEPT_ALWAYS = 0,   /* accept.py:15 always_accept                            */
        RC_ACCEPT_CUT_EDGE = 1  /* accept.py:19-35 cut_edge_accept: a valid proposal is taken
@@ -104,6 +109,9 @@ typedef struct RcConfig {
   int32_t threads_per_cta;    /* 0: engine picks                                       */
   int32_t max_invalid_streak; /* consecutive invalid proposals before RC_ERR_INVALID_STREAK (0: 1000) */
   int32_t accept_rule;        /* RC_ACCEPT_*: MarkovChain(accept=)  chain.py:192        */
+  int32_t proposal_kind;      /* RC_PROPOSAL_*                                          */
+  int32_t rev_M;              /* reversible_recom(M=): bound on the number of balanced cuts */
+  int32_t reserved_;
 } RcConfig;
 
 /* ---- chain state, resident in HBM, owned by the caller --------------------------- */

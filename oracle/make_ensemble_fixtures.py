@@ -38,6 +38,8 @@ CASES = {
     "grid12_region": dict(dims=(12, 12), eps=0.1, tree="mst", steps=60, chains=384, region=True),
     # Metropolis acceptance on the number of cut edges (accept.py:19-35)
     "grid20_cutaccept": dict(dims=(20, 20), eps=0.05, tree="mst", steps=60, chains=384, accept="cut_edge"),
+    # reversible ReCom (tree_proposals.py:149-267): most proposals are self-loops, hence many steps
+    "grid12_reversible": dict(dims=(12, 12), eps=0.1, tree="wilson", steps=1500, chains=256, reversible_M=12),
 }
 
 
@@ -73,7 +75,13 @@ def run_chain(seed, case):
     kw = dict(pop_col="population", pop_target=ideal, epsilon=case["eps"], node_repeats=1, method=method)
     if case.get("region"):
         kw["region_surcharge"] = {"county": 0.5}
-    chain = MarkovChain(partial(recom, **kw),
+    proposal = partial(recom, **kw)
+    if case.get("reversible_M"):
+        from gerrychain.proposals.tree_proposals import reversible_recom
+
+        proposal = partial(reversible_recom, pop_col="population", pop_target=ideal, epsilon=case["eps"],
+                           M=case["reversible_M"])
+    chain = MarkovChain(proposal,
                         [constraints.within_percent_of_ideal_population(part, case["eps"])],
                         accept.cut_edge_accept if case.get("accept") == "cut_edge" else accept.always_accept,
                         part, total_steps=case["steps"] + 1)

@@ -613,6 +613,86 @@ static int rco_propose(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t
   return RC_OK;
 }
 
+/* proposals/tree_proposals.py:149-267 reversible_recom; *accepted = 1 also for self-loops
+ * (the chain counts every call as a step), 0 only when the proposal fails the Bounds. */
+static int rco_propose_reversible(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t chain,
+                                  uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
+                                  uint32_t prop_no, int64_t* counters, int* accepted, int32_t* last_pair) {
+  int k = c->n_districts, M = c->rev_M > 0 ? c->rev_M : 1;
+  *accepted = 1;
+  RcPhilox rp = rc_draw(c->seed, chain, RC_DRAW_PAIR, 0, 0, prop_no, 0);
+  int pr = (int)rc_below(rp.v[0], rp.v[1], (uint32_t)(k * k));
+  int d_out = pr / k, d_in = pr % k;
+  if (d_out == d_in) return RC_OK;
+  int n_pair = 0;
+  for (int e = 0; e < g->n_edges; ++e) {
+    int la = assign[g->edge_uv[2 * e]], lb = assign[g->edge_uv[2 * e + 1]];
+    if ((la == d_out && lb == d_in) || (la == d_in && lb == d_out)) ++n_pair;
+  }
+  if (!n_pair) return RC_OK;
+  int kth = (int)rc_below(rp.v[2], rp.v[3], (uint32_t)n_pair), e_star = -1;
+  for (int e = 0; e < g->n_edges; ++e) {
+    int la = assign[g->edge_uv[2 * e]], lb = assign[g->edge_uv[2 * e + 1]];
+    if (((la == d_out && lb == d_in) || (la == d_in && lb == d_out)) && kth-- == 0) { e_star = e; break; }
+  }
+  int lab_root = assign[g->edge_uv[2 * e_star]], lab_other = assign[g->edge_uv[2 * e_star + 1]];
+  int a = lab_root < lab_other ? lab_root : lab_other, b = lab_root < lab_other ? lab_other : lab_root;
+  rco_gather(g, w, assign, a, b);
+  counters[RC_CTR_NODES] += w->n;
+  for (int i = 0; i < w->n; ++i) counters[RC_CTR_SLOTS] += g->row_ptr[w->nodes[i] + 1] - g->row_ptr[w->nodes[i]];
+  if (w->n < 3) { rco_ungather(w); return RC_ERR_NO_ROOT; }
+  int rc = rco_wilson(g, c, w, chain, 0, prop_no, NULL, 0, &counters[RC_CTR_WALK]);
+  counters[RC_CTR_TREES]++; counters[RC_CTR_ATTEMPTS]++;
+  if (rc) { rco_ungather(w); return rc; }
+  build_tree_adj(w);
+  int n_int = 0, root = -1;
+  for (int i = 0; i < w->n; ++i) n_int += (w->toff[i + 1] - w->toff[i]) > 1;
+  if (!n_int) { rco_ungather(w); return RC_ERR_NO_ROOT; }
+  {
+    RcPhilox p = rc_draw(c->seed, chain, RC_DRAW_ROOT, 0, 0, prop_no, 0);
+    int q = (int)rc_below(p.v[0], p.v[1], (uint32_t)n_int);
+    for (int i = 0; i < w->n; ++i)
+      if ((w->toff[i + 1] - w->toff[i]) > 1 && q-- == 0) { root = i; break; }
+  }
+  rco_bfs(w, root);
+  rco_subtree_pops(g, w);
+  int nb = rco_balanced_cuts(w, c->pop_target, c->epsilon, root);
+  if (nb > M) { rco_ungather(w); return RC_ERR_REVERSIBILITY; }
+  if (!nb) { rco_ungather(w); return RC_OK; }
+  RcPhilox pc = rc_draw(c->seed, chain, RC_DRAW_CUT, 0, 0, prop_no, 0);
+  int pick = (int)rc_below(pc.v[0], pc.v[1], (uint32_t)nb);
+  int child = w->bal_child[pick];
+  int64_t pop_other = w->subpop[child], pop_root = w->totpop - pop_other;
+  mark_subtree(w, child);  /* side = 1: cut away from the root -> lab_other */
+  int seam = 0, delta = 0;
+  for (int j = 0; j < w->m; ++j) {
+    int e = w->eid[j];
+    int was = mask[e >> 5] >> (e & 31) & 1;
+    int now = w->side[w->eu[j]] != w->side[w->ev[j]];
+    seam += now; delta += now - was;
+  }
+  double prob = (double)nb / (double)((int64_t)M * seam);
+  if (prob > 1.0) { rco_ungather(w); return RC_ERR_REVERSIBILITY; }
+  RcPhilox pa = rc_draw(c->seed, chain, RC_DRAW_ACCEPT, 0, 0, prop_no, 0);
+  if (!(rc_unit_double(pa.v[0], pa.v[1]) < prob)) { rco_ungather(w); return RC_OK; }
+  if (c->pop_lower <= c->pop_upper) {
+    double lo = (double)(pop_root < pop_other ? pop_root : pop_other), hi = (double)(pop_root < pop_other ? pop_other : pop_root);
+    if (!(c->pop_lower <= lo && hi <= c->pop_upper)) { counters[RC_CTR_INVALID]++; *accepted = 0; rco_ungather(w); return RC_OK; }
+  }
+  for (int i = 0; i < w->n; ++i) assign[w->nodes[i]] = (uint8_t)(w->side[i] ? lab_other : lab_root);
+  tally[lab_root] = pop_root; tally[lab_other] = pop_other;
+  for (int j = 0; j < w->m; ++j) {
+    int e = w->eid[j];
+    int was = mask[e >> 5] >> (e & 31) & 1;
+    int now = w->side[w->eu[j]] != w->side[w->ev[j]];
+    if (was != now) mask[e >> 5] ^= 1u << (e & 31);
+  }
+  *cut_count += delta;
+  if (last_pair) { last_pair[0] = a; last_pair[1] = b; }
+  rco_ungather(w);
+  return RC_OK;
+}
+
 /* chain.py:185-195: propose until a valid state, accept (always), count the step. */
 int rco_step(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t global_chain,
              uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
@@ -621,8 +701,11 @@ int rco_step(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t global_ch
   for (int streak = 0; streak < streak_cap; ++streak) {
     int accepted = 0;
     uint32_t p = (*proposal_no)++;
-    int rc = rco_propose(g, c, w, global_chain, assign, tally, mask, cut_count, p, counters,
-                         flags, NULL, NULL, NULL, &accepted, last_pair);
+    int rc = c->proposal_kind == RC_PROPOSAL_REVERSIBLE
+                 ? rco_propose_reversible(g, c, w, global_chain, assign, tally, mask, cut_count, p, counters,
+                                          &accepted, last_pair)
+                 : rco_propose(g, c, w, global_chain, assign, tally, mask, cut_count, p, counters,
+                               flags, NULL, NULL, NULL, &accepted, last_pair);
     if (rc) return rc;
     if (accepted) return RC_OK;
   }

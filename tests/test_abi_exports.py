@@ -26,7 +26,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_abi.RcReplayStep) == 24
     assert ctypes.sizeof(_abi.RcGraph) == 8 + 5 * 8 + 8 + 2 * 8
     assert ctypes.sizeof(_abi.RcState) == 9 * 8 + 16 + 8
-    assert ctypes.sizeof(_abi.RcConfig) == 96  # == sizeof(RcConfig) in include/recom_b200.h
+    assert ctypes.sizeof(_abi.RcConfig) == 112  # == sizeof(RcConfig) in include/recom_b200.h
 
 
 def test_create_rejects_bad_arguments_without_gpu():

@@ -19,7 +19,7 @@ from gerrychain_b200.csr import csr_from_networkx
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ALPHA = 0.01
-CASES = ["grid20_mst", "grid20_wilson", "grid12_region", "grid20_cutaccept"]
+CASES = ["grid20_mst", "grid20_wilson", "grid12_region", "grid20_cutaccept", "grid12_reversible"]
 
 
 def _case(name, n_chains, seed):
@@ -40,7 +40,9 @@ def _case(name, n_chains, seed):
     cfg = EngineConfig(n_districts=k, n_chains=n_chains, pop_target=ideal, epsilon=eps,
                        pop_lower=(1 - eps) * ideal, pop_upper=(1 + eps) * ideal, seed=seed,
                        tree_kind=tree_kind, cut_policy=cut_policy_for(regions, tree_kind),
-                       accept_rule=_abi.RC_ACCEPT_CUT_EDGE if meta.get("accept") == "cut_edge" else _abi.RC_ACCEPT_ALWAYS)
+                       accept_rule=_abi.RC_ACCEPT_CUT_EDGE if meta.get("accept") == "cut_edge" else _abi.RC_ACCEPT_ALWAYS,
+                       proposal_kind=_abi.RC_PROPOSAL_REVERSIBLE if meta.get("reversible_M") else _abi.RC_PROPOSAL_RECOM,
+                       rev_M=meta.get("reversible_M", 1))
     return z, meta, g, csr, cfg, ideal
 
 

@@ -221,3 +221,22 @@ def test_from_random_assignment_and_recursive_tree_part():
                                    total_steps=11, n_chains=32, seed=1, initial_assignments=plans)
     last = runner.run_to_end()
     assert (np.abs(last.population() - ideal) <= 3.6).all()
+
+
+def test_reversible_recom_as_a_proposal():
+    """Reference tests/test_tree.py:305-317: a reversible_recom chain keeps districts contiguous."""
+    random.seed(5)
+    graph = _three_by_three()
+    partition = Partition(graph, {0: 1, 1: 1, 2: 1, 3: 1, 4: 1, 5: 2, 6: 2, 7: 2, 8: 2}, {"pop": Tally("pop")})
+    ideal = sum(partition["pop"].values()) / 2
+    proposal = functools.partial(gc.reversible_recom, pop_col="pop", pop_target=ideal, epsilon=0.25, M=4)
+    chain = MarkovChain(proposal, [within_percent_of_ideal_population(partition, 0.25, "pop")], always_accept,
+                        partition, total_steps=300)
+    seen = set()
+    for state in chain:
+        assert _contiguous(state)
+        seen.add(state.assignment_vector().tobytes())
+    assert len(seen) > 1
+    runner = gc.BatchedMarkovChain(proposal, [within_percent_of_ideal_population(partition, 0.25, "pop")],
+                                   always_accept, partition, total_steps=201, n_chains=16, seed=2)
+    assert (np.abs(runner.run_to_end().population() - ideal) <= 0.25 * ideal).all()

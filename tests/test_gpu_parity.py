@@ -202,6 +202,29 @@ def test_cut_edge_accept_bit_exact_with_oracle():
     assert not np.array_equal(eng.assignments(), eng0.assignments())
 
 
+def test_reversible_recom_bit_exact_with_oracle():
+    """tree_proposals.py:149-267: ordered pair, one Wilson tree, bound M, seam-length acceptance."""
+    for M in (30, 3):  # M = 3 also meets trees with more than M balanced cuts -> RC_ERR_REVERSIBILITY
+        csr, plan, cfg = workloads.config1(n_chains=24, seed=9, tree_kind=_abi.RC_TREE_WILSON,
+                                           proposal_kind=_abi.RC_PROPOSAL_REVERSIBLE, rev_M=M)
+        from oracle import oracle
+
+        eng = _engine(csr, cfg, plan)
+        eng.run(400).synchronize()
+        ora = oracle.OracleChains(csr, cfg, plan).run(400, n_threads=8)
+        assert np.array_equal(eng.status.cpu().numpy(), ora.status)
+        assert np.array_equal(eng.assignments(), ora.assignments())
+        assert np.array_equal(eng.tally.cpu().numpy(), ora.tally)
+        assert np.array_equal(eng.cut_count.cpu().numpy(), ora.cut_count)
+        assert np.array_equal(eng.step_no.cpu().numpy(), ora.step_no)
+        _naive_check(csr, cfg.n_districts, eng.assignments(), eng.tally.cpu().numpy(),
+                     eng.cut_mask.cpu().numpy(), eng.cut_count.cpu().numpy())
+        if M == 30:
+            assert (ora.status == 0).all() and (eng.assignments() != plan).any()
+        else:
+            assert (ora.status == _abi.RC_ERR_REVERSIBILITY).any()
+
+
 def test_pair_reselection():
     csr, plan, cfg = workloads.config1(n_chains=8, seed=5, max_attempts=2, allow_pair_reselection=True)
     _free_run_vs_oracle(csr, plan, cfg, 60)
