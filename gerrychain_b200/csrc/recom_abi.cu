@@ -179,7 +179,7 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   CUDA_OK(cudaFuncSetAttribute(e->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->ctas_per_sm, e->kernel, e->threads, e->smem));
   if (e->ctas_per_sm < 1) { rc_engine_destroy(e); return fail(RC_ERR_CAPACITY, "kernel does not fit an SM"); }
-  // persistent grid: every CTA resident, (chain, step) tickets handed out in order
+  // persistent grid: every CTA resident; they pop ready chains from a ring (recom_step_kernel)
   e->grid = e->ctas_per_sm * e->n_sms;
   if (e->grid > cfg->n_chains) e->grid = cfg->n_chains;
   // scratch

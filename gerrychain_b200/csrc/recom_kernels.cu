@@ -1284,11 +1284,10 @@ __device__ __forceinline__ void st_release(int32_t* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Free-running mode is a persistent grid: CTAs draw (chain, step) tickets from a global
-// counter, so every SM stays busy whatever the number of chains and however unevenly the
-// retries fall.  Step s of a chain waits (acquire) for step s-1 of the same chain, which an
-// earlier ticket - held by a CTA that is resident by construction - publishes (release).
-// Replay mode (TEST HOOK) is one CTA walking one chain through the record.
+// Free-running mode is a persistent grid over a ring of READY chains (see the loop below):
+// every SM stays busy whatever the number of chains and however unevenly the retries fall,
+// and a slow step delays only its own chain.  Replay mode (TEST HOOK) is one CTA walking one
+// chain through the record.
 template <bool kWilson, bool kSpill>
 __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
