@@ -1397,7 +1397,7 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
     __syncthreads();
     RC_PH(PH_FLUSH);
     if (!replay && tid == 0) {
-      const int done = p.progress[chain] + 1;  // this CTA owns the chain until it is pushed back
+      const int done = __ldcg(p.progress + chain) + 1;  // this CTA owns the chain until it is pushed back
       p.progress[chain] = done;
       if (done < p.n_steps) {
         const unsigned long long q = atomicAdd(p.work_counter + 1, 1ull);
