@@ -39,6 +39,8 @@ CASES = {
     # Metropolis acceptance on the number of cut edges (accept.py:19-35)
     "grid20_cutaccept": dict(dims=(20, 20), eps=0.05, tree="mst", steps=60, chains=384, accept="cut_edge"),
     # reversible ReCom (tree_proposals.py:149-267): most proposals are self-loops, hence many steps
+    # random planar graph with real-valued (integer) populations: 600-node Delaunay, 5 districts
+    "delaunay600_mst": dict(graph="delaunay", n=600, k=5, eps=0.05, tree="mst", steps=60, chains=384),
     "grid12_reversible": dict(dims=(12, 12), eps=0.1, tree="wilson", steps=1500, chains=256, reversible_M=12),
 }
 
@@ -49,6 +51,17 @@ def _build(case):
     from gerrychain import Graph, Partition
     from gerrychain.updaters import Tally, cut_edges
 
+    if case.get("graph") == "delaunay":
+        from gerrychain.tree import recursive_tree_part
+        from gerrychain_b200 import synthetic as syn
+
+        g = syn.delaunay_graph(case["n"], seed=0)
+        graph = Graph.from_networkx(g)
+        random.seed(12345)  # one fixed seed plan for every chain of the ensemble
+        tot = sum(g.nodes[v]["population"] for v in g)
+        plan = recursive_tree_part(graph, range(case["k"]), tot / case["k"], "population", case["eps"])
+        part = Partition(graph, plan, {"population": Tally("population"), "cut_edges": cut_edges})
+        return graph, part, plan
     m, n = case["dims"]
     g = networkx.grid_2d_graph(m, n)
     for (i, j) in g.nodes:

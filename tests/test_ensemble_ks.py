@@ -19,14 +19,18 @@ from gerrychain_b200.csr import csr_from_networkx
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ALPHA = 0.01
-CASES = ["grid20_mst", "grid20_wilson", "grid12_region", "grid20_cutaccept", "grid12_reversible"]
+CASES = ["grid20_mst", "grid20_wilson", "grid12_region", "grid20_cutaccept", "grid12_reversible", "delaunay600_mst"]
 
 
 def _case(name, n_chains, seed):
     z = np.load(os.path.join(GOLDEN, f"ensemble_{name}.npz"))
     meta = json.loads(str(z["meta"]))
-    m, n = meta["dims"]
-    g = synthetic.grid_graph(m, n)
+    if meta.get("graph") == "delaunay":
+        g = synthetic.delaunay_graph(meta["n"], seed=0)
+        m = n = 0
+    else:
+        m, n = meta["dims"]
+        g = synthetic.grid_graph(m, n)
     regions = None
     if meta.get("region"):
         for (i, j) in g.nodes:
