@@ -325,21 +325,51 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
   while (nlive > 0 && nv > 1) {
     ++rounds;
     // A: minimum key per component (native 32-bit shared atomics)
-    for (int q = tid; q < nlive; q += T) {
-      const uint32_t ab = s.lab[q];
-      const uint32_t k = s.key[s.lj[q]];
-      atomicMin(&s.best[ab & 0xffffu], k);
-      atomicMin(&s.best[ab >> 16], k);
+    {  // two adjacent edges per iteration: one 64-bit load of the endpoints, one 32-bit of the ids
+      const uint2* lab2 = reinterpret_cast<const uint2*>(s.lab);
+      const uint32_t* lj2 = reinterpret_cast<const uint32_t*>(s.lj);
+      for (int t = tid; t < (nlive >> 1); t += T) {
+        const uint2 ab = lab2[t];
+        const uint32_t jj = lj2[t];
+        const uint32_t k0 = s.key[jj & 0xffffu], k1 = s.key[jj >> 16];
+        atomicMin(&s.best[ab.x & 0xffffu], k0);
+        atomicMin(&s.best[ab.x >> 16], k0);
+        atomicMin(&s.best[ab.y & 0xffffu], k1);
+        atomicMin(&s.best[ab.y >> 16], k1);
+      }
+      if ((nlive & 1) && tid == 0) {
+        const uint32_t ab = s.lab[nlive - 1];
+        const uint32_t k = s.key[s.lj[nlive - 1]];
+        atomicMin(&s.best[ab & 0xffffu], k);
+        atomicMin(&s.best[ab >> 16], k);
+      }
     }
     __syncthreads();
     // B: among the (almost always single) edges attaining it, the lowest edge index
-    for (int q = tid; q < nlive; q += T) {
-      const uint32_t ab = s.lab[q];
-      const uint32_t j = s.lj[q];
-      const uint32_t k = s.key[j];
-      const uint32_t v = (j << 16) | (uint32_t)q;
-      if (k == s.best[ab & 0xffffu]) atomicMin(&s.bpos[ab & 0xffffu], v);
-      if (k == s.best[ab >> 16]) atomicMin(&s.bpos[ab >> 16], v);
+    {
+      const uint2* lab2 = reinterpret_cast<const uint2*>(s.lab);
+      const uint32_t* lj2 = reinterpret_cast<const uint32_t*>(s.lj);
+      for (int t = tid; t < (nlive >> 1); t += T) {
+        const uint2 ab = lab2[t];
+        const uint32_t jj = lj2[t];
+        const uint32_t j0 = jj & 0xffffu, j1 = jj >> 16;
+        const uint32_t k0 = s.key[j0], k1 = s.key[j1];
+        const uint32_t b00 = s.best[ab.x & 0xffffu], b01 = s.best[ab.x >> 16];
+        const uint32_t b10 = s.best[ab.y & 0xffffu], b11 = s.best[ab.y >> 16];
+        if (k0 == b00) atomicMin(&s.bpos[ab.x & 0xffffu], (j0 << 16) | (uint32_t)(2 * t));
+        if (k0 == b01) atomicMin(&s.bpos[ab.x >> 16], (j0 << 16) | (uint32_t)(2 * t));
+        if (k1 == b10) atomicMin(&s.bpos[ab.y & 0xffffu], (j1 << 16) | (uint32_t)(2 * t + 1));
+        if (k1 == b11) atomicMin(&s.bpos[ab.y >> 16], (j1 << 16) | (uint32_t)(2 * t + 1));
+      }
+      if ((nlive & 1) && tid == 0) {
+        const int q = nlive - 1;
+        const uint32_t ab = s.lab[q];
+        const uint32_t j = s.lj[q];
+        const uint32_t k = s.key[j];
+        const uint32_t v = (j << 16) | (uint32_t)q;
+        if (k == s.best[ab & 0xffffu]) atomicMin(&s.bpos[ab & 0xffffu], v);
+        if (k == s.best[ab >> 16]) atomicMin(&s.bpos[ab >> 16], v);
+      }
     }
     __syncthreads();
     // C: every component hooks onto the other side of its lightest edge; of a mutual pair
