@@ -240,3 +240,25 @@ def test_reversible_recom_as_a_proposal():
     runner = gc.BatchedMarkovChain(proposal, [within_percent_of_ideal_population(partition, 0.25, "pop")],
                                    always_accept, partition, total_steps=201, n_chains=16, seed=2)
     assert (np.abs(runner.run_to_end().population() - ideal) <= 0.25 * ideal).all()
+
+
+def test_flip_chain_incremental_updaters_equal_naive():
+    """Reference tests/test_tally.py:56-76 and tests/updaters/test_cut_edges.py:31-125: after
+    every (multi-node) flip the device-backed Tally / cut_edges equal the naive recomputation,
+    and no edge appears as both (u, v) and (v, u)."""
+    rng = random.Random(4)
+    grid = Grid((8, 8))
+    state = grid
+    nodes = list(grid.graph.nodes)
+    for _ in range(60):
+        flips = {}
+        for _ in range(rng.randint(1, 3)):
+            e = rng.choice(sorted(state["cut_edges"]))
+            src, dst = (e[0], e[1]) if rng.random() < 0.5 else (e[1], e[0])
+            flips[src] = state.assignment.mapping[dst]
+        state = state.flip(flips)
+        assert state["cut_edges"] == _naive_cut_edges(state)
+        assert state["population"] == _naive_tally(state, "population")
+        assert not any((v, u) in state["cut_edges"] for (u, v) in state["cut_edges"])
+        assert state.flips == flips and state.parent is not None
+    assert len(nodes) == 64
