@@ -20,11 +20,11 @@ from .grid import Grid
 from .partition import Assignment, GeographicPartition, Partition
 from .proposals import MetagraphError, ReCom, ReversibilityError, recom, reversible_recom
 from .tree import BipartitionWarning, bipartition_tree
-from .updaters import Tally, cut_edges
+from .updaters import Election, Tally, cut_edges, tally_region_splits
 
 __all__ = [
     "MarkovChain", "BatchedMarkovChain", "ChainBatch", "Partition", "GeographicPartition", "Assignment",
     "Grid", "Graph", "recom", "reversible_recom", "ReversibilityError", "ReCom", "MetagraphError", "BipartitionWarning", "bipartition_tree",
     "within_percent_of_ideal_population", "Validator", "Bounds", "Tally", "cut_edges",
-    "always_accept", "accept", "constraints", "proposals", "tree", "updaters",
+    "Election", "tally_region_splits", "always_accept", "accept", "constraints", "proposals", "tree", "updaters",
 ]

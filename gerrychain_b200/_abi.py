@@ -179,6 +179,8 @@ EXPORTS = (
     "rc_engine_replay",
     "rc_engine_histograms",
     "rc_engine_tally",
+    "rc_engine_region_splits",
+    "rc_engine_contiguity",
     "rc_engine_info",
     "rc_engine_last_run_ms",
 )
@@ -227,6 +229,8 @@ def load() -> C.CDLL:
     lib.rc_engine_histograms.argtypes = [
         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]
     lib.rc_engine_tally.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rc_engine_region_splits.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.rc_engine_contiguity.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.rc_engine_info.argtypes = [C.c_void_p, C.POINTER(RcEngineInfo)]
     lib.rc_engine_last_run_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     if lib.rc_abi_version() != 1:

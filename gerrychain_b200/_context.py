@@ -52,6 +52,7 @@ class GraphContext:
         self._csr: Dict[Tuple, GraphCSR] = {}
         self._engines: Dict[Tuple, object] = {}
         self._edge_labels = None
+        self._region_codes: Dict[str, Tuple[np.ndarray, int]] = {}
 
     @property
     def graph(self):
@@ -151,3 +152,28 @@ class GraphContext:
         eng.synchronize()
         return (eng.tally[0].cpu().numpy().copy(), eng.cut_mask[0].cpu().numpy().view(np.uint32).copy(),
                 int(eng.cut_count[0].item()))
+
+    def region_codes(self, reg_attr: str) -> Tuple[np.ndarray, int]:
+        """Dense int32 code per node for the values of a node attribute.  ``None`` is a value
+        like any other, as it is for the reference's ``==`` (updaters/county_splits.py:152-156)."""
+        hit = self._region_codes.get(reg_attr)
+        if hit is None:
+            g = self.graph
+            codes: Dict = {}
+            col = np.fromiter((codes.setdefault(g.nodes[lab][reg_attr], len(codes)) for lab in self.labels),
+                              dtype=np.int32, count=self.n_nodes)
+            hit = (col, len(codes))
+            self._region_codes[reg_attr] = hit
+        return hit
+
+    def region_stats(self, vec: np.ndarray, reg_attr: str, k: int) -> Tuple[int, int, int]:
+        col, n_regions = self.region_codes(reg_attr)
+        eng = self.engine(("scan",), None, k)
+        eng.set_assignment(vec)
+        out = eng.region_splits(col, n_regions)[0].cpu().numpy()
+        return int(out[0]), int(out[1]), int(out[2])
+
+    def district_pieces(self, vec: np.ndarray, k: int) -> np.ndarray:
+        eng = self.engine(("scan",), None, k)
+        eng.set_assignment(vec)
+        return eng.contiguity()[0].cpu().numpy().copy()

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librecom_b200.so")
 SOURCES = ["recom_abi.cu"]
-DEPS = ["recom_abi.cu", "recom_kernels.cu", "recom_device.cuh",
+DEPS = ["recom_abi.cu", "recom_kernels.cu", "recom_stats.cu", "recom_device.cuh",
         "../../include/recom_b200.h", "../../include/recom_rng.h"]
 
 

@@ -160,6 +160,25 @@ class ChainBatch:
         col = self._r.initial_state._ctx.column(field)
         return self._r.engine.tally_column(col).cpu().numpy()
 
+    def region_splits(self, reg_attr: str) -> np.ndarray:
+        """int32 [n_chains, 3]: per chain the number of ``reg_attr`` regions with a cut edge
+        inside them (``tally_region_splits``), the number spread over more than one district,
+        and the total (region, district) pieces (``rc_engine_region_splits``)."""
+        col, n_regions = self._r.initial_state._ctx.region_codes(reg_attr)
+        return self._r.engine.region_splits(col, n_regions).cpu().numpy()
+
+    def district_pieces(self) -> np.ndarray:
+        """int32 [n_chains, k]: connected pieces of every district (``rc_engine_contiguity``)."""
+        return self._r.engine.contiguity().cpu().numpy()
+
+    def contiguous(self) -> np.ndarray:
+        """bool [n_chains]: ``constraints.contiguous`` of every chain's plan."""
+        return (self.district_pieces() <= 1).all(axis=1)
+
+    def election(self, election) -> np.ndarray:
+        """int64 [n_chains, parties, k]: the vote totals of an ``Election`` for every chain."""
+        return np.stack([self.tally(col) for col in election.columns], axis=1)
+
     @property
     def district_labels(self):
         return list(self._r.initial_state._district_labels)

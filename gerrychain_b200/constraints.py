@@ -83,3 +83,27 @@ def deviation_from_ideal(partition, attribute: str = "population") -> Dict:
     total = sum(partition[attribute].values())
     ideal = total / number_of_districts
     return {part: (value - ideal) / ideal for part, value in partition[attribute].items()}
+
+
+def contiguous(partition) -> bool:
+    """Are the districts connected?  (constraints/contiguity.py:169-181.)  Like the reference
+    only the districts the last move touched are examined (contiguity.py:141-166
+    ``affected_parts``); the pieces of every district are counted on the device
+    (``rc_engine_contiguity``: union-find over the edges that are not cut)."""
+    pieces = partition._district_pieces()
+    flips, parent = partition.flips, partition.parent
+    if flips is None:
+        return bool((pieces <= 1).all())
+    touched = set(flips.values())
+    if parent is not None:
+        touched.update(parent.assignment.mapping[node] for node in flips)
+    rank = partition._rank
+    return all(pieces[rank[part]] <= 1 for part in touched)
+
+
+contiguous_bfs = contiguous
+
+
+def number_of_contiguous_parts(partition) -> int:
+    """How many districts are connected (constraints/contiguity.py:207-216)."""
+    return int((partition._district_pieces() == 1).sum())

@@ -5,6 +5,7 @@
 #include <new>
 
 #include "recom_kernels.cu"
+#include "recom_stats.cu"
 
 namespace {
 
@@ -50,6 +51,7 @@ struct RcEngine {
   int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_slot_edge = nullptr, *d_edge_uv = nullptr,
           *d_pop = nullptr, *d_region = nullptr;
   void* d_scratch = nullptr;
+  int* d_cc_scratch = nullptr;  // union-find parents of rc_engine_contiguity when N words exceed shared memory
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
 };
@@ -71,7 +73,7 @@ int rc_engine_destroy(RcEngine* e) {
   if (!e) return RC_OK;
   cudaSetDevice(e->device);
   cudaFree(e->d_row_ptr); cudaFree(e->d_col_idx); cudaFree(e->d_slot_edge); cudaFree(e->d_edge_uv);
-  cudaFree(e->d_pop); cudaFree(e->d_region); cudaFree(e->d_scratch);
+  cudaFree(e->d_pop); cudaFree(e->d_region); cudaFree(e->d_scratch); cudaFree(e->d_cc_scratch);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   delete e;
@@ -362,6 +364,45 @@ int rc_engine_tally(RcEngine* e, const int32_t* d_column, int64_t* d_out, void* 
   if (!d_column || !d_out) return fail(RC_ERR_INVALID_ARG, "null argument");
   CUDA_OK(cudaSetDevice(e->device));
   rc::tally_column_kernel<<<e->p.cfg.n_chains, 256, 0, (cudaStream_t)stream>>>(e->p, d_column, (long long*)d_out);
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return RC_OK;
+}
+
+int rc_engine_region_splits(RcEngine* e, const int32_t* d_region, int32_t n_regions, int32_t* d_out, void* stream) {
+  if (!e || !e->bound) return fail(RC_ERR_INVALID_ARG, "engine has no bound state");
+  if (!d_region || !d_out || n_regions < 1) return fail(RC_ERR_INVALID_ARG, "null argument or no regions");
+  CUDA_OK(cudaSetDevice(e->device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, e->device));
+  const size_t words = (size_t)n_regions * (1 + (e->p.cfg.n_districts + 31) / 32);
+  const size_t smem = words * sizeof(uint32_t);
+  if (smem + 1024 > prop.sharedMemPerBlockOptin)
+    return fail(RC_ERR_CAPACITY, "%d regions x %d districts need %zu bytes of shared memory", n_regions,
+                e->p.cfg.n_districts, smem);
+  CUDA_OK(cudaFuncSetAttribute(rc::region_splits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = e->p.cfg.n_chains < 4 * e->n_sms ? e->p.cfg.n_chains : 4 * e->n_sms;
+  rc::region_splits_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(e->p, d_region, n_regions, d_out);
+  e->launches++;
+  CUDA_OK(cudaGetLastError());
+  return RC_OK;
+}
+
+int rc_engine_contiguity(RcEngine* e, int32_t* d_out, void* stream) {
+  if (!e || !e->bound) return fail(RC_ERR_INVALID_ARG, "engine has no bound state");
+  if (!d_out) return fail(RC_ERR_INVALID_ARG, "null argument");
+  CUDA_OK(cudaSetDevice(e->device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, e->device));
+  const size_t bytes = (size_t)e->p.g.N * sizeof(int);
+  const bool in_smem = bytes + 1024 <= prop.sharedMemPerBlockOptin;
+  int grid = e->p.cfg.n_chains < 2 * e->n_sms ? e->p.cfg.n_chains : 2 * e->n_sms;
+  if (in_smem) {
+    CUDA_OK(cudaFuncSetAttribute(rc::contiguity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  } else if (!e->d_cc_scratch) {
+    CUDA_OK(cudaMalloc((void**)&e->d_cc_scratch, (size_t)2 * e->n_sms * bytes));
+  }
+  rc::contiguity_kernel<<<grid, 512, in_smem ? bytes : 0, (cudaStream_t)stream>>>(e->p, e->d_cc_scratch, in_smem ? 1 : 0, d_out);
   e->launches++;
   CUDA_OK(cudaGetLastError());
   return RC_OK;

@@ -209,6 +209,31 @@ class Engine:
         self.synchronize()  # `col` must outlive the kernel
         return out
 
+    def region_splits(self, region_ids, n_regions: Optional[int] = None):
+        """int32 [n_chains, 3] (``rc_engine_region_splits``): per chain the regions with a cut
+        edge inside them (the reference's ``total_reg_splits``), the regions spread over more
+        than one district, and the total number of (region, district) pieces."""
+        t = self.torch
+        reg = np.ascontiguousarray(region_ids, dtype=np.int32)
+        if reg.size != self.csr.n_nodes:
+            raise ValueError("region_ids must have one entry per node")
+        if n_regions is None:
+            n_regions = int(reg.max()) + 1 if reg.size else 0
+        col = t.as_tensor(reg).to(self.device)
+        out = t.empty((self.cfg.n_chains, 3), dtype=t.int32, device=self.device)
+        _check(self.lib, self.lib.rc_engine_region_splits(self._handle, col.data_ptr(), int(n_regions),
+                                                          out.data_ptr(), self._stream()))
+        self.synchronize()  # `col` must outlive the kernel
+        return out
+
+    def contiguity(self):
+        """int32 [n_chains, k] (``rc_engine_contiguity``): connected pieces of every district
+        (0 = empty district); a plan is contiguous iff no entry exceeds 1."""
+        t = self.torch
+        out = t.empty((self.cfg.n_chains, self.cfg.n_districts), dtype=t.int32, device=self.device)
+        _check(self.lib, self.lib.rc_engine_contiguity(self._handle, out.data_ptr(), self._stream()))
+        return out
+
     def replay(self, rec, chain: int = 0):
         """TEST HOOK: apply recorded reference steps (tests/_golden.ReplayArrays)."""
         t = self.torch

@@ -269,6 +269,21 @@ class Partition:
             self._scan(fields)
         return self._dev_tally[fields]
 
+    def _region_stats(self, reg_attr: str):
+        """(regions with a cut edge inside, regions over > 1 district, pieces) of this plan
+        for the node attribute ``reg_attr`` (``rc_engine_region_splits``)."""
+        key = ("region_stats", reg_attr)
+        if key not in self._cache:
+            self._cache[key] = self._ctx.region_stats(self._vec, reg_attr, len(self._district_labels))
+        return self._cache[key]
+
+    def _district_pieces(self) -> np.ndarray:
+        """Connected pieces of every district (``rc_engine_contiguity``)."""
+        key = ("district_pieces",)
+        if key not in self._cache:
+            self._cache[key] = self._ctx.district_pieces(self._vec, len(self._district_labels))
+        return self._cache[key]
+
     @property
     def n_cut_edges(self) -> int:
         """``len(partition["cut_edges"])`` without materialising the set."""

@@ -1,4 +1,5 @@
-"""Updaters of the ReCom path: ``Tally`` and ``cut_edges``.
+"""Updaters of the ReCom path: ``Tally`` and ``cut_edges``, and the statistics users read
+behind every state: ``Election`` vote tallies and ``tally_region_splits``.
 
 Reference: /root/reference/gerrychain/updaters/tally.py:69-170 and
 updaters/cut_edges.py:99-120.  The reference recomputes both incrementally on the host
@@ -9,7 +10,10 @@ values in the reference's shapes (``{part: sum}`` and ``{(u, v), ...}``).
 
 from __future__ import annotations
 
-from typing import List, Optional, Type, Union
+import math
+from typing import Dict, List, Optional, Type, Union
+
+import numpy as np
 
 
 class Tally:
@@ -45,3 +49,121 @@ def cut_edges_by_part(partition):
         out[mapping[e[0]]].add(e)
         out[mapping[e[1]]].add(e)
     return out
+
+
+def tally_region_splits(reg_attr_lst):
+    """``{region attribute: number of its regions that are split}``
+    (updaters/county_splits.py:120-161): a region counts as split when some cut edge has both
+    ends in it.  Counted on the device over the plan's cut-edge bitmask
+    (``rc_engine_region_splits``)."""
+
+    def _get_splits(partition):
+        if "cut_edges" not in partition.updaters:
+            raise ValueError("The cut_edges updater must be attached to the partition")
+        return {reg_attr: partition._region_stats(reg_attr)[0] for reg_attr in reg_attr_lst}
+
+    return _get_splits
+
+
+def regions_in_several_districts(reg_attr: str):
+    """Number of regions of ``reg_attr`` whose nodes lie in more than one district - the
+    counties ``county_splits`` (updaters/county_splits.py:58-117) marks other than NOT_SPLIT."""
+
+    def _count(partition):
+        return partition._region_stats(reg_attr)[1]
+
+    return _count
+
+
+class Election:
+    """``Election(name, parties_to_columns, alias=None)`` (updaters/election.py:7-122): one
+    vote column per party, tallied per district on the device (``rc_engine_tally``, or by the
+    step kernel's incremental tally when the column is the balanced population).  Calling it
+    on a partition returns :class:`ElectionResults`."""
+
+    def __init__(self, name: str, parties_to_columns: Union[Dict, List], alias: Optional[str] = None):
+        self.name = name
+        self.alias = alias if alias is not None else name
+        if isinstance(parties_to_columns, dict):
+            pairs = list(parties_to_columns.items())
+        elif isinstance(parties_to_columns, list):
+            pairs = [(col, col) for col in parties_to_columns]
+        else:
+            raise TypeError("Election expects parties_to_columns to be a dict or list")
+        for _, col in pairs:
+            if not isinstance(col, str):
+                raise TypeError("vote columns must be node-attribute names; the device tallies graph columns")
+        self.parties = [party for party, _ in pairs]
+        self.columns = [col for _, col in pairs]
+        self.parties_to_columns = dict(pairs)
+
+    def __str__(self):
+        return "Election '{}' with vote totals for parties {} from columns {}.".format(
+            self.name, str(self.parties), str(self.columns))
+
+    def __repr__(self):
+        return "Election(parties={}, columns={}, alias={})".format(str(self.parties), str(self.columns), str(self.alias))
+
+    def __call__(self, partition) -> "ElectionResults":
+        matrix = np.stack([partition._tally((col,)) for col in self.columns])
+        return ElectionResults(self, matrix, list(partition._district_labels))
+
+
+class ElectionResults:
+    """Per-district vote totals with the reference's queries (updaters/election.py:188-367).
+    Held as one ``[party, district]`` int64 matrix; the dict views the reference exposes
+    (``totals_for_party``, ``totals``, ``percents_for_party``) are derived from it."""
+
+    def __init__(self, election: Election, matrix: np.ndarray, regions: List):
+        self.election = election
+        self.regions = regions
+        self._matrix = np.asarray(matrix, dtype=np.int64)
+        self._row = {party: i for i, party in enumerate(election.parties)}
+        self._col = {region: j for j, region in enumerate(regions)}
+        district_totals = self._matrix.sum(axis=0)
+        self.totals_for_party = {party: {r: int(self._matrix[i, j]) for r, j in self._col.items()}
+                                 for party, i in self._row.items()}
+        self.totals = {r: int(district_totals[j]) for r, j in self._col.items()}
+        self.percents_for_party = {
+            party: {r: (self._matrix[i, j] / district_totals[j] if district_totals[j] > 0 else math.nan)
+                    for r, j in self._col.items()}
+            for party, i in self._row.items()}
+
+    def __str__(self):
+        lines = ["Election Results for {}".format(self.election.name)]
+        for region in self.regions:
+            lines.append("{}:".format(region))
+            lines.extend("  {}: {}".format(party, round(self.percents_for_party[party][region], 4))
+                         for party in self.election.parties)
+        return "\n".join(lines)
+
+    def won(self, party: str, region) -> bool:
+        column = self._matrix[:, self._col[region]]
+        mine = column[self._row[party]]
+        return bool(all(mine > other for i, other in enumerate(column) if i != self._row[party]))
+
+    def seats(self, party: str) -> int:
+        return sum(self.won(party, region) for region in self.regions)
+
+    wins = seats
+
+    def count(self, party: str, region=None) -> int:
+        if region is not None:
+            return int(self._matrix[self._row[party], self._col[region]])
+        return int(self._matrix[self._row[party]].sum())
+
+    def counts(self, party: str):
+        return tuple(int(x) for x in self._matrix[self._row[party]])
+
+    votes = counts
+
+    def percent(self, party: str, region=None) -> float:
+        if region is not None:
+            return self.percents_for_party[party][region]
+        return self.count(party) / self.total_votes()
+
+    def percents(self, party: str):
+        return tuple(self.percents_for_party[party][region] for region in self.regions)
+
+    def total_votes(self) -> int:
+        return int(self._matrix.sum())

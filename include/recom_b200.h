@@ -247,6 +247,24 @@ int rc_engine_histograms(RcEngine* e, int64_t* d_cut_hist, int32_t n_cut_bins,
  * vote totals of an Election updater (updaters/election.py). */
 int rc_engine_tally(RcEngine* e, const int32_t* d_column, int64_t* d_out, void* stream);
 
+/* How a region column (counties, municipalities ...) is split by every chain's plan.
+ * d_region[v] = dense region id in [0, n_regions) of node v, negative = none.
+ * d_out[chain] = { regions with a cut edge whose two ends lie in the region - the count
+ *                  tally_region_splits / total_reg_splits report (updaters/county_splits.py:120-161),
+ *                  regions whose nodes lie in more than one district - the counties
+ *                  compute_county_splits marks other than NOT_SPLIT (updaters/county_splits.py:58-117),
+ *                  sum over regions of the number of districts present in them }  (int32 x 3).
+ * RC_ERR_CAPACITY when n_regions * (1 + ceil(k/32)) words exceed one CTA's shared memory. */
+int rc_engine_region_splits(RcEngine* e, const int32_t* d_region, int32_t n_regions, int32_t* d_out,
+                            void* stream);
+
+/* Contiguity of every chain's plan (constraints/contiguity.py:169-181 contiguous, :226-241
+ * contiguous_components): d_out[chain][d] = number of connected pieces of district d in the
+ * graph without its cut edges (0: the district owns no node), int32 [n_chains][n_districts].
+ * The plan is contiguous iff no entry exceeds 1.  A debug assertion for the step kernel too:
+ * ReCom keeps plans contiguous by construction. */
+int rc_engine_contiguity(RcEngine* e, int32_t* d_out, void* stream);
+
 /* Introspection: caps chosen, shared memory per CTA, resident CTAs per SM, grid. */
 typedef struct RcEngineInfo {
   int32_t cap_nodes, cap_edges, threads_per_cta, ctas_per_sm, n_sms, grid;

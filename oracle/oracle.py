@@ -47,6 +47,9 @@ def load():
         _lib.rco_seed_plan.argtypes = [
             C.POINTER(_abi.RcGraph), C.POINTER(_abi.RcConfig), C.c_void_p, C.c_uint32, C.c_int32,
             C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.RcReplay)]
+        _lib.rco_region_splits.argtypes = [C.POINTER(_abi.RcGraph), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                           C.c_void_p]
+        _lib.rco_contiguity.argtypes = [C.POINTER(_abi.RcGraph), C.c_int32, C.c_void_p, C.c_void_p]
         _lib.rco_philox.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.rco_philox.restype = None
     return _lib
@@ -76,6 +79,27 @@ def mst_of_graph(csr, weights):
     if nt < 0:
         raise RuntimeError(_abi.STATUS_NAMES[-nt])
     return np.sort(out[:nt])
+
+
+def region_splits(csr, k, assignment, region_ids, n_regions=None):
+    """(regions with an inner cut edge, regions over > 1 district, pieces) of one plan."""
+    a = np.ascontiguousarray(assignment, dtype=np.uint8)
+    r = np.ascontiguousarray(region_ids, dtype=np.int32)
+    if n_regions is None:
+        n_regions = int(r.max()) + 1
+    out = np.zeros(3, dtype=np.int32)
+    g = _abi.graph_struct(csr)
+    load().rco_region_splits(C.byref(g), k, a.ctypes.data, r.ctypes.data, n_regions, out.ctypes.data)
+    return tuple(int(x) for x in out)
+
+
+def contiguity(csr, k, assignment):
+    """int32 [k]: connected pieces of every district of one plan."""
+    a = np.ascontiguousarray(assignment, dtype=np.uint8)
+    out = np.zeros(k, dtype=np.int32)
+    g = _abi.graph_struct(csr)
+    load().rco_contiguity(C.byref(g), k, a.ctypes.data, out.ctypes.data)
+    return out
 
 
 def seed_plans(csr, cfg: EngineConfig, n_plans=1, max_attempts=10000, rec=None):

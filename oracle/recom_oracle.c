@@ -966,3 +966,60 @@ void rco_philox(uint32_t k0, uint32_t k1, const uint32_t* ctr, uint32_t* out) {
   RcPhilox p = rc_philox4x32_10(k0, k1, ctr[0], ctr[1], ctr[2], ctr[3]);
   memcpy(out, p.v, 16);
 }
+
+/* ---- per-plan statistics --------------------------------- */
+
+/* updaters/county_splits.py:145-161 total_reg_splits: walk the cut edges, mark a region when
+ * both ends of a cut edge lie in it, count the marked regions -> out[0];
+ * updaters/county_splits.py:82-99 compute_county_splits (no parent): the set of districts
+ * seen in every county; counties with more than one -> out[1]; total set sizes -> out[2]. */
+int rco_region_splits(const RcGraph* g, int32_t k, const uint8_t* assign, const int32_t* region,
+                      int32_t n_regions, int32_t* out) {
+  uint8_t* marked = (uint8_t*)xcalloc((size_t)n_regions, 1);
+  uint8_t* seen = (uint8_t*)xcalloc((size_t)n_regions * (size_t)k, 1);
+  for (int e = 0; e < g->n_edges; ++e) {
+    const int u = g->edge_uv[2 * e], v = g->edge_uv[2 * e + 1];
+    if (assign[u] == assign[v]) continue; /* not a cut edge */
+    if (region[u] == region[v] && region[u] >= 0 && region[u] < n_regions) marked[region[u]] = 1;
+  }
+  for (int v = 0; v < g->n_nodes; ++v)
+    if (region[v] >= 0 && region[v] < n_regions) seen[(size_t)region[v] * k + assign[v]] = 1;
+  out[0] = out[1] = out[2] = 0;
+  for (int r = 0; r < n_regions; ++r) {
+    int nd = 0;
+    for (int d = 0; d < k; ++d) nd += seen[(size_t)r * k + d];
+    out[0] += marked[r];
+    out[1] += nd > 1;
+    out[2] += nd;
+  }
+  free(marked);
+  free(seen);
+  return RC_OK;
+}
+
+/* constraints/contiguity.py:169-181 contiguous -> is_connected_bfs per district
+ * (contiguity.py:184-204, :244-270) and contiguous_components (:226-241): here one breadth-first sweep
+ * that never crosses a cut edge counts the pieces of every district.  out[d] = pieces of d. */
+int rco_contiguity(const RcGraph* g, int32_t k, const uint8_t* assign, int32_t* out) {
+  const int n = g->n_nodes;
+  uint8_t* visited = (uint8_t*)xcalloc((size_t)n, 1);
+  int32_t* queue = (int32_t*)xcalloc((size_t)n, sizeof(int32_t));
+  for (int d = 0; d < k; ++d) out[d] = 0;
+  for (int s = 0; s < n; ++s) {
+    if (visited[s]) continue;
+    if (assign[s] < k) out[assign[s]]++;
+    int head = 0, tail = 0;
+    queue[tail++] = s;
+    visited[s] = 1;
+    while (head < tail) {
+      const int u = queue[head++];
+      for (int q = g->row_ptr[u]; q < g->row_ptr[u + 1]; ++q) {
+        const int v = g->col_idx[q];
+        if (!visited[v] && assign[v] == assign[u]) { visited[v] = 1; queue[tail++] = v; }
+      }
+    }
+  }
+  free(visited);
+  free(queue);
+  return RC_OK;
+}

@@ -35,6 +35,9 @@ int rco_mst_of_graph(const RcGraph* g, const double* weights, int32_t* out_eids)
 int rco_init_chains(const RcGraph* g, const RcConfig* c, const RcState* st);
 int rco_run_chains(const RcGraph* g, const RcConfig* c, int64_t n_steps, const RcState* st,
                    int n_threads);
+int rco_region_splits(const RcGraph* g, int32_t k, const uint8_t* assign, const int32_t* region,
+                      int32_t n_regions, int32_t* out);
+int rco_contiguity(const RcGraph* g, int32_t k, const uint8_t* assign, int32_t* out);
 void rco_philox(uint32_t k0, uint32_t k1, const uint32_t* ctr, uint32_t* out);
 
 #ifdef __cplusplus

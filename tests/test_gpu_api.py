@@ -262,3 +262,96 @@ def test_flip_chain_incremental_updaters_equal_naive():
         assert not any((v, u) in state["cut_edges"] for (u, v) in state["cut_edges"])
         assert state.flips == flips and state.parent is not None
     assert len(nodes) == 64
+
+
+def _stats_fixture_graph(name):
+    import json
+    import os
+
+    import _golden
+
+    z = np.load(os.path.join(_golden.GOLDEN, f"stats_{name}.npz"))
+    meta = json.loads(str(z["meta"]))
+    g = networkx.Graph()
+    for v in range(z["pop"].shape[0]):
+        attrs = {"pop": int(z["pop"][v]), "votes_a": int(z["votes"][0, v]), "votes_b": int(z["votes"][1, v])}
+        for c, col in enumerate(meta["region_cols"]):
+            attrs[col] = int(z["region_ids"][c, v])
+        g.add_node(v, **attrs)
+    g.add_edges_from((int(a), int(b)) for a, b in z["edge_uv"])
+    return z, meta, g
+
+
+@pytest.mark.parametrize("name", ["8x8_muni", "delaunay600"])
+def test_statistics_updaters_match_reference_fixture(name):
+    """tally_region_splits (reference tests/updaters/test_split_scores.py), Election
+    (tests/updaters/test_election.py) and the contiguous constraint
+    (tests/constraints/test_validity.py:73-99), evaluated through the Partition API on the
+    plans whose reference values tests/golden/stats_*.npz holds."""
+    from gerrychain_b200 import Election, tally_region_splits
+    from gerrychain_b200.constraints import contiguous, number_of_contiguous_parts
+
+    z, meta, g = _stats_fixture_graph(name)
+    cols = meta["region_cols"]
+    updaters = {"pop": Tally("pop"), "cut_edges": cut_edges, "splits": tally_region_splits(cols),
+                "election": Election("synthetic", {"A": "votes_a", "B": "votes_b"})}
+    for i in range(0, len(z["plans"]), 7):
+        plan = z["plans"][i]
+        if len(set(plan.tolist())) < meta["k"]:
+            continue
+        part = Partition(g, {v: int(plan[v]) for v in g.nodes}, updaters)
+        assert part["splits"] == {col: int(z["edge_splits"][i, c]) for c, col in enumerate(cols)}
+        res = part["election"]
+        for pi, party in enumerate(("A", "B")):
+            assert res.counts(party) == tuple(int(x) for x in z["vote_counts"][i, pi])
+            assert res.seats(party) == int(z["seats"][i, pi]) == res.wins(party)
+        assert res.total_votes() == int(z["votes"].sum())
+        assert abs(res.percent("A") + res.percent("B") - 1.0) < 1e-12
+        assert contiguous(part) == bool(z["is_contiguous"][i])
+        assert number_of_contiguous_parts(part) == int((z["district_pieces"][i] == 1).sum())
+    with pytest.raises(ValueError):
+        tally_region_splits(cols)(Partition(g, {v: int(z["plans"][0][v]) for v in g.nodes}, {"pop": Tally("pop")},
+                                            use_default_updaters=False))
+
+
+def test_contiguous_checks_only_the_districts_a_flip_touched():
+    """constraints/contiguity.py:141-181: with a parent, only affected parts are examined."""
+    from gerrychain_b200.constraints import contiguous
+
+    grid = Grid((6, 6))
+    assert contiguous(grid)
+    # move the corner of district 0 away: district 0 stays connected, so does the target
+    child = grid.flip({(2, 2): 3})
+    touched_ok = contiguous(child)
+    assert touched_ok == _contiguous(child)
+    # a far-away node dropped into the middle of another district splits nothing it touches
+    # but leaves an island: the island's district is "affected" and reported
+    island = grid.flip({(0, 0): 3})
+    assert contiguous(island) is False and _contiguous(island) is False
+
+
+def test_chain_batch_statistics():
+    from gerrychain_b200 import BatchedMarkovChain, Election
+
+    z, meta, g = _stats_fixture_graph("delaunay600")
+    k = meta["k"]
+    plan0 = z["plans"][0]
+    init = Partition(g, {v: int(plan0[v]) for v in g.nodes}, {"pop": Tally("pop"), "cut_edges": cut_edges})
+    ideal = sum(init["pop"].values()) / k
+    proposal = functools.partial(recom, pop_col="pop", pop_target=ideal, epsilon=0.1, node_repeats=1)
+    batch = BatchedMarkovChain(proposal, [within_percent_of_ideal_population(init, 0.1, pop_key="pop")], always_accept,
+                               init, total_steps=26, n_chains=64, seed=5)
+    last = batch.run_to_end()
+    assert last.contiguous().all() and (last.district_pieces() == 1).all()
+    splits = last.region_splits("county")
+    election = Election("synthetic", {"A": "votes_a", "B": "votes_b"})
+    votes = last.election(election)
+    assert votes.shape == (64, 2, k) and (votes.sum(axis=2) == z["votes"].sum(axis=1)[None, :]).all()
+    from gerrychain_b200 import tally_region_splits
+
+    for ch in (0, 13, 63):
+        part = last.partition(ch)
+        assert tally_region_splits(["county"])(part) == {"county": int(splits[ch, 0])}
+        assert _contiguous(part)
+        res = election(part)
+        assert res.counts("A") == tuple(int(x) for x in votes[ch, 0])
