@@ -104,7 +104,7 @@ class RcConfig(C.Structure):
         ("accept_rule", C.c_int32),
         ("proposal_kind", C.c_int32),
         ("rev_M", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("wilson_handoff", C.c_int32),
     ]
 
 

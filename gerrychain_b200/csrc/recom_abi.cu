@@ -189,8 +189,8 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   size_t b_eids = (size_t)e->grid * cap_edges * sizeof(int32_t);
   size_t b_bad = cfg->allow_pair_reselection ? (size_t)e->grid * 2048 * sizeof(uint32_t) : 0;
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-  // pop/push indices, phase timers, progress words, ring of ready chains
-  size_t b_prog = 512 + 2 * (size_t)cfg->n_chains * sizeof(int32_t);
+  // pop/push indices, phase timers, progress words, ring of ready chains, CTAs counted per SM
+  size_t b_prog = 512 + 2 * (size_t)cfg->n_chains * sizeof(int32_t) + 1024 * sizeof(int32_t);
   size_t b_spill = (size_t)e->grid * e->spill_bytes;
   e->scratch_bytes = al(b_nodes) + al(b_eids) + al(b_bad) + al(b_prog) + al(b_spill);
   CUDA_OK(cudaMalloc(&e->d_scratch, e->scratch_bytes));
@@ -203,6 +203,7 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   p.progress = (int32_t*)(base + 512);
   p.ring = p.progress + cfg->n_chains;
   p.ring_cap = cfg->n_chains;
+  p.sm_slots = p.ring + cfg->n_chains;
   base += al(b_prog);
   p.spill = b_spill ? (unsigned char*)base : nullptr;
   p.spill_stride = (int64_t)e->spill_bytes;

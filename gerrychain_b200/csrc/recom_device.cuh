@@ -43,6 +43,7 @@ struct Params {
   int32_t* progress;      // [n_chains] steps of this launch completed per chain
   int32_t* ring;          // [ring_cap] ready chains (chain id + 1; 0 = empty)
   int32_t ring_cap;
+  int32_t* sm_slots;      // [1024] CTAs of this launch counted per SM (%smid): spreads lone-thread work over the SM's schedulers
   int32_t keep_counters;  // init_state_kernel: 1 = leave step/proposal numbers and counters
                           // alone; 2 = after seeding: also keep a failed chain's status
   int32_t seed_max_attempts;
@@ -75,13 +76,12 @@ struct Smem {
   // uniform-spanning-tree phase (Wilson; aliases the same region)
   uint32_t* wtmp;    // [CN] row cursors while the adjacency is built
   lid_t* wcnt;       // [CN] successor draws consumed by node u
-  lid_t* wsl;        // [CN] adjacency slot of u's current successor
   lid_t* wgA;        // [CN] pointer doubling, ping
   lid_t* wgB;        // [CN] pointer doubling, pong
   uint32_t* wmark;   // [CN/32] nodes found on a cycle; later: nodes in the tree
-  lid_t* wnx;        // [CN] current successor of u (== ladj[wsl[u]]; the root points at itself)
-  unsigned long long* wst;  // [CN] sequential finish: successor | stamp | draws | table base
-  lid_t* wtab;       // [CN][8] the next 8 successors of u (draws base .. base + 7)
+  lid_t* wnx;        // [CN] current successor of u (the root points at itself)
+  unsigned long long* wst;  // [CN] sequential finish: successor | stamp | draws consumed | end of tabulated draws
+  lid_t* wtab;       // [CN][8] ring of tabulated successor draws of u: draw j at slot j & 7
   uint32_t* best;    // [CN] minimum key over the live edges of a component
   uint32_t* bpos;    // [CN] (local edge << 16 | live-list position) of that minimum
   lid_t* hook;       // [CN] component merge forest
@@ -140,7 +140,6 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
   size_t o_vlB = take(wilson ? 0 : size_t(CN / 2 + 2) * 2);
   size_t o_wtmp = take(wilson ? size_t(CN) * 4 : 0);
   size_t o_wcnt = take(wilson ? size_t(CN) * 2 : 0);
-  size_t o_wsl = take(wilson ? size_t(CN) * 2 : 0);
   size_t o_wgA = take(wilson ? size_t(CN) * 2 : 0);
   size_t o_wgB = take(wilson ? size_t(CN) * 2 : 0);
   size_t o_wmark = take(wilson ? size_t((CN + 31) / 32) * 4 : 0);
@@ -178,7 +177,6 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
     s->ladje = (lid_t*)(base + o_ladje);
     s->wtmp = (uint32_t*)(base + o_wtmp);
     s->wcnt = (lid_t*)(base + o_wcnt);
-    s->wsl = (lid_t*)(base + o_wsl);
     s->wgA = (lid_t*)(base + o_wgA);
     s->wgB = (lid_t*)(base + o_wgB);
     s->wmark = (uint32_t*)(base + o_wmark);
@@ -210,7 +208,7 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
 
 // misc[] slots
 enum { M_WSUM = 0 /* 0..63: two alternating banks of 32 warp sums */,
-       M_ERR = 65, M_PICK, M_CNT, M_TOT, M_NINT, M_SUBSET, M_DELTA, M_NLIVE, M_NBAL, M_TAILLEN, M_NV,
+       M_ERR = 65, M_PICK, M_CNT, M_TOT, M_NINT, M_SUBSET, M_DELTA, M_NLIVE, M_NBAL, M_TAILLEN, M_NV, M_WALKER /* thread that runs single-thread sections */,
        M_BEST64 = 80 /* 80..81, 8-byte aligned */, M_TICKET = 82 /* 82..85: two 8-byte slots */, M_CTR = 88 /* 88..95 counters */ };
 
 #ifdef __CUDACC__

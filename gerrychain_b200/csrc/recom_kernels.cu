@@ -463,11 +463,15 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
 // this is the tree - and the per-node draw counts - of the reference's sequential
 // loop-erased walks fed with the same stacks.  Short cycles (<= 4) are found by a local
 // look-ahead; what remains by pointer doubling over the functional graph.
+//
+// Draws are tabulated: wtab[u] is a ring of 8 successors, draws [hi - 8, hi) of node u at
+// slot (j & 7), filled four at a time (one Philox block) - the first 8 by everybody at the
+// start, the later ones by whoever consumes draw j == hi.  A pop is then one table look-up;
+// the generator runs once per four pops, off the pointer-chasing paths.
 constexpr int kLook = 2;  // nodes per thread whose look-ahead result is staged in registers
-constexpr int kLocalThreshold = 4;  // a local pass with fewer busy threads: try a global detection
-constexpr int kFullThreshold = 8;   // a global detection with fewer busy threads: finish sequentially
+constexpr int kHandoff = 2;  // default RcConfig.wilson_handoff (measured: the parallel passes beat the lone thread to the very end)
 constexpr int kMaxPasses = 4096;    // safety (disconnected input plans): then phase 3's budget applies
-constexpr int kTab = 8;  // draws per node precomputed for the sequential finish
+constexpr int kTab = 8;  // ring of tabulated draws per node
 constexpr uint32_t kInTree = 0xffffu;  // walk stamp of a node that leads to the root
 
 __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t prop_no, long long tree_idx,
@@ -487,46 +491,63 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     root = (int)rc_below(r.v[0], r.v[1], (uint32_t)n);
   }
   const int64_t* sp = replay ? p.rp.stack_ptr + tree_idx * ((long long)p.g.N + 1) : nullptr;
-  // take the next draw of node u (tree.py:119)
-  auto draw = [&](int u) {
-    const uint32_t j = s.wcnt[u];
-    s.wcnt[u] = (lid_t)(j + 1);
+  // replay: successor draw j of node u from the recorded stacks (tree.py:119)
+  auto recorded = [&](int u, uint32_t j) {
     const int r0 = s.loff[u], d = s.loff[u + 1] - r0;
-    if (replay) {
-      const int gu = c.nodes[u];
-      int slot = -1;
-      if (sp[gu] + (long long)j < sp[gu + 1]) {
-        const int gv = p.rp.stack_val[sp[gu] + j];
-        if (gv >= 0 && gv < p.g.N && is_member(s, gv)) {
-          const int lv = local_id(s, gv);
-          for (int q = 0; q < d; ++q) if (s.ladj[r0 + q] == lv) slot = r0 + q;
-        }
+    const int gu = c.nodes[u];
+    int nn = -1;
+    if (sp[gu] + (long long)j < sp[gu + 1]) {
+      const int gv = p.rp.stack_val[sp[gu] + j];
+      if (gv >= 0 && gv < p.g.N && is_member(s, gv)) {
+        const int lv = local_id(s, gv);
+        for (int q = 0; q < d; ++q) if (s.ladj[r0 + q] == lv) nn = lv;
       }
-      if (slot < 0) { s.misc[M_ERR] = RC_ERR_REPLAY; slot = r0; }
-      s.wsl[u] = (lid_t)slot;
-      s.wnx[u] = s.ladj[slot];
-    } else {
-      const RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WALK, (uint32_t)u, tree_no, prop_no, j >> 2);
-      const int slot = r0 + (int)rc_below32(r.v[j & 3u], (uint32_t)d);
-      s.wsl[u] = (lid_t)slot;
-      s.wnx[u] = s.ladj[slot];
     }
+    if (nn < 0) { s.misc[M_ERR] = RC_ERR_REPLAY; nn = s.ladj[r0]; }
+    return nn;
+  };
+  // free-running: draws 4b .. 4b + 3 of node u into their ring slots (one 64-bit store)
+  auto fill_block = [&](int u, uint32_t b) {
+    const int r0 = s.loff[u];
+    const uint32_t d = (uint32_t)(s.loff[u + 1] - r0);
+    const RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WALK, (uint32_t)u, tree_no, prop_no, b);
+    const uint32_t a0 = s.ladj[r0 + (int)rc_below32(r.v[0], d)], a1 = s.ladj[r0 + (int)rc_below32(r.v[1], d)];
+    const uint32_t a2 = s.ladj[r0 + (int)rc_below32(r.v[2], d)], a3 = s.ladj[r0 + (int)rc_below32(r.v[3], d)];
+    *reinterpret_cast<uint2*>(s.wtab + u * kTab + ((b & 1u) << 2)) = make_uint2(a0 | (a1 << 16), a2 | (a3 << 16));
+  };
+  // successor draw j of node u, for the thread that owns u's ring (phase 1: hi is implied,
+  // max(8, 4 * ceil(j / 4)): blocks beyond the first two are filled exactly when first needed)
+  auto next_draw = [&](int u, uint32_t j) {
+    if (replay) return recorded(u, j);
+    if (j >= (uint32_t)kTab && (j & 3u) == 0) fill_block(u, j >> 2);
+    return (int)s.wtab[u * kTab + (j & 7u)];
+  };
+  auto pop1 = [&](int u) {  // node u takes its next draw
+    const uint32_t j = s.wcnt[u];
+    s.wnx[u] = (lid_t)next_draw(u, j);
+    s.wcnt[u] = (lid_t)(j + 1);
   };
   auto succ_of = [&](int u) { return (int)s.wnx[u]; };  // wnx[root] == root
   if (tid == 0) s.misc[M_ERR] = 0;
   for (int u = tid; u < n; u += T) {
-    s.wcnt[u] = 0;
     if (u != root) {
-      if (s.loff[u + 1] == s.loff[u]) s.misc[M_ERR] = RC_ERR_DISCONNECTED; else draw(u);
+      if (s.loff[u + 1] == s.loff[u]) { s.misc[M_ERR] = RC_ERR_DISCONNECTED; continue; }
+      if (!replay) { fill_block(u, 0); fill_block(u, 1); }
+      s.wnx[u] = (lid_t)(replay ? recorded(u, 0) : (int)s.wtab[u * kTab]);
+      s.wcnt[u] = 1;
     } else {
       s.wnx[u] = (lid_t)u;
-      s.wsl[u] = 0;
+      s.wcnt[u] = 0;
     }
   }
   for (int i = tid; i < (m + 31) >> 5; i += T) s.tflag[i] = 0;
   for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
   __syncthreads();
   if (s.misc[M_ERR]) return s.misc[M_ERR];
+  // a local pass with fewer busy threads than kLocalThreshold: try a global detection;
+  // a global detection with fewer than kFullThreshold: finish sequentially
+  const int kLocalThreshold = p.cfg.wilson_handoff > 0 ? p.cfg.wilson_handoff : kHandoff;
+  const int kFullThreshold = 2 * kLocalThreshold;
   int walk = 0, passes = 0;
   // Phase 1 - while cycles are plentiful, pop them in parallel.  Local passes: u is on a
   // cycle of length <= 4 iff following the pointers brings it back to itself (early on about
@@ -557,9 +578,9 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
       __syncthreads();  // every pointer has been read
 #pragma unroll
       for (int k = 0; k < kLook; ++k)
-        if (on[k]) { draw(tid + k * T); ++popped; }
+        if (on[k]) { pop1(tid + k * T); ++popped; }
       for (int u = tid + kLook * T; u < n; u += T)
-        if ((s.wmark[u >> 5] >> (u & 31)) & 1u) { draw(u); ++popped; }
+        if ((s.wmark[u >> 5] >> (u & 31)) & 1u) { pop1(u); ++popped; }
       walk += popped;
       const int busy = __syncthreads_count(popped > 0);
       if (n > kLook * T) {
@@ -586,7 +607,7 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     __syncthreads();
     int popped = 0;
     for (int u = tid; u < n; u += T)
-      if ((s.wmark[u >> 5] >> (u & 31)) & 1u) { draw(u); ++popped; }
+      if ((s.wmark[u >> 5] >> (u & 31)) & 1u) { pop1(u); ++popped; }
     walk += popped;
     const int busy = __syncthreads_count(popped > 0);
     for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
@@ -605,85 +626,119 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     __syncthreads();
     lid_t* tmp = A; A = B; B = tmp;
   }
-  // ... and, for the sequential part, one packed state word per node - successor, walk
-  // stamp (kInTree: leads to the root), draws consumed, first tabulated draw - plus the next
-  // kTab successors of every node, computed by all threads (a draw is a pure function of
-  // (node, draw number)).  One 64-bit load per walk step, one 128-bit load per pop.
+  // ... and, for the sequential part, one packed state word per node - successor (bits
+  // 0-15), walk stamp (16-31; kInTree: leads to the root), draws consumed (32-47), end of the
+  // tabulated draws hi (48-63) - with every ring topped up to at least 5 unread draws by all
+  // threads.  One 64-bit load per walk step, one 16-bit look-up per pop.
   unsigned long long* __restrict__ wst = s.wst;
   for (int u = tid; u < n; u += T) {
-    const uint32_t j0 = s.wcnt[u];
+    const uint32_t cnt = s.wcnt[u];
+    uint32_t hi = cnt > (uint32_t)kTab ? ((cnt + 3u) & ~3u) : (uint32_t)kTab;
+    if (!replay && u != root)
+      while (hi - cnt <= 4u) { fill_block(u, hi >> 2); hi += 4u; }
     const uint32_t stamp = (int)A[u] == root ? kInTree : 0u;
     wst[u] = (unsigned long long)s.wnx[u] | ((unsigned long long)stamp << 16) |
-             ((unsigned long long)j0 << 32) | ((unsigned long long)j0 << 48);
-    if (!replay && u != root) {
-      const int r0 = s.loff[u];
-      const uint32_t d = (uint32_t)(s.loff[u + 1] - r0);
-      RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WALK, (uint32_t)u, tree_no, prop_no, j0 >> 2);
-#pragma unroll
-      for (int q = 0; q < kTab; ++q) {
-        const uint32_t j = j0 + q;
-        if (q && (j & 3u) == 0) r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WALK, (uint32_t)u, tree_no, prop_no, j >> 2);
-        s.wtab[u * kTab + q] = s.ladj[r0 + (int)rc_below32(r.v[j & 3u], d)];
-      }
-    }
+             ((unsigned long long)cnt << 32) | ((unsigned long long)hi << 48);
   }
   __syncthreads();
   RC_PH(PH_W2);
   // Phase 3 - the remaining cycles hang on a handful of components that pop one after the
   // other (the long tail of Wilson's algorithm is sequential): one thread finishes them as
-  // loop-erased walks over the current pointers, drawing only where a loop closes.
-  if (tid == 0) {
-    auto nx_of = [](unsigned long long w) { return (int)(w & 0xffffu); };
-    auto stamp_of = [](unsigned long long w) { return (uint32_t)(w >> 16) & 0xffffu; };
-    auto pop = [&](int v, unsigned long long w) {  // node v takes its next draw; returns new word
-      const uint32_t cnt = (uint32_t)(w >> 32) & 0xffffu, base = (uint32_t)(w >> 48);
-      const uint32_t q = cnt - base;
-      int nn;
-      if (!replay && q < (uint32_t)kTab) {
-        nn = s.wtab[v * kTab + q];
-      } else {
-        s.wcnt[v] = (lid_t)cnt;
-        draw(v);
-        nn = s.wnx[v];
-      }
-      return (unsigned long long)nn | ((unsigned long long)((cnt + 1) & 0xffffu) << 32) |
-             ((unsigned long long)base << 48);  // stamp cleared
-    };
-    // a connected pair needs ~10-20 draws per node; a walk that cannot reach the root
-    // (disconnected input plan) is cut off instead of spinning for ever
-    const long long budget = 2048ll * n + 65536;
-    long long spent = 0;
-    for (int node = 0; node < n && spent <= budget; ++node) {
-      if (stamp_of(wst[node]) == kInTree) continue;
-      const uint32_t id = (uint32_t)(node % 0xfffe) + 1u;  // 1..0xfffe, never kInTree
-      int u = node;
-      for (;;) {
-        unsigned long long w = wst[u];
-        const uint32_t sp_ = stamp_of(w);
-        if (sp_ == kInTree || spent > budget) break;
-        if (sp_ == id) {  // the walk closed a loop at u: pop it
-          int v = u;
-          do {
-            const unsigned long long wv = wst[v];
-            wst[v] = pop(v, wv);
-            ++walk;
-            v = nx_of(wv);
-          } while (v != u);
-          w = wst[u];
+  // loop-erased walks over the current pointers, drawing only where a loop closes.  The
+  // loops are written for a lone thread: the next node's word is requested before the
+  // current one is dealt with, and only the half of a word that changes is stored.
+  if (tid == s.misc[M_WALKER]) {
+    // the walk proper, over accessors: M.ld(u) / M.st(u, w) the 64-bit word of node u,
+    // M.ldlo / M.stlo its low half (successor | stamp), M.tab(i) entry i of the draw rings
+    auto finish = [&](auto M) {
+      auto pop = [&](int v, unsigned long long w) {  // node v takes its next draw; returns new word
+        const uint32_t cnt = (uint32_t)(w >> 32) & 0xffffu;
+        uint32_t hi = (uint32_t)(w >> 48);
+        uint32_t nn;
+        if (replay) {
+          nn = (uint32_t)recorded(v, cnt);
+        } else {
+          if (cnt == hi) { fill_block(v, hi >> 2); hi += 4u; }
+          nn = M.tab(v * kTab + (int)(cnt & 7u));
         }
-        wst[u] = (w & ~0xffff0000ull) | ((unsigned long long)id << 16);
-        u = nx_of(w);
-        ++spent;
+        return (unsigned long long)nn | ((unsigned long long)((cnt + 1u) & 0xffffu) << 32) |
+               ((unsigned long long)(hi & 0xffffu) << 48);  // stamp cleared
+      };
+      // a connected pair needs ~10-20 draws per node; a walk that cannot reach the root
+      // (disconnected input plan) is cut off instead of spinning for ever
+      int left = 2048 * n + 65536;  // n < 65536
+      int pops = 0;
+      for (int node = 0; node < n && left >= 0; ++node) {
+        unsigned long long w = M.ld(node);
+        if ((((uint32_t)w) >> 16) == kInTree) continue;
+        const uint32_t id = (uint32_t)(node % 0xfffe) + 1u;  // 1..0xfffe, never kInTree
+        const uint32_t idbits = id << 16;
+        int u = node;
+        for (;;) {  // w == word of u, u does not lead to the root yet
+          uint32_t lo = (uint32_t)w;
+          if ((lo >> 16) == id) {  // the walk closed a loop at u: pop it
+            int v = u;
+            unsigned long long wv = w;
+            do {
+              const int vn = (int)((uint32_t)wv & 0xffffu);
+              const unsigned long long wn = M.ld(vn);
+              M.st(v, pop(v, wv));
+              ++pops;
+              v = vn;
+              wv = wn;
+            } while (v != u);
+            lo = M.ldlo(u);
+          }
+          const int un = (int)(lo & 0xffffu);
+          w = M.ld(un);
+          M.stlo(u, (lo & 0xffffu) | idbits);
+          u = un;
+          if (--left < 0 || (((uint32_t)w) >> 16) == kInTree) break;
+        }
+        if (left < 0) break;
+        for (u = node;;) {
+          const uint32_t lo = M.ldlo(u);
+          if ((lo >> 16) == kInTree) break;
+          M.stlo(u, lo | 0xffff0000u);
+          u = (int)(lo & 0xffffu);
+        }
       }
-      if (spent > budget) break;
-      for (u = node;;) {
-        const unsigned long long w = wst[u];
-        if (stamp_of(w) == kInTree) break;
-        wst[u] = w | 0xffff0000ull;
-        u = nx_of(w);
-      }
+      walk += pops;
+      if (left < 0 && !s.misc[M_ERR]) s.misc[M_ERR] = RC_ERR_DISCONNECTED;
+    };
+    if (__isShared(wst)) {
+      // shared-window offsets pinned in registers and explicit ld/st.shared: the loop must not
+      // re-derive the window address (a special-register read) in front of every load
+      struct Sh {
+        uint32_t w, t;
+        __device__ __forceinline__ unsigned long long ld(int u) const {
+          unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(w + 8u * (uint32_t)u) : "memory"); return v; }
+        __device__ __forceinline__ void st(int u, unsigned long long v) const {
+          asm volatile("st.shared.u64 [%0], %1;" :: "r"(w + 8u * (uint32_t)u), "l"(v) : "memory"); }
+        __device__ __forceinline__ uint32_t ldlo(int u) const {
+          uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(w + 8u * (uint32_t)u) : "memory"); return v; }
+        __device__ __forceinline__ void stlo(int u, uint32_t v) const {
+          asm volatile("st.shared.u32 [%0], %1;" :: "r"(w + 8u * (uint32_t)u), "r"(v) : "memory"); }
+        __device__ __forceinline__ uint32_t tab(int i) const {
+          uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(t + 2u * (uint32_t)i) : "memory"); return v; }
+      } M;
+      M.w = (uint32_t)__cvta_generic_to_shared(wst);
+      M.t = (uint32_t)__cvta_generic_to_shared(s.wtab);
+      asm volatile("" : "+r"(M.w), "+r"(M.t));
+      finish(M);
+    } else {  // spill mode: the arrays live in this CTA's global scratch
+      struct Gl {
+        unsigned long long* w; const lid_t* t;
+        __device__ __forceinline__ unsigned long long ld(int u) const { return w[u]; }
+        __device__ __forceinline__ void st(int u, unsigned long long v) const { w[u] = v; }
+        __device__ __forceinline__ uint32_t ldlo(int u) const { return reinterpret_cast<const uint32_t*>(w)[2 * u]; }
+        __device__ __forceinline__ void stlo(int u, uint32_t v) const { reinterpret_cast<uint32_t*>(w)[2 * u] = v; }
+        __device__ __forceinline__ uint32_t tab(int i) const { return t[i]; }
+      } M;
+      M.w = wst;
+      M.t = s.wtab;
+      finish(M);
     }
-    if (spent > budget && !s.misc[M_ERR]) s.misc[M_ERR] = RC_ERR_DISCONNECTED;
   }
   RC_PH(PH_W3);
   __syncthreads();
@@ -1335,6 +1390,16 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
 #endif
   int32_t* ctr = c.s.misc + M_CTR;  // [RC_N_COUNTERS]
   if (tid < RC_N_COUNTERS) ctr[tid] = 0;
+  if (tid == 0) {
+    // Long single-thread sections (Wilson's sequential tail) run in a different warp in each
+    // of the CTAs that share an SM: warp w issues from scheduler w % 4, and lone threads of
+    // co-resident CTAs that all sit in warp 0 would queue on one scheduler.
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const int slot = atomicAdd(p.sm_slots + (smid & 1023u), 1);
+    const int n_warps = (int)blockDim.x >> 5;
+    c.s.misc[M_WALKER] = 32 * (slot % (n_warps < 4 ? n_warps : 4));
+  }
   __syncthreads();
   const bool replay = p.rp.n_steps > 0;
   const long long n_chains = p.cfg.n_chains;

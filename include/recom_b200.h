@@ -111,7 +111,9 @@ typedef struct RcConfig {
   int32_t accept_rule;        /* RC_ACCEPT_*: MarkovChain(accept=)  chain.py:192        */
   int32_t proposal_kind;      /* RC_PROPOSAL_*                                          */
   int32_t rev_M;              /* reversible_recom(M=): bound on the number of balanced cuts */
-  int32_t reserved_;
+  int32_t wilson_handoff;     /* RC_TREE_WILSON tuning / test knob: hand the tree to the sequential
+                               * finish once a parallel pass pops cycles on fewer threads than this;
+                               * 0 = default (2: the parallel passes run to the end)              */
 } RcConfig;
 
 /* ---- chain state, resident in HBM, owned by the caller --------------------------- */

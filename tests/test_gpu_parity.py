@@ -45,12 +45,14 @@ def test_replay_bit_exact_with_reference(name):
                  eng.cut_mask.cpu().numpy(), eng.cut_count.cpu().numpy())
 
 
+@pytest.mark.parametrize("handoff", [0, 100000])
 @pytest.mark.parametrize("name", _golden.names("wilson"))
-def test_wilson_replay_bit_exact_with_reference(name):
+def test_wilson_replay_bit_exact_with_reference(name, handoff):
     """uniform_spanning_tree (tree.py:97-132): the reference's recorded per-node successor
     draws, replayed through the device's parallel cycle popping, give the reference's
-    assignment after every step."""
+    assignment after every step (handoff = 100000: through the sequential finish alone)."""
     g = _golden.load(name)
+    g.cfg.wilson_handoff = handoff
     eng = _engine(g.csr, g.cfg, g.init_assignment)
     trace, info = eng.replay(g.rec)
     assert (info[:, 3] == 0).all(), [_abi.STATUS_NAMES.get(int(x)) for x in info[:, 3]]
@@ -64,12 +66,17 @@ def test_wilson_replay_bit_exact_with_reference(name):
                  eng.cut_mask.cpu().numpy(), eng.cut_count.cpu().numpy())
 
 
+@pytest.mark.parametrize("handoff", [0, 16, 100000])
 @pytest.mark.parametrize("name", _golden.names("wilson"))
-def test_wilson_free_run_bit_exact_with_oracle(name):
+def test_wilson_free_run_bit_exact_with_oracle(name, handoff):
+    """handoff: parallel cycle popping to the end (default), an early hand-over to the
+    sequential finish, and (no parallel pass ever pops enough) the sequential finish alone -
+    the tree and the per-node draw counts are the same whatever the popping order."""
     g = _golden.load(name)
     cfg = g.cfg
     cfg.n_chains = 16
     cfg.seed = 4321
+    cfg.wilson_handoff = handoff
     eng = _free_run_vs_oracle(g.csr, g.init_assignment, cfg, 30)
     from oracle import oracle  # walk-step counts agree as well
 
@@ -77,8 +84,10 @@ def test_wilson_free_run_bit_exact_with_oracle(name):
     assert np.array_equal(eng.counters.cpu().numpy()[:, _abi.RC_CTR_WALK], ora.counters[:, _abi.RC_CTR_WALK])
 
 
-def test_wilson_free_run_config3():
-    csr, plan, cfg = workloads.config3(n_chains=16, seed=21, tree_kind=_abi.RC_TREE_WILSON)
+@pytest.mark.parametrize("handoff", [0, 32])
+def test_wilson_free_run_config3(handoff):
+    csr, plan, cfg = workloads.config3(n_chains=16, seed=21, tree_kind=_abi.RC_TREE_WILSON,
+                                       wilson_handoff=handoff)
     _free_run_vs_oracle(csr, plan, cfg, 10)
 
 
