@@ -461,18 +461,20 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
 // cycles are popped (every node on a cycle takes its next draw) until none is left.  The
 // popped cycles and the final tree do not depend on the popping order (Wilson 1996), so
 // this is the tree - and the per-node draw counts - of the reference's sequential
-// loop-erased walks fed with the same stacks.  Short cycles (<= 4) are found by a local
-// look-ahead; what remains by pointer doubling over the functional graph.
+// loop-erased walks fed with the same stacks.  Cycles of up to kHop nodes are found by a
+// look-ahead from the nodes whose pointer just changed; longer ones by pointer doubling
+// over the functional graph.
 //
 // Draws are tabulated: wtab[u] is a ring of 8 successors, draws [hi - 8, hi) of node u at
 // slot (j & 7), filled four at a time (one Philox block) - the first 8 by everybody at the
 // start, the later ones by whoever consumes draw j == hi.  A pop is then one table look-up;
 // the generator runs once per four pops, off the pointer-chasing paths.
-constexpr int kLook = 2;  // nodes per thread whose look-ahead result is staged in registers
-constexpr int kHandoff = 2;  // default RcConfig.wilson_handoff (measured: the parallel passes beat the lone thread to the very end)
+constexpr int kHop = 8;      // a worklist node looks this many pointers ahead for a cycle through itself
+constexpr int kHandoff = 1;  // default RcConfig.wilson_handoff (measured: the parallel rounds beat the lone thread to the very end)
 constexpr int kMaxPasses = 4096;    // safety (disconnected input plans): then phase 3's budget applies
 constexpr int kTab = 8;  // ring of tabulated draws per node
 constexpr uint32_t kInTree = 0xffffu;  // walk stamp of a node that leads to the root
+
 
 __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t prop_no, long long tree_idx,
                            int32_t* ctr) {
@@ -515,16 +517,19 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     const uint32_t a2 = s.ladj[r0 + (int)rc_below32(r.v[2], d)], a3 = s.ladj[r0 + (int)rc_below32(r.v[3], d)];
     *reinterpret_cast<uint2*>(s.wtab + u * kTab + ((b & 1u) << 2)) = make_uint2(a0 | (a1 << 16), a2 | (a3 << 16));
   };
-  // successor draw j of node u, for the thread that owns u's ring (phase 1: hi is implied,
-  // max(8, 4 * ceil(j / 4)): blocks beyond the first two are filled exactly when first needed)
-  auto next_draw = [&](int u, uint32_t j) {
-    if (replay) return recorded(u, j);
-    if (j >= (uint32_t)kTab && (j & 3u) == 0) fill_block(u, j >> 2);
-    return (int)s.wtab[u * kTab + (j & 7u)];
-  };
-  auto pop1 = [&](int u) {  // node u takes its next draw
+  // node u takes its next draw (one thread per node and round).  The end of the tabulated
+  // draws is implied in phase 1 - max(8, 4 * ceil(j / 4)): blocks beyond the first two are
+  // filled exactly when their first draw is taken
+  auto pop1 = [&](int u) {
     const uint32_t j = s.wcnt[u];
-    s.wnx[u] = (lid_t)next_draw(u, j);
+    int nn;
+    if (replay) {
+      nn = recorded(u, j);
+    } else {
+      if (j >= (uint32_t)kTab && (j & 3u) == 0) fill_block(u, j >> 2);
+      nn = s.wtab[u * kTab + (j & 7u)];
+    }
+    s.wnx[u] = (lid_t)nn;
     s.wcnt[u] = (lid_t)(j + 1);
   };
   auto succ_of = [&](int u) { return (int)s.wnx[u]; };  // wnx[root] == root
@@ -544,57 +549,71 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
   for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
   __syncthreads();
   if (s.misc[M_ERR]) return s.misc[M_ERR];
-  // a local pass with fewer busy threads than kLocalThreshold: try a global detection;
-  // a global detection with fewer than kFullThreshold: finish sequentially
+  // Phase 1 - pop cycles in parallel, driven by a worklist.  A cycle that was not there
+  // before must run through a node whose pointer just changed, so only the nodes popped in
+  // the previous round are examined: the thread that holds worklist entry u follows the
+  // pointers for up to kHop steps; if that leads back to u it has found a cycle (its members
+  // in registers).  Every worklist member of the cycle finds it; the one that first sets the
+  // bit of the cycle's lowest node pops it - all members take their next draw and form the
+  // next worklist.  Round one examines every node.  Work per round is O(popped), not O(n):
+  // late rounds keep a warp or two busy and leave the SM to the co-resident CTA.
+  //   When the worklist runs dry, what is left are cycles longer than kHop (or none): one
+  // global detection (pointer doubling: after >= n steps every node sits on a cycle or at the
+  // root, and every cycle node is somebody's landing point) pops them and refills the
+  // worklist.  A global detection that finds nothing ends the phase: the tree is complete.
+  // RcConfig.wilson_handoff > 1 ends it earlier (worklist / detection yield below the
+  // threshold) and leaves the rest to the sequential finish - kept as a tuning and test knob.
   const int kLocalThreshold = p.cfg.wilson_handoff > 0 ? p.cfg.wilson_handoff : kHandoff;
   const int kFullThreshold = 2 * kLocalThreshold;
   int walk = 0, passes = 0;
-  // Phase 1 - while cycles are plentiful, pop them in parallel.  Local passes: u is on a
-  // cycle of length <= 4 iff following the pointers brings it back to itself (early on about
-  // a third of all nodes sits on such a cycle).  When a local pass finds almost nothing, one
-  // global detection (pointer doubling: after >= n steps every node sits on a cycle or at the
-  // root, and every cycle node is somebody's landing point) pops the longer cycles as well.
-  // The loop ends when even that yields little: what is left is Wilson's sequential tail.
+  lid_t* __restrict__ P = s.wgA;  // worklists alias the pointer-doubling buffers (never live together)
+  lid_t* __restrict__ Q = s.wgB;
+  int32_t* const wq = s.misc + M_WQ;  // wq[0], wq[1]: length of the list being built, by round parity
+  for (int i = tid; i < n - 1; i += T) P[i] = (lid_t)(i + (i >= root));
+  if (tid == 0) { wq[0] = 0; wq[1] = 0; }
+  int np = n - 1, par = 0;
+  __syncthreads();
   for (;;) {
-    for (;;) {
-      bool on[kLook];
-      int popped = 0;
+    while (np >= kLocalThreshold && passes <= kMaxPasses) {
+      ++passes;
+      for (int i = tid; i < np; i += T) {
+        const int u = P[i];
+        lid_t mem[kHop];
+        int L = 0, v = u;
+        uint32_t mn = (uint32_t)u;
 #pragma unroll
-      for (int k = 0; k < kLook; ++k) {
-        const int u = tid + k * T;
-        on[k] = false;
-        if (u < n && u != root) {
-          const int v1 = succ_of(u), v2 = succ_of(v1);
-          bool hit = v2 == u;
-          if (!hit) { const int v3 = succ_of(v2); hit = v3 == u || succ_of(v3) == u; }
-          on[k] = hit;
+        for (int h = 0; h < kHop; ++h) {
+          mem[h] = (lid_t)v;
+          v = succ_of(v);
+          if (v == u) { L = h + 1; break; }
+          if (v == root) break;
+          mn = min(mn, (uint32_t)v);
+        }
+        if (L && !((atomicOr(&s.wmark[mn >> 5], 1u << (mn & 31u)) >> (mn & 31u)) & 1u)) {
+          // this thread owns the cycle: its members are the next worklist
+          const int slot = atomicAdd(&wq[par], L);
+#pragma unroll
+          for (int h = 0; h < kHop; ++h) if (h < L) Q[slot + h] = mem[h];
         }
       }
-      for (int u = tid + kLook * T; u < n; u += T) {  // merged pairs larger than kLook * T nodes
-        if (u == root) continue;
-        const int v1 = succ_of(u), v2 = succ_of(v1), v3 = succ_of(v2);
-        if (v2 == u || v3 == u || succ_of(v3) == u) atomicOr(&s.wmark[u >> 5], 1u << (u & 31));
-      }
-      __syncthreads();  // every pointer has been read
-#pragma unroll
-      for (int k = 0; k < kLook; ++k)
-        if (on[k]) { pop1(tid + k * T); ++popped; }
-      for (int u = tid + kLook * T; u < n; u += T)
-        if ((s.wmark[u >> 5] >> (u & 31)) & 1u) { pop1(u); ++popped; }
-      walk += popped;
-      const int busy = __syncthreads_count(popped > 0);
-      if (n > kLook * T) {
-        for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
-        __syncthreads();
-      }
-      if (busy < kLocalThreshold || ++passes > kMaxPasses) break;
+      __syncthreads();  // every pointer has been read; Q is complete (a cycle's nodes appear once)
+      const int nq = wq[par];
+      for (int i = tid; i < nq; i += T) { pop1(Q[i]); ++walk; }
+      for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;  // the owners' marks
+      if (tid == 0) wq[par ^ 1] = 0;  // the next round's counter: everybody has read it by now
+      __syncthreads();
+      np = nq;
+      par ^= 1;
+      lid_t* t_ = P; P = Q; Q = t_;
     }
     if (passes > kMaxPasses) break;
-    // global detection
-    for (int u = tid; u < n; u += T) s.wgA[u] = (lid_t)succ_of(u);
-    __syncthreads();
+    ++passes;
+    // global detection (the worklist is dead: P and Q are free)
     lid_t* __restrict__ A = s.wgA;
     lid_t* __restrict__ B = s.wgB;
+    for (int u = tid; u < n; u += T) A[u] = (lid_t)succ_of(u);
+    __syncthreads();
+    if (tid == 0) wq[par ^ 1] = 0;
     for (int span = 1; span < n; span <<= 1) {
       for (int u = tid; u < n; u += T) B[u] = A[A[u]];
       __syncthreads();
@@ -604,15 +623,28 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
       const int v = A[u];
       if (v != root) atomicOr(&s.wmark[v >> 5], 1u << (v & 31));
     }
+    __syncthreads();  // A and B are dead from here on
+    P = s.wgA;
+    Q = s.wgB;
+    for (int u0 = 0; u0 < n; u0 += T) {
+      const int u = u0 + tid;
+      const bool hit = u < n && ((s.wmark[u >> 5] >> (u & 31)) & 1u);
+      if (hit) { pop1(u); ++walk; }
+      // warp-aggregated append to the worklist
+      const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+      if (bal) {
+        int slot = 0;
+        if ((tid & 31) == 0) slot = atomicAdd(&wq[par], __popc(bal));
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (hit) P[slot + __popc(bal & ((1u << (tid & 31)) - 1u))] = (lid_t)u;
+      }
+    }
     __syncthreads();
-    int popped = 0;
-    for (int u = tid; u < n; u += T)
-      if ((s.wmark[u >> 5] >> (u & 31)) & 1u) { pop1(u); ++popped; }
-    walk += popped;
-    const int busy = __syncthreads_count(popped > 0);
+    np = wq[par];
+    par ^= 1;
     for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
     __syncthreads();
-    if (busy < kFullThreshold || ++passes > kMaxPasses) break;
+    if (np < kFullThreshold) break;
   }
   RC_PH(PH_W1);
   // Phase 2 - which nodes already lead to the root?  After >= n steps of the functional
