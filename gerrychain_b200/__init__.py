@@ -18,6 +18,7 @@ from .constraints import Bounds, Validator, within_percent_of_ideal_population
 from .graph import Graph
 from .grid import Grid
 from .partition import Assignment, GeographicPartition, Partition
+from .record import Record, Replay
 from .proposals import MetagraphError, ReCom, ReversibilityError, recom, reversible_recom
 from .tree import BipartitionWarning, bipartition_tree
 from .updaters import Election, Tally, cut_edges, tally_region_splits
@@ -26,5 +27,5 @@ __all__ = [
     "MarkovChain", "BatchedMarkovChain", "ChainBatch", "Partition", "GeographicPartition", "Assignment",
     "Grid", "Graph", "recom", "reversible_recom", "ReversibilityError", "ReCom", "MetagraphError", "BipartitionWarning", "bipartition_tree",
     "within_percent_of_ideal_population", "Validator", "Bounds", "Tally", "cut_edges",
-    "Election", "tally_region_splits", "always_accept", "accept", "constraints", "proposals", "tree", "updaters",
+    "Election", "tally_region_splits", "Record", "Replay", "always_accept", "accept", "constraints", "proposals", "tree", "updaters",
 ]

@@ -355,3 +355,24 @@ def test_chain_batch_statistics():
         assert _contiguous(part)
         res = election(part)
         assert res.counts("A") == tuple(int(x) for x in votes[ch, 0])
+
+
+def test_record_and_replay_a_recom_chain(tmp_path):
+    """Record(chain, file) / Replay(graph, file, updaters) (reference
+    docs/topics/reproducibility.rst:21-60): the replayed run has the recorded assignments,
+    and its device-backed updaters give the recorded values."""
+    from gerrychain_b200 import Record, Replay
+
+    random.seed(12)
+    grid = Grid((10, 10))
+    proposal = functools.partial(recom, pop_col="population", pop_target=25, epsilon=0.2, node_repeats=1)
+    chain = MarkovChain(proposal, [within_percent_of_ideal_population(grid, 0.2)], always_accept, grid, total_steps=25)
+    path = str(tmp_path / "run.rcd")
+    seen = [(dict(s.assignment.mapping), set(s["cut_edges"]), dict(s["population"])) for s in Record(chain, path)]
+    assert len(seen) == 25
+    replayed = list(Replay(grid.graph, path, updaters=grid.updaters))
+    assert len(replayed) == 25
+    for (mapping, cuts, pops), state in zip(seen, replayed):
+        assert state.assignment.mapping == mapping
+        assert set(state["cut_edges"]) == cuts
+        assert dict(state["population"]) == pops

@@ -206,3 +206,44 @@ def test_graph_json_round_trip_feeds_the_csr_builder(tmp_path):
     island.add_edge(0, 1)
     with pytest.warns(UserWarning, match="islands"):
         gc.Graph.from_networkx(island).issue_warnings()
+
+
+def test_record_replay_round_trip(tmp_path):
+    """Record / Replay (reference docs/topics/reproducibility.rst:21-60): every recorded state
+    comes back with the same assignment, parts and flips; the file is a fraction of the
+    dense plans.  Host logic only - no device value is touched."""
+    import random
+
+    import networkx
+
+    from gerrychain_b200 import Partition, Record, Replay
+
+    g = networkx.grid_2d_graph(12, 12)
+    rng = random.Random(3)
+    labels = ["north", "south", "east", "west"]
+    plan = {v: labels[(v[0] >= 6) * 2 + (v[1] >= 6)] for v in g.nodes}
+    states = [Partition(g, plan, {})]
+    for _ in range(40):
+        flips = {rng.choice(list(g.nodes)): rng.choice(labels) for _ in range(rng.randint(0, 30))}
+        states.append(states[-1].flip(flips))
+    path = str(tmp_path / "run.rcd")
+    passed = list(Record(iter(states), path))
+    assert passed == states  # passed through untouched
+    replayed = list(Replay(g, path, updaters={}))
+    assert len(replayed) == len(states)
+    for a, b in zip(states, replayed):
+        assert a.assignment.mapping == b.assignment.mapping
+        assert a.parts == b.parts
+        assert isinstance(b, Partition) and len(b) == 4
+    for prev, cur in zip(replayed, replayed[1:]):
+        changed = {v: cur.assignment.mapping[v] for v in g.nodes if cur.assignment.mapping[v] != prev.assignment.mapping[v]}
+        assert cur.flips == changed
+    import os
+
+    assert os.path.getsize(path) < 0.2 * len(states) * 144
+    with pytest.raises(ValueError):
+        list(Replay(networkx.grid_2d_graph(3, 3), path))
+    bad = tmp_path / "bad.rcd"
+    bad.write_bytes(b"nope")
+    with pytest.raises(ValueError):
+        list(Replay(g, str(bad)))
