@@ -5,7 +5,7 @@
     python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (oracle port)
 
 One bench *step* = one pass of the hot path over the batch: every resident chain advances
-by ``--chain-steps`` (default 128) accepted ReCom steps (one launch of the chain-step kernel).  Workload:
+by ``--chain-steps`` (default 512) accepted ReCom steps (one launch of the chain-step kernel).  Workload:
 BASELINE.json configs[1] (Grid 100x100, 10 districts, eps 0.05, random_spanning_tree ReCom,
 1024 chains per GPU); ``--workload config3|config5|config1`` select the others.  Weak
 scaling: every rank owns ``--chains`` chains with distinct Philox subsequences; there is
@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config4", "config5"])
     ap.add_argument("--chains", type=int, default=1024, help="chains per GPU")
-    ap.add_argument("--chain-steps", type=int, default=128, help="ReCom steps per chain per bench step")
+    ap.add_argument("--chain-steps", type=int, default=512, help="ReCom steps per chain per bench step")
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
