@@ -209,7 +209,8 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
 // misc[] slots
 enum { M_WSUM = 0 /* 0..63: two alternating banks of 32 warp sums */,
        M_ERR = 65, M_PICK, M_CNT, M_TOT, M_NINT, M_SUBSET, M_DELTA, M_NLIVE, M_NBAL, M_TAILLEN, M_NV, M_WALKER /* thread that runs single-thread sections */, M_WQ /* 77..78: Wilson worklist lengths */,
-       M_BEST64 = 80 /* 80..81, 8-byte aligned */, M_TICKET = 82 /* 82..85: two 8-byte slots */, M_CTR = 88 /* 88..95 counters */ };
+       M_BEST64 = 80 /* 80..81, 8-byte aligned */, M_TICKET = 82 /* 82..85: two 8-byte slots */,
+       M_WBC = 86 /* 86..87: Wilson, what warp 0 hands back after a stretch of rounds on its own */, M_CTR = 88 /* 88..95 counters */ };
 
 #ifdef __CUDACC__
 

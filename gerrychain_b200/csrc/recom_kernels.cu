@@ -473,6 +473,8 @@ constexpr int kHop = 8;      // a worklist node looks this many pointers ahead f
 constexpr int kHandoff = 1;  // default RcConfig.wilson_handoff (measured: the parallel rounds beat the lone thread to the very end)
 constexpr int kMaxPasses = 4096;    // safety (disconnected input plans): then phase 3's budget applies
 constexpr int kTab = 8;  // ring of tabulated draws per node
+constexpr int kWarpRoundsEnter = 32;  // worklists this short are handled by warp 0 alone ...
+constexpr int kWarpRoundsExit = 64;   // ... until they outgrow this (multiple of 32)
 constexpr uint32_t kInTree = 0xffffu;  // walk stamp of a node that leads to the root
 
 
@@ -573,29 +575,75 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
   if (tid == 0) { wq[0] = 0; wq[1] = 0; }
   int np = n - 1, par = 0;
   __syncthreads();
+  // one worklist entry: look ahead from P[i]; the owner of a cycle appends its members to Q
+  // and returns the cycle's lowest node (whose mark it clears after the round), else kNoCycle
+  constexpr uint32_t kNoCycle = 0xffffffffu;
+  auto detect = [&](const lid_t* __restrict__ Pl, lid_t* __restrict__ Ql, int i, int parity) -> uint32_t {
+    const int u = Pl[i];
+    lid_t mem[kHop];
+    int L = 0, v = u;
+    uint32_t mn = (uint32_t)u;
+#pragma unroll
+    for (int h = 0; h < kHop; ++h) {
+      mem[h] = (lid_t)v;
+      v = succ_of(v);
+      if (v == u) { L = h + 1; break; }
+      if (v == root) break;
+      mn = min(mn, (uint32_t)v);
+    }
+    if (L && !((atomicOr(&s.wmark[mn >> 5], 1u << (mn & 31u)) >> (mn & 31u)) & 1u)) {
+      const int slot = atomicAdd(&wq[parity], L);
+#pragma unroll
+      for (int h = 0; h < kHop; ++h) if (h < L) Ql[slot + h] = mem[h];
+      return mn;
+    }
+    return kNoCycle;
+  };
+  int32_t* const wbc = s.misc + M_WBC;  // what warp 0 hands back to the block: np, rounds done
   for (;;) {
     while (np >= kLocalThreshold && passes <= kMaxPasses) {
-      ++passes;
-      for (int i = tid; i < np; i += T) {
-        const int u = P[i];
-        lid_t mem[kHop];
-        int L = 0, v = u;
-        uint32_t mn = (uint32_t)u;
+      if (np <= kWarpRoundsEnter) {
+        // Short worklists (nearly every round after the first few): warp 0 runs the rounds on
+        // its own, separated by __syncwarp() instead of block barriers, while the other warps
+        // wait at ONE barrier for the whole stretch and issue nothing.  It hands the block back
+        // a worklist that outgrew it (a popped cycle can be longer than the list that found it)
+        // or ran dry.
+        if (tid < 32) {
+          int rounds = 0;
+          int npw = np, parw = par;
+          lid_t* Pw = P; lid_t* Qw = Q;
+          while (npw >= kLocalThreshold && npw <= kWarpRoundsExit && passes + rounds <= kMaxPasses) {
+            ++rounds;
+            uint32_t own[kWarpRoundsExit / 32];
 #pragma unroll
-        for (int h = 0; h < kHop; ++h) {
-          mem[h] = (lid_t)v;
-          v = succ_of(v);
-          if (v == u) { L = h + 1; break; }
-          if (v == root) break;
-          mn = min(mn, (uint32_t)v);
-        }
-        if (L && !((atomicOr(&s.wmark[mn >> 5], 1u << (mn & 31u)) >> (mn & 31u)) & 1u)) {
-          // this thread owns the cycle: its members are the next worklist
-          const int slot = atomicAdd(&wq[par], L);
+            for (int r = 0; r < kWarpRoundsExit / 32; ++r) {
+              const int i = r * 32 + tid;
+              own[r] = i < npw ? detect(Pw, Qw, i, parw) : kNoCycle;
+            }
+            __syncwarp();
+            const int nq = *(volatile int32_t*)&wq[parw];
+            for (int i = tid; i < nq; i += 32) { pop1(Qw[i]); ++walk; }
 #pragma unroll
-          for (int h = 0; h < kHop; ++h) if (h < L) Q[slot + h] = mem[h];
+            for (int r = 0; r < kWarpRoundsExit / 32; ++r)
+              if (own[r] != kNoCycle) atomicAnd(&s.wmark[own[r] >> 5], ~(1u << (own[r] & 31u)));
+            if (tid == 0) wq[parw ^ 1] = 0;
+            __syncwarp();
+            npw = nq;
+            parw ^= 1;
+            lid_t* t_ = Pw; Pw = Qw; Qw = t_;
+          }
+          if (tid == 0) { wbc[0] = npw; wbc[1] = rounds; }
         }
+        __syncthreads();
+        const int rounds = wbc[1];
+        np = wbc[0];
+        passes += rounds;
+        if (rounds & 1) { par ^= 1; lid_t* t_ = P; P = Q; Q = t_; }
+        __syncthreads();  // wbc is rewritten only after everybody has read it
+        if (rounds > 0) continue;
       }
+      ++passes;
+      for (int i = tid; i < np; i += T) detect(P, Q, i, par);
       __syncthreads();  // every pointer has been read; Q is complete (a cycle's nodes appear once)
       const int nq = wq[par];
       for (int i = tid; i < nq; i += T) { pop1(Q[i]); ++walk; }
@@ -647,6 +695,10 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     if (np < kFullThreshold) break;
   }
   RC_PH(PH_W1);
+  // A global detection that found no cycle at all means the pointers ARE the tree (the
+  // normal end with the default hand-off threshold): phases 2-3 have nothing to do.
+  const bool complete = np == 0 && passes <= kMaxPasses;
+  if (!complete) {
   // Phase 2 - which nodes already lead to the root?  After >= n steps of the functional
   // graph every node sits on a cycle or at the root.
   for (int u = tid; u < n; u += T) s.wgA[u] = (lid_t)succ_of(u);
@@ -775,13 +827,13 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
   RC_PH(PH_W3);
   __syncthreads();
   if (s.misc[M_ERR]) return s.misc[M_ERR];
+  }  // !complete
   // the tree: edge (u, successor of u) for every node but the root; the slot of the
   // successor in u's row gives the edge
   for (int u = tid; u < n; u += T) {
     walk += (u != root);  // the first draw of every node
     if (u == root) continue;
-    const unsigned long long w = wst[u];
-    const int nn = (int)(w & 0xffffu);
+    const int nn = complete ? succ_of(u) : (int)(s.wst[u] & 0xffffu);
     int j = -1;
     for (int q = s.loff[u]; q < s.loff[u + 1]; ++q)
       if (s.ladj[q] == nn) { j = s.ladje[q]; break; }
