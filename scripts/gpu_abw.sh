@@ -14,9 +14,9 @@ print('$tag', '$BARGS', round(d['value']), 'e2e', round(d['e2e']['value']), 'cta
 }
 for tag in "$@"; do
 BARGS="--workload config3 --chain-steps 128 --steps 3"
-run $tag RECOM_B200_LIB=$PWD/variants/lib_$tag.so RECOM_B200_HOT=0
+run $tag RECOM_B200_LIB=$PWD/variants/lib_$tag.so
 BARGS="--workload config1 --chain-steps 128 --steps 5"
-run $tag RECOM_B200_LIB=$PWD/variants/lib_$tag.so RECOM_B200_HOT=0
+run $tag RECOM_B200_LIB=$PWD/variants/lib_$tag.so
 BARGS="--workload config4 --chain-steps 8 --steps 2"
-run $tag RECOM_B200_LIB=$PWD/variants/lib_$tag.so RECOM_B200_HOT=0
+run $tag RECOM_B200_LIB=$PWD/variants/lib_$tag.so
 done
