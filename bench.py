@@ -354,15 +354,17 @@ def run_b200(args):
     bytes_total = algorithmic_bytes(tot[_abi.RC_CTR_NODES], tot[_abi.RC_CTR_SLOTS], total_steps)
     # per GPU: bytes of this rank's launches / this rank's kernel time == total/world / kernel_ms
     achieved = bytes_total / world / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = on_chip = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and not args.wilson:
         try:
-            per_step = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_recom_step")
+            prof = json.load(open(tp)).get(args.workload, {})
+            per_step = prof.get("dram_bytes_per_recom_step")
             if per_step is not None:  # per launch, like `achieved`
                 traffic = per_step * total_steps / world / args.steps
+            on_chip = prof.get("on_chip")  # ncu counters of the same capture: what bounds the kernel
         except Exception:
-            traffic = None
+            traffic = on_chip = None
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src, "kernel": "rc::recom_step_kernel",
@@ -374,6 +376,7 @@ def run_b200(args):
         "boruvka_rounds_per_tree": tot[_abi.RC_CTR_ROUNDS] / max(tot[_abi.RC_CTR_TREES], 1),
         "mean_n_sub": tot[_abi.RC_CTR_NODES] / total_steps,
         "mean_d_sub": tot[_abi.RC_CTR_SLOTS] / total_steps,
+        "on_chip": on_chip,
     }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
