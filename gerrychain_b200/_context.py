@@ -53,6 +53,7 @@ class GraphContext:
         self._engines: Dict[Tuple, object] = {}
         self._edge_labels = None
         self._region_codes: Dict[str, Tuple[np.ndarray, int]] = {}
+        self._geometry = None
 
     @property
     def graph(self):
@@ -152,6 +153,30 @@ class GraphContext:
         eng.synchronize()
         return (eng.tally[0].cpu().numpy().copy(), eng.cut_mask[0].cpu().numpy().view(np.uint32).copy(),
                 int(eng.cut_count[0].item()))
+
+    def geometry(self):
+        """Flat copies of the geometric attributes the compactness updaters read
+        (updaters/compactness.py): per node ``boundary_node`` (bool) and ``boundary_perim``
+        (0 where absent), per edge of ``self.edges`` ``shared_perim``; plus whether every value
+        met was a Python int (the reference's ``sum`` then yields ints)."""
+        if self._geometry is None:
+            g = self.graph
+            on_boundary = np.fromiter((bool(g.nodes[lab].get("boundary_node", False)) for lab in self.labels),
+                                      dtype=bool, count=self.n_nodes)
+            seen = []
+            perim = np.zeros(self.n_nodes, dtype=np.float64)
+            for i in np.nonzero(on_boundary)[0].tolist():
+                value = g.nodes[self.labels[i]]["boundary_perim"]  # KeyError as in the reference
+                perim[i] = value
+                seen.append(value)
+            shared = np.empty(len(self.edges), dtype=np.float64)
+            for e, (u, v, data) in enumerate(g.edges(data=True)):
+                value = data["shared_perim"]
+                shared[e] = value
+                seen.append(value)
+            integral = all(isinstance(x, (int, np.integer)) and not isinstance(x, bool) for x in seen)
+            self._geometry = (on_boundary, perim, shared, integral)
+        return self._geometry
 
     def region_codes(self, reg_attr: str) -> Tuple[np.ndarray, int]:
         """Dense int32 code per node for the values of a node attribute.  ``None`` is a value

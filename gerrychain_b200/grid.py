@@ -5,9 +5,9 @@ API of the reference's ``Grid`` (/root/reference/gerrychain/grid.py:32-288): nod
 ``(i, j)`` tuples with ``population = 1`` / ``area = 1``, edges carry ``shared_perim``, the
 default plan is the four quadrants, ``as_list_of_lists()`` / ``str()`` render the plan.  The
 lattice itself comes from ``gerrychain_b200.synthetic.grid_graph``; rendering reads the dense
-district vector the engine works on instead of walking a dict.  The reference's geometric
-default updaters (perimeter, boundaries, polsby_popper) are downstream statistics outside the
-accelerated path; ``population``, ``area``, ``cut_edges`` and ``cut_edges_by_part`` are kept.
+district vector the engine works on instead of walking a dict.  The default updaters are the
+reference's: ``population`` / ``area`` / ``cut_edges`` come from the device, the geometric
+ones (perimeter, boundaries, ``polsby_popper``) are host statistics over the same vector.
 """
 
 from __future__ import annotations
@@ -18,7 +18,9 @@ import numpy as np
 
 from . import synthetic
 from .partition import Partition
-from .updaters import Tally, cut_edges, cut_edges_by_part
+from .metrics import polsby_popper
+from .updaters import (Tally, boundary_nodes, cut_edges, cut_edges_by_part, exterior_boundaries,
+                       interior_boundaries, perimeter)
 
 
 def create_grid_graph(dimensions: Tuple[int, int], with_diagonals: bool = False):
@@ -37,10 +39,15 @@ def color_quadrants(node: Tuple[int, int], thresholds: Tuple[int, int]) -> int:
 
 
 class Grid(Partition):
-    default_updaters = {
+    default_updaters = {  # grid.py:44-54
         "cut_edges": cut_edges,
         "population": Tally("population"),
+        "perimeter": perimeter,
+        "exterior_boundaries": exterior_boundaries,
+        "interior_boundaries": interior_boundaries,
+        "boundary_nodes": boundary_nodes,
         "area": Tally("area", alias="area"),
+        "polsby_popper": polsby_popper,
         "cut_edges_by_part": cut_edges_by_part,
     }
 

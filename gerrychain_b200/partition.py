@@ -20,7 +20,8 @@ from typing import Any, Callable, Dict, Optional, Tuple
 import numpy as np
 
 from ._context import GraphContext, context_of
-from .updaters import cut_edges
+from .updaters import (Tally, boundary_nodes, cut_edges, cut_edges_by_part, exterior_boundaries,
+                       interior_boundaries, perimeter)
 
 
 class Assignment(Mapping):
@@ -307,8 +308,17 @@ class Partition:
 
 
 class GeographicPartition(Partition):
-    """partition/geographic.py:13.  The geometric default updaters of the reference
-    (perimeter, area, boundaries) are downstream statistics outside the accelerated path
-    (SURVEY.md section 2); ``area`` is kept as a plain Tally when the graph carries it."""
+    """partition/geographic.py:13: a ``Partition`` with areas, perimeters and boundary
+    information, the inputs of compactness scores.  The geometric updaters are host
+    statistics over the dense district vector (``updaters.perimeter`` etc.); ``area`` is a
+    ``Tally`` like any other."""
 
-    default_updaters = {"cut_edges": cut_edges}
+    default_updaters = {
+        "perimeter": perimeter,
+        "exterior_boundaries": exterior_boundaries,
+        "interior_boundaries": interior_boundaries,
+        "boundary_nodes": boundary_nodes,
+        "cut_edges": cut_edges,
+        "area": Tally("area", alias="area"),
+        "cut_edges_by_part": cut_edges_by_part,
+    }

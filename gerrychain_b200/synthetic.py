@@ -23,11 +23,11 @@ def grid_graph(m: int, n: int, with_diagonals: bool = False) -> networkx.Graph:
         g.add_edges_from(diag, shared_perim=0)
     networkx.set_node_attributes(g, 1, "population")
     networkx.set_node_attributes(g, 1, "area")
-    for (i, j) in g.nodes:
-        on_edge = i in (0, m - 1) or j in (0, n - 1)
-        g.nodes[(i, j)]["boundary_node"] = on_edge
-        if on_edge:
-            g.nodes[(i, j)]["boundary_perim"] = 1
+    for (i, j) in g.nodes:  # grid.py:196-236: sides of the cell on the rim; corners have two
+        sides = int(i in (0, m - 1)) + int(j in (0, n - 1))
+        g.nodes[(i, j)]["boundary_node"] = sides > 0
+        if sides:
+            g.nodes[(i, j)]["boundary_perim"] = sides
     return g
 
 

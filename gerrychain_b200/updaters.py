@@ -1,5 +1,6 @@
 """Updaters of the ReCom path: ``Tally`` and ``cut_edges``, and the statistics users read
-behind every state: ``Election`` vote tallies and ``tally_region_splits``.
+behind every state: ``Election`` vote tallies, ``tally_region_splits`` and the compactness
+updaters of ``GeographicPartition`` (perimeter, boundaries).
 
 Reference: /root/reference/gerrychain/updaters/tally.py:69-170 and
 updaters/cut_edges.py:99-120.  The reference recomputes both incrementally on the host
@@ -49,6 +50,73 @@ def cut_edges_by_part(partition):
         out[mapping[e[0]]].add(e)
         out[mapping[e[1]]].add(e)
     return out
+
+
+# ---- compactness (updaters/compactness.py) -------------------------------------------------
+# Host-side statistics behind a state, computed with numpy from the dense district vector the
+# engine works on (no flows to replay: a ReCom child rewrites two whole districts).  They are
+# not on the accelerated path and touch neither the device nor the oracle.
+
+def _per_part(partition, totals, integral):
+    cast = (lambda x: int(round(x))) if integral else float
+    return {part: cast(t) for part, t in zip(partition._district_labels, totals)}
+
+
+def boundary_nodes(partition, alias: str = "boundary_nodes"):
+    """Nodes on the boundary of the whole graph (``boundary_node`` attribute;
+    updaters/compactness.py:8-25)."""
+    on_boundary = partition._ctx.geometry()[0]
+    labels = partition._ctx.labels
+    return {labels[i] for i in np.nonzero(on_boundary)[0].tolist()}
+
+
+def exterior_boundaries_as_a_set(partition):
+    """``{part: boundary nodes in it}`` (updaters/compactness.py:28-69)."""
+    on_boundary = partition._ctx.geometry()[0]
+    labels, dl, vec = partition._ctx.labels, partition._district_labels, partition._vec
+    out = {part: set() for part in dl}
+    for i in np.nonzero(on_boundary)[0].tolist():
+        out[dl[int(vec[i])]].add(labels[i])
+    return out
+
+
+def exterior_boundaries(partition):
+    """``{part: total boundary_perim of its boundary nodes}`` (updaters/compactness.py:72-121).
+    Every part has an entry (the reference's defaultdict answers 0 for the others)."""
+    on_boundary, perim, _, integral = partition._ctx.geometry()
+    k = len(partition._district_labels)
+    totals = np.bincount(partition._vec[on_boundary], weights=perim[on_boundary], minlength=k)
+    return _per_part(partition, totals, integral)
+
+
+def interior_boundaries(partition):
+    """``{part: total shared_perim of the cut edges touching it}``
+    (updaters/compactness.py:124-175)."""
+    _, _, shared, integral = partition._ctx.geometry()
+    edges, vec = partition._ctx.edges, partition._vec
+    k = len(partition._district_labels)
+    if len(edges) == 0:
+        return _per_part(partition, np.zeros(k), integral)
+    a, b = vec[edges[:, 0]], vec[edges[:, 1]]
+    cut = a != b
+    totals = (np.bincount(a[cut], weights=shared[cut], minlength=k)
+              + np.bincount(b[cut], weights=shared[cut], minlength=k))
+    return _per_part(partition, totals, integral)
+
+
+def perimeter_of_part(partition, part):
+    """updaters/compactness.py:190-211."""
+    return partition["exterior_boundaries"][part] + partition["interior_boundaries"][part]
+
+
+def perimeter(partition):
+    """``{part: exterior + interior boundary}`` (updaters/compactness.py:214-222)."""
+    return {part: perimeter_of_part(partition, part) for part in partition.parts}
+
+
+def flips(partition):
+    """updaters/compactness.py:178-187."""
+    return partition.flips
 
 
 def tally_region_splits(reg_attr_lst):
