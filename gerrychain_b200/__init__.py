@@ -11,7 +11,7 @@ a ctypes C ABI (include/recom_b200.h).  There is no CPU fallback: using the pack
 the built library or without a CUDA device raises.
 """
 
-from . import accept, constraints, proposals, tree, updaters  # noqa: F401
+from . import accept, constraints, metrics, proposals, tree, updaters  # noqa: F401
 from .accept import always_accept
 from .chain import BatchedMarkovChain, ChainBatch, MarkovChain
 from .constraints import Bounds, Validator, within_percent_of_ideal_population
@@ -27,5 +27,5 @@ __all__ = [
     "MarkovChain", "BatchedMarkovChain", "ChainBatch", "Partition", "GeographicPartition", "Assignment",
     "Grid", "Graph", "recom", "reversible_recom", "ReversibilityError", "ReCom", "MetagraphError", "BipartitionWarning", "bipartition_tree",
     "within_percent_of_ideal_population", "Validator", "Bounds", "Tally", "cut_edges",
-    "Election", "tally_region_splits", "Record", "Replay", "always_accept", "accept", "constraints", "proposals", "tree", "updaters",
+    "Election", "tally_region_splits", "Record", "Replay", "always_accept", "accept", "constraints", "metrics", "proposals", "tree", "updaters",
 ]

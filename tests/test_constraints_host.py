@@ -1,0 +1,84 @@
+"""Scalar bound wrappers, validity helpers and Polsby-Popper norms of ``constraints``
+(constraints/bounds.py:36-236, validity.py:125-186, constraints/compactness.py of the
+reference): known answers, including the reference's quirks (the ``>=`` in ``UpperBound``'s
+name, a falsy self-configured bound being configured again, the configuring call of
+``WithinPercentRangeOfBounds`` answering True).  Host logic only."""
+
+import math
+
+import pytest
+
+from gerrychain_b200 import constraints as C
+
+
+def score(x):
+    return x
+
+
+class FakePartition(dict):
+    def __init__(self, parent=None, parts=None, **updaters):
+        super().__init__(**updaters)
+        self.parent = parent
+        self.parts = parts or {}
+
+    @property
+    def assignment(self):
+        return self
+
+
+def test_upper_and_lower_bound():
+    up, low = C.UpperBound(score, 5), C.LowerBound(score, 5)
+    assert [up(4), up(5), up(5.1)] == [True, True, False]
+    assert [low(4.9), low(5), low(6)] == [False, True, True]
+    assert up.__name__ == "UpperBound(score >= 5)" and repr(up) == "<UpperBound(score >= 5)>"
+    assert low.__name__ == "LowerBound(score <= 5)"
+
+
+def test_self_configuring_bounds():
+    up = C.SelfConfiguringUpperBound(score)
+    assert [up(3), up(4), up(2), up(3)] == [True, False, True, True] and up.bound == 3
+    zero = C.SelfConfiguringUpperBound(score)
+    assert zero(0) and zero(7) and zero.bound == 7  # bound 0 is falsy: configured again (bounds.py:139-141)
+    low = C.SelfConfiguringLowerBound(score, epsilon=0.5)
+    assert [low(3), low(2.5), low(2.49)] == [True, True, False] and low.bound == 2.5
+    assert C.SelfConfiguringLowerBound(score).epsilon == 0.05
+    assert low.__name__ == "SelfConfiguringLowerBound(score)"
+
+
+def test_within_percent_range_of_bounds():
+    w = C.WithinPercentRangeOfBounds(score, 10)
+    assert w(100) is True  # the configuring call
+    assert (w.lbound, w.ubound) == (90.0, 110.00000000000001)
+    assert [w(109), w(111), w(90), w(89)] == [True, False, True, False]
+    assert w.__name__ == "WithinPercentRangeOfBounds(score)"
+
+
+def test_validator_accepts_the_wrappers_and_rejects_non_booleans():
+    v = C.Validator([C.UpperBound(score, 5), C.LowerBound(score, 1)])
+    assert v(3) is True and v(6) is False and v(0) is False
+    with pytest.raises(TypeError):
+        C.Validator([lambda p: 1])(3)
+
+
+def test_districts_within_tolerance_and_vanishing_districts():
+    p = FakePartition(population={0: 100, 1: 105, 2: 95})
+    assert C.districts_within_tolerance(p, "population", 0.11) is True  # 10 <= 0.11 * 95
+    assert C.districts_within_tolerance(p, "population", 0.1) is False
+    assert C.districts_within_tolerance(p, "population", 11) is True   # >= 1 is read as percent
+    assert C.districts_within_tolerance(p, "population", 10) is False
+    assert C.no_vanishing_districts(FakePartition(parts={0: set()})) is True  # no parent: nothing moved
+    child = FakePartition(parent=p, parts={0: {1, 2}, 1: set()})
+    assert C.no_vanishing_districts(child) is False
+    assert C.no_vanishing_districts(FakePartition(parent=p, parts={0: {1}, 1: {2}})) is True
+
+
+def test_polsby_popper_norms():
+    p = FakePartition(parts={0: {1}, 1: {2}, 2: {3}}, polsby_popper={0: 0.5, 1: 0.25, 2: 0.8})
+    assert C.L1_reciprocal_polsby_popper(p) == 2 + 4 + 1.25
+    assert math.isclose(C.L1_polsby_popper(p), 1.55, rel_tol=1e-15)
+    assert math.isclose(C.L2_polsby_popper(p), math.sqrt(0.25 + 0.0625 + 0.64), rel_tol=1e-15)
+    assert C.L_minus_1_polsby_popper(p) == 3 / 7.25
+    assert isinstance(C.no_worse_L1_reciprocal_polsby_popper, C.SelfConfiguringUpperBound)
+    assert isinstance(C.no_worse_L_minus_1_polsby_popper, C.SelfConfiguringLowerBound)
+    assert isinstance(C.no_more_discontiguous, C.SelfConfiguringLowerBound)
+    assert C.no_more_discontiguous.func is C.number_of_contiguous_parts
