@@ -235,3 +235,24 @@ class ElectionResults:
 
     def total_votes(self) -> int:
         return int(self._matrix.sum())
+
+    # partisan scores (updaters/election.py:369-422 -> metrics/partisan.py)
+    def mean_median(self) -> float:
+        from . import metrics
+        return metrics.mean_median(self)
+
+    def mean_thirdian(self) -> float:
+        from . import metrics
+        return metrics.mean_thirdian(self)
+
+    def efficiency_gap(self) -> float:
+        from . import metrics
+        return metrics.efficiency_gap(self)
+
+    def partisan_bias(self) -> float:
+        from . import metrics
+        return metrics.partisan_bias(self)
+
+    def partisan_gini(self) -> float:
+        from . import metrics
+        return metrics.partisan_gini(self)

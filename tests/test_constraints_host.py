@@ -82,3 +82,22 @@ def test_polsby_popper_norms():
     assert isinstance(C.no_worse_L_minus_1_polsby_popper, C.SelfConfiguringLowerBound)
     assert isinstance(C.no_more_discontiguous, C.SelfConfiguringLowerBound)
     assert C.no_more_discontiguous.func is C.number_of_contiguous_parts
+
+
+def test_partisan_scores_of_election_results():
+    """metrics/partisan.py through ElectionResults (updaters/election.py:369-422): a five-district
+    two-party election worked by hand - shares .60 .45 .30 .52 .48, mean .47, median .48."""
+    import numpy as np
+
+    from gerrychain_b200 import metrics
+    from gerrychain_b200.updaters import Election, ElectionResults
+
+    votes = np.array([[60, 45, 30, 52, 48], [40, 55, 70, 48, 52]])
+    res = ElectionResults(Election("SEN", {"A": "a", "B": "b"}), votes, list(range(5)))
+    assert math.isclose(res.mean_median(), 0.01, abs_tol=1e-15)
+    assert math.isclose(res.mean_thirdian(), 0.01, abs_tol=1e-15)  # sorted shares[round(5 / 3)] = .48
+    assert math.isclose(res.efficiency_gap(), -0.04, abs_tol=1e-15)  # (30 - 40 - 10 + 46 - 46) / 500
+    assert math.isclose(res.partisan_bias(), 0.1, abs_tol=1e-15)    # 3 of 5 districts above the mean
+    assert math.isclose(res.partisan_gini(), 0.032, abs_tol=1e-15)
+    assert metrics.wasted_votes(60, 40) == (10, 40) and metrics.wasted_votes(50, 50) == (50, 0)
+    assert res.wins("A") == res.seats("A") == 2 and res.votes("B") == res.counts("B") == (40, 55, 70, 48, 52)
