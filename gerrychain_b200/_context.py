@@ -54,6 +54,7 @@ class GraphContext:
         self._edge_labels = None
         self._region_codes: Dict[str, Tuple[np.ndarray, int]] = {}
         self._geometry = None
+        self._region_members: Dict[str, Tuple] = {}
 
     @property
     def graph(self):
@@ -189,6 +190,23 @@ class GraphContext:
                               dtype=np.int32, count=self.n_nodes)
             hit = (col, len(codes))
             self._region_codes[reg_attr] = hit
+        return hit
+
+    def region_members(self, reg_attr: str):
+        """(codes per node, values by code, node labels by code) of a node attribute: the
+        per-county node lists of ``county_splits`` (updaters/county_splits.py:75-90), shared by
+        every state of the graph."""
+        hit = self._region_members.get(reg_attr)
+        if hit is None:
+            col, n = self.region_codes(reg_attr)
+            g = self.graph
+            values = [None] * n
+            members = [[] for _ in range(n)]
+            for lab, code in zip(self.labels, col.tolist()):
+                values[code] = g.nodes[lab][reg_attr]
+                members[code].append(lab)
+            hit = (col, values, members)
+            self._region_members[reg_attr] = hit
         return hit
 
     def region_stats(self, vec: np.ndarray, reg_attr: str, k: int) -> Tuple[int, int, int]:

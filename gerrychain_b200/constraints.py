@@ -193,6 +193,17 @@ def districts_within_tolerance(partition, attribute_name: str = "population", pe
     return max(values) - smallest <= percentage * smallest
 
 
+def refuse_new_splits(partition_county_field: str) -> Callable:
+    """Reject a state that splits a county which was whole before; ``partition_county_field``
+    names a ``county_splits`` updater (validity.py:156-173)."""
+    from .updaters import CountySplit
+
+    def _refuse_new_splits(partition) -> bool:
+        return all(info.split != CountySplit.NEW_SPLIT for info in partition[partition_county_field].values())
+
+    return _refuse_new_splits
+
+
 def no_vanishing_districts(partition) -> bool:
     """No district may be emptied by a move (validity.py:176-186)."""
     if not partition.parent:

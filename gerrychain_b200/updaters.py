@@ -11,7 +11,9 @@ values in the reference's shapes (``{part: sum}`` and ``{(u, v), ...}``).
 
 from __future__ import annotations
 
+import collections
 import math
+from enum import Enum
 from typing import Dict, List, Optional, Type, Union
 
 import numpy as np
@@ -117,6 +119,53 @@ def perimeter(partition):
 def flips(partition):
     """updaters/compactness.py:178-187."""
     return partition.flips
+
+
+# ---- county splits (updaters/county_splits.py:1-117) -----------------------------------------
+CountyInfo = collections.namedtuple("CountyInfo", "split nodes contains")
+
+
+class CountySplit(Enum):
+    """Is a county in one district, split since the start, or split by this chain?"""
+
+    NOT_SPLIT = 0
+    NEW_SPLIT = 1
+    OLD_SPLIT = 2
+
+
+def county_splits(partition_name: str, county_field_name: str):
+    """Updater ``{county: CountyInfo(split, nodes, contains)}``; ``partition_name`` is the
+    key this updater is registered under (a child reads its parent's value through it)."""
+
+    def _get_county_splits(partition):
+        return compute_county_splits(partition, county_field_name, partition_name)
+
+    return _get_county_splits
+
+
+def compute_county_splits(partition, county_field: str, partition_field: str):
+    """Districts present in every county, from the dense plan: the distinct (county,
+    district) pairs.  Without a parent a county in several districts is an OLD_SPLIT; with one,
+    it is OLD_SPLIT only if the parent said so and a NEW_SPLIT otherwise
+    (updaters/county_splits.py:94-117)."""
+    codes, values, members = partition._ctx.region_members(county_field)
+    dl = partition._district_labels
+    k = len(dl)
+    pairs = np.unique(codes.astype(np.int64) * k + partition._vec)
+    contains = [set() for _ in values]
+    for pair in pairs.tolist():
+        contains[pair // k].add(dl[pair % k])
+    before = partition.parent[partition_field] if partition.parent else None
+    out = {}
+    for value, nodes, seen in zip(values, members, contains):
+        if len(seen) <= 1:
+            split = CountySplit.NOT_SPLIT
+        elif before is None or before[value].split == CountySplit.OLD_SPLIT:
+            split = CountySplit.OLD_SPLIT
+        else:
+            split = CountySplit.NEW_SPLIT
+        out[value] = CountyInfo(split, nodes, seen)
+    return out
 
 
 def tally_region_splits(reg_attr_lst):

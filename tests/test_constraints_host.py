@@ -101,3 +101,40 @@ def test_partisan_scores_of_election_results():
     assert math.isclose(res.partisan_gini(), 0.032, abs_tol=1e-15)
     assert metrics.wasted_votes(60, 40) == (10, 40) and metrics.wasted_votes(50, 50) == (50, 0)
     assert res.wins("A") == res.seats("A") == 2 and res.votes("B") == res.counts("B") == (40, 55, 70, 48, 52)
+
+
+def test_county_splits_and_refuse_new_splits():
+    """updaters/county_splits.py:58-117 and validity.py:156-173 on a 4 x 4 lattice whose
+    counties are the four quadrants: the start plan (left / right half) splits none of them; moving one
+    cell makes a NEW_SPLIT, which stays NEW in later states (the reference never ages it),
+    while a county split from the start is an OLD_SPLIT for good."""
+    import networkx as nx
+
+    from gerrychain_b200 import Partition
+    from gerrychain_b200.updaters import CountyInfo, CountySplit, county_splits
+
+    g = nx.grid_2d_graph(4, 4)
+    for (i, j) in g.nodes:
+        g.nodes[(i, j)]["county"] = "NSEW"[(i >= 2) + 2 * (j >= 2)]
+    ups = {"splits": county_splits("splits", "county")}
+    start = Partition(g, {v: int(v[0] >= 2) for v in g.nodes}, ups)
+    info = start["splits"]
+    assert set(info) == set("NSEW")
+    assert all(isinstance(x, CountyInfo) and x.split == CountySplit.NOT_SPLIT for x in info.values())
+    assert sorted(info["N"].nodes) == [(0, 0), (0, 1), (1, 0), (1, 1)] and info["N"].contains == {0}
+    assert C.refuse_new_splits("splits")(start) is True
+
+    child = start.flip({(1, 1): 1})
+    assert child["splits"]["N"].split == CountySplit.NEW_SPLIT and child["splits"]["N"].contains == {0, 1}
+    assert child["splits"]["S"].split == CountySplit.NOT_SPLIT
+    assert C.refuse_new_splits("splits")(child) is False
+    grandchild = child.flip({(0, 3): 1})
+    assert grandchild["splits"]["N"].split == CountySplit.NEW_SPLIT  # parent was NEW, not OLD
+    assert grandchild["splits"]["E"].split == CountySplit.NEW_SPLIT
+    healed = grandchild.flip({(1, 1): 0})
+    assert healed["splits"]["N"].split == CountySplit.NOT_SPLIT
+
+    rows = Partition(g, {v: int(v[1] >= 1) for v in g.nodes}, ups)  # cuts N and S from the start
+    assert rows["splits"]["N"].split == CountySplit.OLD_SPLIT and rows["splits"]["E"].split == CountySplit.NOT_SPLIT
+    assert rows.flip({(3, 3): 0})["splits"]["N"].split == CountySplit.OLD_SPLIT
+    assert C.refuse_new_splits("splits")(rows.flip({(0, 0): 1})) is True  # N stays an OLD split
