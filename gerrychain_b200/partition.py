@@ -202,6 +202,23 @@ class Partition:
                                 epsilon=epsilon)
         return cls(graph, assignment, updaters, use_default_updaters=use_default_updaters)
 
+    @classmethod
+    def from_districtr_file(cls, graph, districtr_file: str, updaters=None):
+        """partition.py:253-296: a plan exported from Districtr - ``assignment`` keyed by the
+        unit id found in the node attribute named by ``idColumn.key``."""
+        import json
+
+        with open(districtr_file) as handle:
+            exported = json.load(handle)
+        id_key = exported["idColumn"]["key"]
+        plan = exported["assignment"]
+        try:
+            unit_of = {node: str(graph.nodes[node][id_key]) for node in graph}
+        except KeyError:
+            raise TypeError(f"The provided graph is missing the {id_key} column, which is needed to "
+                            "match the Districtr assignment to the nodes of the graph.") from None
+        return cls(graph, {node: plan[unit_of[node]] for node in graph}, updaters)
+
     # -- reference surface -------------------------------------------------------------
     def __repr__(self):
         number_of_parts = len(self)

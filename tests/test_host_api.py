@@ -247,3 +247,23 @@ def test_record_replay_round_trip(tmp_path):
     bad.write_bytes(b"nope")
     with pytest.raises(ValueError):
         list(Replay(g, str(bad)))
+
+
+def test_partition_from_districtr_file(tmp_path):
+    """partition/partition.py:253-296: the plan is keyed by the unit id column."""
+    import json
+
+    import networkx as nx
+
+    from gerrychain_b200 import Partition
+
+    g = nx.path_graph(4)
+    for v in g.nodes:
+        g.nodes[v]["GEOID"] = 100 + v
+    path = tmp_path / "plan.json"
+    path.write_text(json.dumps({"idColumn": {"key": "GEOID"}, "assignment": {"100": 0, "101": 0, "102": 1, "103": 1}}))
+    p = Partition.from_districtr_file(g, str(path))
+    assert dict(p.assignment.items()) == {0: 0, 1: 0, 2: 1, 3: 1} and len(p) == 2
+    path.write_text(json.dumps({"idColumn": {"key": "missing"}, "assignment": {}}))
+    with pytest.raises(TypeError):
+        Partition.from_districtr_file(g, str(path))
