@@ -638,6 +638,7 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
         // wait at ONE barrier for the whole stretch and issue nothing.  It hands the block back
         // a worklist that outgrew it (a popped cycle can be longer than the list that found it)
         // or ran dry.
+        RC_PH(PH_W1);  // timers build: W1 = block-wide rounds, W2 / W3 = detect / pop of warp-0 rounds, slot 14 = global detections
         if (tid < 32) {
           int rounds = 0;
           int npw = np, parw = par;
@@ -651,6 +652,7 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
               own[r] = i < npw ? detect(Pw, Qw, i, parw) : kNoCycle;
             }
             __syncwarp();
+            RC_PH(PH_W2);
             const int nq = *(volatile int32_t*)&wq[parw];
             for (int i = tid; i < nq; i += 32) { pop1(Qw[i]); ++walk; }
 #pragma unroll
@@ -658,6 +660,7 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
               if (own[r] != kNoCycle) atomicAnd(&s.wmark[own[r] >> 5], ~(1u << (own[r] & 31u)));
             if (tid == 0) wq[parw ^ 1] = 0;
             __syncwarp();
+            RC_PH(PH_W3);
             npw = nq;
             parw ^= 1;
             lid_t* t_ = Pw; Pw = Qw; Qw = t_;
@@ -686,6 +689,7 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     }
     if (passes > kMaxPasses) break;
     ++passes;
+    RC_PH(PH_W1);
     // global detection (the worklist is dead: P and Q are free)
     lid_t* __restrict__ A = s.wgA;
     lid_t* __restrict__ B = s.wgB;
@@ -722,6 +726,7 @@ __device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     par ^= 1;
     for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
     __syncthreads();
+    RC_PH(PH_N);  // slot 14
     if (np < kFullThreshold) break;
   }
   RC_PH(PH_W1);
@@ -1619,7 +1624,7 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
   }
 #ifdef RC_TIMERS
   __syncthreads();
-  if (tid < PH_N) atomicAdd(p.timers + tid, reinterpret_cast<unsigned long long*>(c.s.misc + 96)[tid]);
+  if (tid <= PH_N) atomicAdd(p.timers + tid, reinterpret_cast<unsigned long long*>(c.s.misc + 96)[tid]);  // slots 0..14
 #endif
 }
 

@@ -30,7 +30,7 @@ ms = eng.last_run_ms()
 out = (C.c_ulonglong * 16)()
 eng.lib.rc_debug_phase_cycles.argtypes = [C.c_void_p, C.c_void_p]
 eng.lib.rc_debug_phase_cycles(eng._handle, out)
-names = ["to-pick", "pick", "gather", "tree", "euler", "balance", "choose", "commit", "flush+fence", "ticket+wait", "state loads", "wilson parallel pops", "wilson in-tree+table", "wilson sequential"]
+names = ["to-pick", "pick", "gather", "tree", "euler", "balance", "choose", "commit", "flush+fence", "ticket+wait", "state loads", "wilson block rounds+rest", "wilson warp-0 detect", "wilson warp-0 pop"]
 tot = sum(out[:14]) or 1
 info = eng.info()
 steps = a.chains * a.chain_steps
@@ -38,6 +38,6 @@ ctr = eng.counters.sum(0).cpu().numpy()
 print("  trees/step %.2f  walk draws/tree %.0f  mean n_sub %.0f" % (ctr[0] / max(eng.step_no.sum().item(), 1), ctr[6] / max(ctr[0], 1), ctr[2] / max(eng.step_no.sum().item(), 1)))
 print(f"{a.workload} wilson={a.wilson} chains={a.chains} steps/chain={a.chain_steps}: {ms:.2f} ms, "
       f"{steps / ms * 1e3:.0f} steps/s, smem {info.smem_bytes} B, ctas/sm {info.ctas_per_sm}, grid {info.grid}")
-names.append("slot14")
+names.append("wilson global detections" if a.wilson else "slot14")
 for n, v in zip(names, out[:15]):
     print(f"  {n:14s} {100 * v / tot:5.1f}%  {v / steps:12.0f} cycles/step (thread 0 of one CTA)")
