@@ -105,6 +105,27 @@ _CORE = ("graph", "updaters", "parent", "_flips", "_cache", "_ctx", "_vec", "_di
          "_rank", "_assignment", "_dev_tally", "_cut_mask", "_cut_count", "_pair")
 
 
+class _SubgraphView:
+    """Lazy ``part -> graph.subgraph(nodes of part)`` (partition/subgraphs.py:5-64)."""
+
+    def __init__(self, graph, parts):
+        self.graph, self.parts, self._built = graph, parts, {}
+
+    def __getitem__(self, part):
+        if part not in self._built:
+            self._built[part] = self.graph.subgraph(self.parts[part])
+        return self._built[part]
+
+    def __iter__(self):
+        return (self[part] for part in self.parts)
+
+    def items(self):
+        return ((part, self[part]) for part in self.parts)
+
+    def __repr__(self):
+        return f"<SubgraphView with {len(self.parts)} and {len(self._built)} cached graphs>"
+
+
 class Partition:
     """Partition of the nodes of a graph into districts (partition.py:12)."""
 
@@ -260,6 +281,11 @@ class Partition:
     @property
     def parts(self):
         return self.assignment.parts
+
+    @property
+    def subgraphs(self):
+        """``{part: induced subgraph}``, built on first use (partition/subgraphs.py)."""
+        return _SubgraphView(self.graph, self.parts)
 
     @property
     def flips(self):

@@ -121,6 +121,21 @@ def flips(partition):
     return partition.flips
 
 
+# ---- spanning-tree counts (updaters/spanning_trees.py) ---------------------------------------
+def num_spanning_trees(partition):
+    """``{part: number of spanning trees of the district's induced subgraph}`` by Kirchhoff's
+    theorem: exp(log |det|) of the Laplacian with one row and one column struck (the
+    reference strikes row 0 and column 1; every first minor has the same magnitude)."""
+    import networkx
+
+    out = {}
+    for part, sub in partition.subgraphs.items():
+        lap = networkx.laplacian_matrix(sub).toarray().astype(np.float64)
+        minor = np.delete(np.delete(lap, 0, 0), 1, 1)
+        out[part] = math.exp(np.linalg.slogdet(minor)[1])
+    return out
+
+
 # ---- county splits (updaters/county_splits.py:1-117) -----------------------------------------
 CountyInfo = collections.namedtuple("CountyInfo", "split nodes contains")
 

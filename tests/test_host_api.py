@@ -267,3 +267,21 @@ def test_partition_from_districtr_file(tmp_path):
     path.write_text(json.dumps({"idColumn": {"key": "missing"}, "assignment": {}}))
     with pytest.raises(TypeError):
         Partition.from_districtr_file(g, str(path))
+
+
+def test_subgraphs_and_num_spanning_trees():
+    """partition/subgraphs.py and updaters/spanning_trees.py: a 3 x 3 block of a lattice has
+    192 spanning trees, a 2 x 2 block 4, a path 1."""
+    import networkx as nx
+
+    from gerrychain_b200 import Partition
+    from gerrychain_b200.updaters import num_spanning_trees
+
+    g = nx.grid_2d_graph(3, 6)
+    plan = {(i, j): 0 if j < 3 else (1 if i < 2 and j < 5 else 2) for (i, j) in g.nodes}
+    p = Partition(g, plan, {"trees": num_spanning_trees})
+    assert set(p.subgraphs[1].nodes) == {(0, 3), (0, 4), (1, 3), (1, 4)}
+    assert sorted(len(sub) for sub in p.subgraphs) == [4, 5, 9]
+    counts = p["trees"]
+    assert round(counts[0]) == 192 and round(counts[1]) == 4 and round(counts[2]) == 1
+    assert abs(counts[0] - 192) < 1e-9
