@@ -121,13 +121,21 @@ def _recom_arguments(proposal):
 
 
 def _device_bounds(constraints, pop_col):
+    """(constraints, lower, upper): the population bounds the device enforces.  ``contiguous``
+    (the constraint of the reference's ReCom walkthrough) is accepted as well: both sides of
+    a tree cut are connected, so every ReCom child of a contiguous plan is contiguous and the
+    constraint only has to hold - and is checked - for the initial state."""
+    from .constraints import contiguous
+
     cons = constraints.constraints if isinstance(constraints, Validator) else (
         [constraints] if callable(constraints) else list(constraints))
     lower, upper = -np.inf, np.inf
     for c in cons:
+        if c is contiguous:  # == contiguous_bfs == single_flip_contiguous
+            continue
         if not isinstance(c, Bounds) or c.pop_key is None:
             raise TypeError(f"constraint {c!r} has no device implementation: BatchedMarkovChain takes "
-                            "within_percent_of_ideal_population(...) bounds only")
+                            "within_percent_of_ideal_population(...) bounds and contiguous only")
         lower, upper = max(lower, c.bounds[0]), min(upper, c.bounds[1])
     return cons, lower, upper
 
@@ -221,8 +229,12 @@ class BatchedMarkovChain:
          method) = _recom_arguments(proposal)
         cons, lower, upper = _device_bounds(constraints, self.pop_col)
         for c in cons:
-            if c.pop_key is not None and initial_state.updaters.get(c.pop_key) is None:
-                raise KeyError(c.pop_key)
+            key = getattr(c, "pop_key", None)
+            if key is not None and initial_state.updaters.get(key) is None:
+                raise KeyError(key)
+        if initial_assignments is not None and any(not isinstance(c, Bounds) for c in cons):
+            raise TypeError("contiguous is checked on initial_state only: with initial_assignments, verify the "
+                            "plans yourself (ChainBatch.contiguous()) and pass the population bounds alone")
         if not Validator(cons)(initial_state):
             failed = [c for c in cons if not c(initial_state)]
             raise ValueError("The given initial_state is not valid according is_valid. "

@@ -285,3 +285,20 @@ def test_subgraphs_and_num_spanning_trees():
     counts = p["trees"]
     assert round(counts[0]) == 192 and round(counts[1]) == 4 and round(counts[2]) == 1
     assert abs(counts[0] - 192) < 1e-9
+
+
+def test_batched_runner_accepts_population_bounds_and_contiguous_only():
+    """chain.py (batched runner): which constraints the device enforces."""
+    from gerrychain_b200 import constraints as C
+    from gerrychain_b200.chain import _device_bounds
+
+    b1 = C.Bounds(lambda p: p["population"].values(), (90.0, 110.0)); b1.pop_key = "population"
+    b2 = C.Bounds(lambda p: p["population"].values(), (95.0, 120.0)); b2.pop_key = "population"
+    cons, lo, hi = _device_bounds([b1, C.contiguous, b2, C.single_flip_contiguous], "population")
+    assert (lo, hi) == (95.0, 110.0) and len(cons) == 4
+    cons, lo, hi = _device_bounds(C.Validator([C.contiguous]), "population")
+    assert lo == -float("inf") and hi == float("inf")
+    with pytest.raises(TypeError):
+        _device_bounds([C.UpperBound(lambda p: 1, 2)], "population")
+    with pytest.raises(TypeError):
+        _device_bounds([C.Bounds(lambda p: [1], (0, 2))], "population")  # not a population bound
