@@ -136,6 +136,119 @@ def num_spanning_trees(partition):
     return out
 
 
+# ---- locality split scores (updaters/locality_split_scores.py) -------------------------------
+class LocalitySplits:
+    """``LocalitySplits(name, col_id, pop_col, scores_to_compute, pent_alpha)``: scores of how
+    a plan cuts localities (counties, municipalities).  All of them are functions of the
+    locality x district contingency table of the dense plan (node counts; populations for the
+    symmetric entropy), of the cut edges inside localities, or of the connected pieces left
+    when the graph is cut along both locality and district lines.  Calling it returns - and
+    stores in ``scores`` - ``{score name: value}`` for the names asked for, as in the
+    reference."""
+
+    KNOWN = ("num_parts", "num_pieces", "naked_boundary", "shannon_entropy", "power_entropy",
+             "symmetric_entropy", "num_split_localities")
+
+    def __init__(self, name: str, col_id: str, pop_col: str, scores_to_compute: List[str] = ["num_parts"],
+                 pent_alpha: float = 0.05):
+        self.name = name
+        self.col_id = col_id
+        self.pop_col = pop_col
+        self.pent_alpha = pent_alpha
+        self.localities = []
+        self.allowed_pieces = {}
+        self.scores = dict.fromkeys(scores_to_compute)
+
+    # -- tables ------------------------------------------------------------------------
+    def _table(self, partition, weights=None):
+        codes, values, _ = partition._ctx.region_members(self.col_id)
+        k = len(partition._district_labels)
+        flat = np.bincount(codes.astype(np.int64) * k + partition._vec, weights=weights, minlength=len(values) * k)
+        return flat.reshape(len(values), k)
+
+    def __call__(self, partition):
+        codes, values, _ = partition._ctx.region_members(self.col_id)
+        if not self.localities:
+            self.localities = set(values)
+        if not self.allowed_pieces:  # districts a locality must touch at least, by population
+            pop = partition._ctx.column(self.pop_col).astype(np.float64)
+            per_locality = np.bincount(codes, weights=pop, minlength=len(values))
+            ideal = pop.sum() / len(partition._district_labels)
+            self.allowed_pieces = {v: math.ceil(t / ideal) for v, t in zip(values, per_locality.tolist())}
+        for score in self.scores:
+            if score in self.KNOWN:
+                self.scores[score] = getattr(self, score)(partition)
+        return self.scores
+
+    # -- scores (locality_split_scores.py:200-431) ---------------------------------------
+    def num_parts(self, partition) -> int:
+        """Distinct (locality, district) pairs."""
+        return int(np.count_nonzero(self._table(partition)))
+
+    def num_split_localities(self, partition) -> int:
+        """Localities touching two or more districts."""
+        return int(np.count_nonzero(np.count_nonzero(self._table(partition), axis=1) > 1))
+
+    def naked_boundary(self, partition) -> int:
+        """Cut edges with both ends in one locality."""
+        codes = partition._ctx.region_members(self.col_id)[0]
+        edges, vec = partition._ctx.edges, partition._vec
+        if len(edges) == 0:
+            return 0
+        u, v = edges[:, 0], edges[:, 1]
+        return int(np.count_nonzero((vec[u] != vec[v]) & (codes[u] == codes[v])))
+
+    def num_pieces(self, partition) -> int:
+        """Connected pieces after cutting along locality AND district boundaries."""
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import connected_components
+
+        codes = partition._ctx.region_members(self.col_id)[0]
+        edges, vec = partition._ctx.edges, partition._vec
+        n = len(vec)
+        if len(edges):
+            u, v = edges[:, 0], edges[:, 1]
+            keep = (vec[u] == vec[v]) & (codes[u] == codes[v])
+            u, v = u[keep], v[keep]
+        else:
+            u = v = np.zeros(0, dtype=np.int64)
+        adj = coo_matrix((np.ones(len(u), dtype=np.int8), (u, v)), shape=(n, n))
+        return int(connected_components(adj, directed=False)[0])
+
+    def _entropy(self, partition, term):
+        table = self._table(partition)
+        total = table.sum()
+        out = 0.0
+        for row in table:
+            size = row.sum()
+            if size == 0:
+                continue
+            shares = row[row > 0] / size
+            out += term(size / total, shares)
+        return out
+
+    def shannon_entropy(self, partition) -> float:
+        """Sum over localities of (share of all nodes) x entropy of its split over districts."""
+        return float(self._entropy(partition, lambda q, p: q * float(np.sum(p * np.log(1.0 / p)))))
+
+    def power_entropy(self, partition) -> float:
+        """Sum over localities of (1 / share of all nodes) x (sum of shares^(1 - alpha) - 1)."""
+        a = self.pent_alpha
+        return float(self._entropy(partition, lambda q, p: (float(np.sum(p ** (1 - a))) - 1.0) / q))
+
+    def symmetric_entropy(self, partition) -> float:
+        """Population-weighted: sum over districts of total x sum sqrt(share of each locality),
+        plus the same with the roles of districts and localities exchanged."""
+        pop = partition._ctx.column(self.pop_col).astype(np.float64)
+        table = self._table(partition, weights=pop)
+        score = 0.0
+        for axis in (0, 1):  # columns = districts over localities, rows = localities over districts
+            totals = table.sum(axis=axis)
+            shares = table / (totals[None, :] if axis == 0 else totals[:, None])
+            score += float(np.sum(totals * np.sqrt(shares).sum(axis=axis)))
+        return score
+
+
 # ---- county splits (updaters/county_splits.py:1-117) -----------------------------------------
 CountyInfo = collections.namedtuple("CountyInfo", "split nodes contains")
 

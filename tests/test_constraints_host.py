@@ -138,3 +138,43 @@ def test_county_splits_and_refuse_new_splits():
     assert rows["splits"]["N"].split == CountySplit.OLD_SPLIT and rows["splits"]["E"].split == CountySplit.NOT_SPLIT
     assert rows.flip({(3, 3): 0})["splits"]["N"].split == CountySplit.OLD_SPLIT
     assert C.refuse_new_splits("splits")(rows.flip({(0, 0): 1})) is True  # N stays an OLD split
+
+
+def _three_by_three_with_counties():
+    import networkx as nx
+
+    g = nx.Graph()
+    g.add_edges_from([(0, 1), (0, 3), (1, 2), (1, 4), (2, 5), (3, 4), (3, 6), (4, 5), (4, 7), (5, 8), (6, 7), (7, 8)])
+    for v in g.nodes:
+        g.nodes[v]["county"] = "abc"[v // 3]
+        g.nodes[v]["pop"] = 1
+    return g
+
+
+ALL_SPLIT_SCORES = ["num_parts", "num_pieces", "naked_boundary", "shannon_entropy", "power_entropy",
+                    "symmetric_entropy", "num_split_localities"]
+
+
+def test_locality_splits_known_answers_of_the_reference():
+    """The reference's own cases (tests/updaters/test_split_scores.py:84-110): rows of a 3 x 3
+    lattice are the counties; districts = rows (nothing split) and districts = columns."""
+    from gerrychain_b200 import Partition
+    from gerrychain_b200.updaters import LocalitySplits
+
+    g = _three_by_three_with_counties()
+    ups = {"splits": LocalitySplits("splittings", "county", "pop", ALL_SPLIT_SCORES)}
+    rows = Partition(g, {v: 1 + v // 3 for v in g.nodes}, ups)
+    got = rows["splits"]
+    assert got is rows.updaters["splits"].scores
+    assert (got["num_parts"], got["num_pieces"], got["naked_boundary"], got["num_split_localities"]) == (3, 3, 0, 0)
+    assert got["shannon_entropy"] == 0 and got["power_entropy"] == 0 and got["symmetric_entropy"] == 18
+    assert rows.updaters["splits"].allowed_pieces == {"a": 1, "b": 1, "c": 1}
+
+    ups = {"splits": LocalitySplits("splittings", "county", "pop", ALL_SPLIT_SCORES)}
+    cols = Partition(g, {v: 1 + v % 3 for v in g.nodes}, ups)
+    got = dict(cols["splits"])
+    assert (got["num_parts"], got["num_pieces"], got["naked_boundary"], got["num_split_localities"]) == (9, 9, 6, 3)
+    assert math.isclose(got["shannon_entropy"], math.log(3), rel_tol=1e-12)          # 1 < . < 1.2 there
+    assert math.isclose(got["power_entropy"], 3 * 3 * (3 * (1 / 3) ** 0.95 - 1), rel_tol=1e-12)  # .5 < . < .6
+    assert math.isclose(got["symmetric_entropy"], 2 * 3 * 3 * 3 * math.sqrt(1 / 3), rel_tol=1e-12)  # 31 < . < 32
+    assert LocalitySplits("s", "county", "pop").scores == {"num_parts": None}
