@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import collections
 import math
+import warnings
 from enum import Enum
 from typing import Dict, List, Optional, Type, Union
 
@@ -36,6 +37,36 @@ class Tally:
     def __call__(self, partition):
         sums = partition._tally(tuple(self.fields))
         return {part: self.dtype(v) for part, v in zip(partition._district_labels, sums)}
+
+
+class DataTally:
+    """``DataTally(data, alias)`` - per-district sum of numbers that need not be node attributes
+    nor integers: a ``{node: value}`` mapping, a pandas Series indexed by node, or the name
+    of a node attribute (updaters/tally.py:12-66).  Summed on the host over the dense plan;
+    NaNs are skipped with the reference's warning."""
+
+    __slots__ = ["data", "alias", "_column"]
+
+    def __init__(self, data, alias: str) -> None:
+        self.data = data
+        self.alias = alias
+        self._column = None
+
+    def __call__(self, partition, previous=None):
+        ctx = partition._ctx
+        if self._column is None or len(self._column) != ctx.n_nodes:
+            if isinstance(self.data, str):
+                nodes, attribute = partition.graph.nodes, self.data
+                self.data = {node: nodes[node][attribute] for node in nodes}
+            self._column = np.array([self.data[lab] for lab in ctx.labels], dtype=np.float64)
+        col = self._column
+        bad = np.isnan(col)
+        for i in np.nonzero(bad)[0].tolist():
+            warnings.warn("ignoring nan encountered at node '{}' for attribute '{}'".format(ctx.labels[i], self.alias))
+        dl = partition._district_labels
+        sums = np.bincount(partition._vec[~bad], weights=col[~bad], minlength=len(dl))
+        integral = all(isinstance(self.data[lab], (int, np.integer)) for lab in ctx.labels)
+        return {part: (int(round(v)) if integral else float(v)) for part, v in zip(dl, sums.tolist())}
 
 
 def cut_edges(partition):

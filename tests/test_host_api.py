@@ -302,3 +302,28 @@ def test_batched_runner_accepts_population_bounds_and_contiguous_only():
         _device_bounds([C.UpperBound(lambda p: 1, 2)], "population")
     with pytest.raises(TypeError):
         _device_bounds([C.Bounds(lambda p: [1], (0, 2))], "population")  # not a population bound
+
+
+def test_data_tally_over_external_values():
+    """updaters/tally.py:12-66: values from a mapping, a Series or an attribute name; NaN
+    is skipped with a warning."""
+    import networkx as nx
+    import pandas
+
+    from gerrychain_b200 import Partition
+    from gerrychain_b200.updaters import DataTally
+
+    g = nx.path_graph(6)
+    for v in g.nodes:
+        g.nodes[v]["w"] = v * 0.5
+    plan = {v: v // 3 for v in g.nodes}
+    p = Partition(g, plan, {"ints": DataTally({v: v + 1 for v in g.nodes}, "ints"),
+                            "series": DataTally(pandas.Series({v: float(v) for v in g.nodes}), "series"),
+                            "attr": DataTally("w", "attr")})
+    assert p["ints"] == {0: 6, 1: 15} and all(isinstance(x, int) for x in p["ints"].values())
+    assert p["series"] == {0: 3.0, 1: 12.0}
+    assert p["attr"] == {0: 1.5, 1: 6.0}
+    assert p.flip({2: 1})["ints"] == {0: 3, 1: 18}
+    holes = Partition(g, plan, {"d": DataTally({v: (float("nan") if v == 4 else 1.0) for v in g.nodes}, "d")})
+    with pytest.warns(UserWarning, match="ignoring nan"):
+        assert holes["d"] == {0: 3.0, 1: 2.0}
