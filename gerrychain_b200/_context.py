@@ -10,12 +10,11 @@ from __future__ import annotations
 
 import random
 import weakref
-from typing import Dict, Hashable, Optional, Tuple
+from typing import Dict, Hashable, Tuple
 
 import numpy as np
 
-from . import _abi
-from .config import EngineConfig, cut_policy_for
+from .config import EngineConfig
 from .csr import GraphCSR, csr_from_edges
 
 _contexts: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()

@@ -15,7 +15,7 @@ wants flat arrays.  Conventions (DESIGN.md "Data layout"):
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Any, Dict, Hashable, Iterable, List, Mapping, Optional, Sequence
+from typing import Any, Dict, Hashable, List, Mapping, Optional, Sequence
 
 import numpy as np
 

@@ -8,7 +8,7 @@ fallback: constructing an ``Engine`` without the library or without a CUDA devic
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence
+from typing import Optional
 
 import numpy as np
 

@@ -15,7 +15,7 @@ exposes (``assignment.mapping``, ``parts``, ``flips``) are built lazily on first
 from __future__ import annotations
 
 from collections.abc import Mapping
-from typing import Any, Callable, Dict, Optional, Tuple
+from typing import Any, Dict, Optional, Tuple
 
 import numpy as np
 

@@ -45,9 +45,6 @@ def random_plans(graph, n_parts: int, epsilon: float, pop_col: str, n_plans: int
 
 def recursive_tree_part(graph, parts, pop_target, pop_col, epsilon, node_repeats=1, method=None):
     """tree.py:971-1085: ``{node: part}`` for ``len(parts)`` balanced, contiguous parts."""
-    from functools import partial as _partial
-
-    from . import tree
     from .proposals import method_config
 
     if node_repeats != 1:
