@@ -13,7 +13,7 @@ import numpy as np
 
 from . import synthetic as syn
 from .config import EngineConfig
-from .csr import GraphCSR, assignment_vector, csr_from_networkx
+from .csr import GraphCSR, assignment_vector, csr_from_edges, csr_from_networkx
 
 _GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -37,12 +37,22 @@ def grid_workload(m: int, n: int, k: int, eps: float, n_chains: int, **kw) -> Tu
 
 def delaunay_workload(n_nodes: int, k: int, eps: float, n_chains: int, counties: int = 0,
                       surcharge: float = 0.5, pop_range=(500, 2500), **kw):
-    g = syn.delaunay_graph(n_nodes, seed=0, pop_range=pop_range)
+    # same arrays as csr_from_networkx(syn.delaunay_graph(...)) (tests/test_host_api.py checks
+    # it), built from the edge list directly: a 200k-node networkx graph takes half a minute
+    rng, pts, e = syn.delaunay_points(n_nodes, seed=0)
+    pop = rng.integers(pop_range[0], pop_range[1], n_nodes)
+    csr = csr_from_edges(n_nodes, e, pop, node_labels=list(range(n_nodes)))
     regions = None
     if counties:
-        syn.voronoi_counties(g, counties, seed=1, key="county")
+        from scipy.spatial import cKDTree
+
+        centres = np.random.default_rng(1).random((counties, 2))  # syn.voronoi_counties(seed=1)
+        _, idx = cKDTree(centres).query(pts)
+        _, first = np.unique(idx, return_index=True)  # codes in order of first appearance
+        code = np.empty(counties, dtype=np.int32)
+        code[idx[np.sort(first)]] = np.arange(len(first), dtype=np.int32)
         regions = {"county": surcharge}
-    csr = csr_from_networkx(g, "population", regions)
+        csr = csr.with_regions(code[idx][None, :], [surcharge], ("county",))
     path = os.path.join(_GOLDEN, f"plan_delaunay{n_nodes}_k{k}.npy")
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path}: run oracle/make_seed_plans.py in the build container")

@@ -42,6 +42,16 @@ CASES = {
     # random planar graph with real-valued (integer) populations: 600-node Delaunay, 5 districts
     "delaunay600_mst": dict(graph="delaunay", n=600, k=5, eps=0.05, tree="mst", steps=60, chains=384),
     "grid12_reversible": dict(dims=(12, 12), eps=0.1, tree="wilson", steps=1500, chains=256, reversible_M=12),
+    # BASELINE configs 3 and 5 at their stated size: Delaunay 9k nodes, 18 districts, eps 0.02, the
+    # committed seed plan (tests/golden/plan_delaunay9000_k18.npy); config 5 adds 67 Voronoi
+    # counties with region_surcharge {"county": 0.5} (the reference's own region-aware pattern,
+    # /root/reference/tests/test_region_aware.py:82-99)
+    "delaunay9000_region": dict(graph="delaunay", n=9000, k=18, eps=0.02, tree="mst", steps=50, chains=256,
+                                region=True, counties=67, plan_file="plan_delaunay9000_k18.npy"),
+    "delaunay9000_mst": dict(graph="delaunay", n=9000, k=18, eps=0.02, tree="mst", steps=50, chains=256,
+                             plan_file="plan_delaunay9000_k18.npy"),
+    "delaunay9000_wilson": dict(graph="delaunay", n=9000, k=18, eps=0.02, tree="wilson", steps=50, chains=192,
+                                plan_file="plan_delaunay9000_k18.npy"),
 }
 
 
@@ -56,10 +66,16 @@ def _build(case):
         from gerrychain_b200 import synthetic as syn
 
         g = syn.delaunay_graph(case["n"], seed=0)
+        if case.get("counties"):
+            syn.voronoi_counties(g, case["counties"], seed=1, key="county")
         graph = Graph.from_networkx(g)
-        random.seed(12345)  # one fixed seed plan for every chain of the ensemble
-        tot = sum(g.nodes[v]["population"] for v in g)
-        plan = recursive_tree_part(graph, range(case["k"]), tot / case["k"], "population", case["eps"])
+        if case.get("plan_file"):
+            vec = np.load(os.path.join(GOLDEN, case["plan_file"]))
+            plan = {v: int(d) for v, d in zip(g.nodes, vec)}
+        else:
+            random.seed(12345)  # one fixed seed plan for every chain of the ensemble
+            tot = sum(g.nodes[v]["population"] for v in g)
+            plan = recursive_tree_part(graph, range(case["k"]), tot / case["k"], "population", case["eps"])
         part = Partition(graph, plan, {"population": Tally("population"), "cut_edges": cut_edges})
         return graph, part, plan
     m, n = case["dims"]

@@ -61,9 +61,26 @@ def names(kind=None):
 def load(name, inject_cut=True) -> Golden:
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     meta = json.loads(str(z["meta"]))
-    n_nodes = int(z["pop"].shape[0])
-    csr = csr_from_edges(n_nodes, z["edge_uv"], z["pop"])
-    assert np.array_equal(csr.edge_uv, z["edge_uv"])
+    if "graph" in meta:
+        # big fixtures name the generator call instead of storing the graph
+        # (oracle/record_config_size.py); the checksum pins what the recorder saw
+        import zlib
+
+        from gerrychain_b200 import synthetic
+
+        kind, n, gseed, lo, hi = meta["graph"]
+        assert kind == "delaunay"
+        rng, _, e = synthetic.delaunay_points(n, gseed)
+        pop = rng.integers(lo, hi, n).astype(np.int32)
+        csr = csr_from_edges(n, e.astype(np.int32), pop)
+        crc = zlib.crc32(np.ascontiguousarray(csr.pop, dtype=np.int32).tobytes(),
+                         zlib.crc32(np.ascontiguousarray(csr.edge_uv, dtype=np.int32).tobytes()))
+        assert crc == meta["graph_crc32"], "regenerated graph differs from the recorded one"
+        n_nodes = n
+    else:
+        n_nodes = int(z["pop"].shape[0])
+        csr = csr_from_edges(n_nodes, z["edge_uv"], z["pop"])
+        assert np.array_equal(csr.edge_uv, z["edge_uv"])
     regions = None
     if z["region_ids"].size:
         csr = csr.with_regions(z["region_ids"], z["surcharges"], meta["region_names"])

@@ -20,6 +20,10 @@ from gerrychain_b200.csr import csr_from_networkx
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ALPHA = 0.01
 CASES = ["grid20_mst", "grid20_wilson", "grid12_region", "grid20_cutaccept", "grid12_reversible", "delaunay600_mst"]
+# BASELINE configs 3 and 5 at their stated size (9k nodes, 18 districts, 67 counties): the
+# reference ensembles took ~10 core-minutes each; the oracle leg runs fewer chains to stay
+# within the CPU suite's budget, the engine leg runs 4096.
+CASES_9K = ["delaunay9000_region", "delaunay9000_mst", "delaunay9000_wilson"]
 
 
 def _case(name, n_chains, seed):
@@ -32,7 +36,10 @@ def _case(name, n_chains, seed):
         m, n = meta["dims"]
         g = synthetic.grid_graph(m, n)
     regions = None
-    if meta.get("region"):
+    if meta.get("counties"):
+        synthetic.voronoi_counties(g, meta["counties"], seed=1, key="county")
+        regions = {"county": 0.5}
+    elif meta.get("region"):
         for (i, j) in g.nodes:
             g.nodes[(i, j)]["county"] = (i // (m // 3)) * 3 + j // (n // 3)
         regions = {"county": 0.5}
@@ -51,11 +58,13 @@ def _case(name, n_chains, seed):
 
 
 def _county_splits(g, csr, assign, k):
-    county = np.array([g.nodes[v]["county"] for v in csr.node_labels])
+    """sum over districts of (distinct counties touched - 1), per chain."""
+    county = np.array([g.nodes[v]["county"] for v in csr.node_labels], dtype=np.int64)
+    nc = int(county.max()) + 1
     out = np.zeros(assign.shape[0], dtype=np.int64)
-    for d in range(k):
-        for c in range(assign.shape[0]):
-            out[c] += len(np.unique(county[assign[c] == d])) - 1
+    for c in range(assign.shape[0]):
+        pairs = np.unique(assign[c].astype(np.int64) * nc + county)
+        out[c] = len(pairs) - len(np.unique(pairs // nc))
     return out
 
 
@@ -85,12 +94,26 @@ def test_oracle_ensemble_matches_reference(name):
     _compare(z, meta, g, csr, cfg, ideal, ora.cut_count, ora.tally, ora.assignments())
 
 
+@pytest.mark.parametrize("name", CASES_9K)
+def test_oracle_ensemble_matches_reference_9k(name):
+    from oracle import oracle
+
+    z, meta, g, csr, cfg, ideal = _case(name, 512 if meta_tree(name) == "mst" else 256, seed=11)
+    ora = oracle.OracleChains(csr, cfg, z["plan"]).run(meta["steps"], n_threads=os.cpu_count() or 1)
+    assert (ora.status == 0).all()
+    _compare(z, meta, g, csr, cfg, ideal, ora.cut_count, ora.tally, ora.assignments())
+
+
+def meta_tree(name):
+    return "wilson" if "wilson" in name else "mst"
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + CASES_9K)
 def test_engine_ensemble_matches_reference(name):
     from gerrychain_b200.engine import Engine
 
-    z, meta, g, csr, cfg, ideal = _case(name, 4096, seed=12)
+    z, meta, g, csr, cfg, ideal = _case(name, 4096 if "wilson" not in name or "9000" not in name else 2048, seed=12)
     eng = Engine(csr, cfg, z["plan"])
     eng.run(meta["steps"]).synchronize()
     eng.check_status()
