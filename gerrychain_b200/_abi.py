@@ -104,7 +104,7 @@ class RcConfig(C.Structure):
         ("accept_rule", C.c_int32),
         ("proposal_kind", C.c_int32),
         ("rev_M", C.c_int32),
-        ("wilson_handoff", C.c_int32),
+        ("wilson_walkers", C.c_int32),
     ]
 
 
@@ -161,6 +161,8 @@ class RcEngineInfo(C.Structure):
         ("smem_bytes", C.c_int64),
         ("scratch_bytes", C.c_int64),
         ("kernel_launches", C.c_int64),
+        ("wilson_walkers", C.c_int32),
+        ("spill", C.c_int32),
     ]
 
 

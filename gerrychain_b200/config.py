@@ -36,7 +36,7 @@ class EngineConfig:
     accept_rule: int = _abi.RC_ACCEPT_ALWAYS
     proposal_kind: int = _abi.RC_PROPOSAL_RECOM
     rev_M: int = 1
-    wilson_handoff: int = 0  # Wilson: threads-with-a-pop below which the sequential finish takes over (0 = default)
+    wilson_walkers: int = 0  # Wilson: trees of one bipartition_tree call drawn concurrently, one walk per lane (0 = engine picks)
 
     def to_struct(self) -> _abi.RcConfig:
         c = _abi.RcConfig()
@@ -61,7 +61,7 @@ class EngineConfig:
         c.accept_rule = int(self.accept_rule)
         c.proposal_kind = int(self.proposal_kind)
         c.rev_M = int(self.rev_M)
-        c.wilson_handoff = int(self.wilson_handoff)
+        c.wilson_walkers = int(self.wilson_walkers)
         return c
 
 

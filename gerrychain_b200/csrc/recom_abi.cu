@@ -27,6 +27,17 @@ int fail(int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                  \
   } while (0)
 
+// inside rc_engine_create after the engine exists: free it before reporting the error
+#define CUDA_OK_E(call)                                                                 \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      rc_engine_destroy(e);                                                             \
+      return fail(RC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),  \
+                  __FILE__, __LINE__);                                                  \
+    }                                                                                   \
+  } while (0)
+
 template <typename T>
 int upload(const T* h, size_t n, T** d) {
   *d = nullptr;
@@ -43,7 +54,7 @@ struct RcEngine {
   rc::Params p{};
   bool bound = false;
   int grid = 0, threads = 0, ctas_per_sm = 0, n_sms = 0;
-  size_t smem = 0, scratch_bytes = 0, sched_bytes = 0, spill_bytes = 0;
+  size_t smem = 0, scratch_bytes = 0, sched_bytes = 0, spill_bytes = 0, cold_bytes = 0;
   bool spill = false;
   const void* kernel = nullptr;
   int64_t launches = 0;
@@ -55,6 +66,8 @@ struct RcEngine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
 };
+
+static int wilson_spill_level(const RcEngine* e) { return e->p.cfg.tree_kind == RC_TREE_WILSON ? e->p.wilson_level : (e->spill ? 2 : 0); }
 
 extern "C" {
 
@@ -138,20 +151,58 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   cap_edges = (cap_edges + 31) & ~31;
   p.cap_nodes = cap_nodes; p.cap_edges = cap_edges;
   const bool wilson = cfg->tree_kind == RC_TREE_WILSON;  // one kernel instantiation per tree kind
-  size_t split = 0;
-  const size_t total = rc::smem_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R, wilson, nullptr, &split);
   cudaDeviceProp prop;
-  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  CUDA_OK_E(cudaGetDeviceProperties(&prop, device));
   e->n_sms = prop.multiProcessorCount;
+  const size_t smem_max = (size_t)prop.sharedMemPerBlockOptin;
+  size_t split = 0, total = 0, cold = 0;
+  if (wilson) {
+    if (cfg->wilson_walkers < 0 || cfg->wilson_walkers > 8) {
+      rc_engine_destroy(e);
+      return fail(RC_ERR_INVALID_ARG, "wilson_walkers must be in [0, 8] (0 = automatic; one warp per walker)");
+    }
+    // Concurrent trees per chain-step.  Every walker is one more independent chain of
+    // dependent steps on the SM (the walks are latency bound), but a tree drawn beyond the
+    // first success is wasted, and each costs 4 B per node of shared memory: 4 is where
+    // trees in flight per SM x P(tree is needed) peaks for the BASELINE configurations
+    // (P(a tree has a balanced cut) ~ 0.25-0.5).  reversible_recom draws ONE tree per proposal.
+    // adjacency slots per node kept in the hot tier: enough for every node of a grid (4), else 8
+    // (a planar triangulation has mean degree < 6; longer rows are read from the cold tier)
+    int maxdeg = 0;
+    for (int v = 0; v < N; ++v) maxdeg = g->row_ptr[v + 1] - g->row_ptr[v] > maxdeg ? g->row_ptr[v + 1] - g->row_ptr[v] : maxdeg;
+    const int sh = maxdeg <= 4 ? 2 : 3;
+    p.nbr_shift = sh;
+    int W = cfg->wilson_walkers > 0 ? cfg->wilson_walkers : 4;
+    if (cfg->proposal_kind == RC_PROPOSAL_REVERSIBLE) W = 1;
+    // placement: everything in shared memory if it fits (with fewer walkers if need be); else
+    // the walkers' state in shared memory and the adjacency in L2; else both in L2
+    size_t glob = 0;
+    int level = 0;
+    for (;;) {
+      total = rc::wilson_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R, W, sh, level, nullptr, nullptr, &glob, &cold);
+      if (total <= smem_max) break;
+      if (cfg->wilson_walkers == 0 && W > 2 && level < 2) { W >>= 1; continue; }
+      if (level == 2) break;
+      ++level;
+      W = cfg->wilson_walkers > 0 ? cfg->wilson_walkers : (cfg->proposal_kind == RC_PROPOSAL_REVERSIBLE ? 1 : 4);
+    }
+    p.walkers = W;
+    p.wilson_level = level;
+    split = total;
+    total += glob;
+    e->cold_bytes = (cold + 255) & ~size_t(255);
+  } else {
+    total = rc::smem_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R, nullptr, &split);
+  }
   // a merged pair that does not fit an SM's shared memory keeps its working arrays in a
   // per-CTA global scratch block instead (L2 resident): same code, generic pointers
-  e->spill = total > (size_t)prop.sharedMemPerBlockOptin;
+  e->spill = wilson ? p.wilson_level > 0 : total > smem_max;
   e->smem = e->spill ? split : total;
   e->spill_bytes = e->spill ? ((total - split + 255) & ~size_t(255)) : 0;
-  if (e->smem > (size_t)prop.sharedMemPerBlockOptin) {
+  if (e->smem > smem_max) {
     rc_engine_destroy(e);
     return fail(RC_ERR_CAPACITY, "graph of %d nodes needs %zu B of shared memory for the membership bitmap (> %zu)",
-                N, e->smem, (size_t)prop.sharedMemPerBlockOptin);
+                N, e->smem, smem_max);
   }
   e->threads = cfg->threads_per_cta;
   if (e->threads == 0) {
@@ -159,7 +210,7 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
     // than more threads each (measured: Grid 20x20 runs 2.2x faster with 8 CTAs x 128 threads
     // than with 2 x 512).  About 4 edges per thread, at most 8 CTAs per SM, and no more
     // threads than the register file (64 regs x 1024 threads) leaves for that many CTAs.
-    e->threads = 512;
+    e->threads = wilson ? 256 : 512;
     if (!e->spill) {
       int c_smem = (int)((size_t)prop.sharedMemPerMultiprocessor / (e->smem + 1024));
       if (c_smem > 8) c_smem = 8;
@@ -168,21 +219,35 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
       int by_work = ((cap_edges / 4) + 31) / 32 * 32;
       int t = by_work < by_regs ? by_work : by_regs;
       if (t < 64) t = 64;
-      if (t > 512) t = 512;
+      if (t > (wilson ? 256 : 512)) t = wilson ? 256 : 512;
       e->threads = t;
     }
+    if (wilson && e->threads < 32 * p.walkers) e->threads = 32 * p.walkers;  // one warp per walker
   }
-  if (e->threads < 64 || e->threads > 512 || e->threads % 32) {
+  if (wilson && e->threads < 32 * p.walkers) {
     rc_engine_destroy(e);
-    return fail(RC_ERR_INVALID_ARG, "threads_per_cta must be a multiple of 32 in [64, 512] (0 = automatic)");
+    return fail(RC_ERR_INVALID_ARG, "threads_per_cta must be at least 32 x wilson_walkers (%d)", 32 * p.walkers);
   }
-  e->kernel = wilson ? (e->spill ? (const void*)rc::recom_step_kernel<true, true> : (const void*)rc::recom_step_kernel<true, false>)
+  if (e->threads < 64 || e->threads > (wilson ? 256 : 512) || e->threads % 32) {
+    rc_engine_destroy(e);
+    return fail(RC_ERR_INVALID_ARG, "threads_per_cta must be a multiple of 32 in [64, %d] (0 = automatic)", wilson ? 256 : 512);
+  }
+  e->kernel = wilson ? (const void*)rc::recom_step_kernel<true, false>  // the placement level is a run-time parameter
                      : (e->spill ? (const void*)rc::recom_step_kernel<false, true> : (const void*)rc::recom_step_kernel<false, false>);
-  CUDA_OK(cudaFuncSetAttribute(e->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->ctas_per_sm, e->kernel, e->threads, e->smem));
+  CUDA_OK_E(cudaFuncSetAttribute(e->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  CUDA_OK_E(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->ctas_per_sm, e->kernel, e->threads, e->smem));
   if (e->ctas_per_sm < 1) { rc_engine_destroy(e); return fail(RC_ERR_CAPACITY, "kernel does not fit an SM"); }
   // persistent grid: every CTA resident; they pop ready chains from a ring (recom_step_kernel)
   e->grid = e->ctas_per_sm * e->n_sms;
+  if (e->spill) {
+    // spill mode: every step of a walk is a round trip to the CTA's scratch block; keep the
+    // blocks of the resident CTAs inside L2 (126 MB) rather than have more CTAs wait on DRAM
+    const size_t per_cta = e->spill_bytes + e->cold_bytes + (size_t)(cap_nodes + cap_edges) * 4;
+    long long fit = (long long)((size_t)96 << 20) / (long long)(per_cta ? per_cta : 1);
+    fit = fit / e->n_sms * e->n_sms;
+    if (fit < e->n_sms) fit = e->n_sms;
+    if (e->grid > fit) e->grid = (int)fit;
+  }
   if (e->grid > cfg->n_chains) e->grid = cfg->n_chains;
   // scratch
   size_t b_nodes = (size_t)e->grid * cap_nodes * sizeof(int32_t);
@@ -192,8 +257,9 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   // pop/push indices, phase timers, progress words, ring of ready chains, CTAs counted per SM
   size_t b_prog = 512 + 2 * (size_t)cfg->n_chains * sizeof(int32_t) + 1024 * sizeof(int32_t);
   size_t b_spill = (size_t)e->grid * e->spill_bytes;
-  e->scratch_bytes = al(b_nodes) + al(b_eids) + al(b_bad) + al(b_prog) + al(b_spill);
-  CUDA_OK(cudaMalloc(&e->d_scratch, e->scratch_bytes));
+  size_t b_cold = (size_t)e->grid * e->cold_bytes;
+  e->scratch_bytes = al(b_nodes) + al(b_eids) + al(b_bad) + al(b_prog) + al(b_spill) + al(b_cold);
+  CUDA_OK_E(cudaMalloc(&e->d_scratch, e->scratch_bytes));
   char* base = (char*)e->d_scratch;
   p.nodes = (int32_t*)base; base += al(b_nodes);
   p.eids = (int32_t*)base; base += al(b_eids);
@@ -207,9 +273,12 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   base += al(b_prog);
   p.spill = b_spill ? (unsigned char*)base : nullptr;
   p.spill_stride = (int64_t)e->spill_bytes;
+  base += al(b_spill);
+  p.cold = b_cold ? (unsigned char*)base : nullptr;
+  p.cold_stride = (int64_t)e->cold_bytes;
   e->sched_bytes = b_prog;
-  CUDA_OK(cudaEventCreate(&e->ev0));
-  CUDA_OK(cudaEventCreate(&e->ev1));
+  CUDA_OK_E(cudaEventCreate(&e->ev0));
+  CUDA_OK_E(cudaEventCreate(&e->ev1));
   *out = e;
   return RC_OK;
 }
@@ -415,6 +484,7 @@ int rc_engine_info(RcEngine* e, RcEngineInfo* out) {
   out->threads_per_cta = e->threads; out->ctas_per_sm = e->ctas_per_sm; out->n_sms = e->n_sms;
   out->grid = e->grid; out->smem_bytes = (int64_t)e->smem; out->scratch_bytes = (int64_t)e->scratch_bytes;
   out->kernel_launches = e->launches;
+  out->wilson_walkers = e->p.walkers; out->spill = wilson_spill_level(e);
   return RC_OK;
 }
 

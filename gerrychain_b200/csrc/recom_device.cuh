@@ -50,6 +50,11 @@ struct Params {
   unsigned long long* timers;  // RC_TIMERS builds: cycles per phase (thread 0 of every CTA)
   unsigned char* spill;   // spill mode: [grid][spill_stride] working arrays in global memory
   int64_t spill_stride;
+  unsigned char* cold;    // Wilson: [grid][cold_stride] arrays only streamed through (pop, eu, ev, ecls)
+  int64_t cold_stride;
+  int32_t walkers;        // Wilson: spanning trees drawn concurrently per chain-step (lanes of one warp)
+  int32_t nbr_shift;      // Wilson: log2 of the adjacency slots per node kept in the hot tier
+  int32_t wilson_level;   // Wilson: 0 = state and adjacency in shared memory, 1 = adjacency in L2, 2 = both in L2
 };
 
 // ---- shared-memory carve-up -------------------------------------------------------
@@ -66,22 +71,22 @@ struct Smem {
   uint32_t* newb;    // [CN/32] the same after the proposed cut
   uint8_t* ecls;     // [CE] bitmask of region columns the edge crosses (R > 0 only)
   // Wilson only: adjacency of the merged pair, rows in ascending neighbour id
-  lid_t* loff;       // [CN+1]
-  lid_t* ladj;       // [2CE] neighbour (local id)
-  lid_t* ladje;      // [2CE] local edge index of that slot
+  uint32_t* nbr;     // [(CN + CN/8) << nbr_shift] rows of D = 1 << nbr_shift slots: row u < n belongs to
+                     // node u; an entry is a neighbour (bits 0-15) | degree OF THAT NEIGHBOUR << 16,
+                     // ascending; a node of degree > D keeps D - 1 entries and a link (slot D - 1) to
+                     // a spare row (index >= n) that holds the next ones, and so on
+  uint16_t* wdeg;    // [CN] degree inside the pair
   // spanning-tree phase
   uint32_t* key;     // [CE] 32-bit weight key of local edge j
   uint32_t* lab;     // [CE] live edge list: endpoints as current component ids (a | b << 16)
   lid_t* lj;         // [CE] live edge list: local edge index
-  // uniform-spanning-tree phase (Wilson; aliases the same region)
-  uint32_t* wtmp;    // [CN] row cursors while the adjacency is built
-  lid_t* wcnt;       // [CN] successor draws consumed by node u
-  lid_t* wgA;        // [CN] pointer doubling, ping
-  lid_t* wgB;        // [CN] pointer doubling, pong
-  uint32_t* wmark;   // [CN/32] nodes found on a cycle; later: nodes in the tree
-  lid_t* wnx;        // [CN] current successor of u (the root points at itself)
-  unsigned long long* wst;  // [CN] sequential finish: successor | stamp | draws consumed | end of tabulated draws
-  lid_t* wtab;       // [CN][8] ring of tabulated successor draws of u: draw j at slot j & 7
+  // uniform-spanning-tree phase (Wilson): one state word per node and walker, see wilson_walk
+  uint16_t* wst;     // [W][CN] successor (bits 0-14) | in the tree (15)
+  uint32_t* wtmp;    // [CN] scratch of the gather / adjacency build; aliases wsum
+  int32_t* wsum;     // [CN] population of the subtree below node u (tree being evaluated)
+  uint32_t* whas;    // [CN/32] bit u: node u has a child in the tree being evaluated
+  int32_t* wmeta;    // [4][32] per walker: root, draws, error, spare
+  uint32_t* wring;   // [W][128] per walker: ring of successor draws (random words), see wilson_walk_warp
   uint32_t* best;    // [CN] minimum key over the live edges of a component
   uint32_t* bpos;    // [CN] (local edge << 16 | live-list position) of that minimum
   lid_t* hook;       // [CN] component merge forest
@@ -107,9 +112,9 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(
 // The first three arrays (misc, membership bitmap, its prefix) always live in shared memory
 // at `base`; the rest follows them there, or - when a merged pair does not fit the 227 KB
 // of an SM (spill mode) - sits in a per-CTA global scratch block at `big` (L2 resident).
-// Returns the total size; *split = size of the always-shared part.
+// Returns the total size; *split = size of the always-shared part.  (MST kernels.)
 __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int N, int CN, int CE, int R,
-                                              int wilson, unsigned char* big = nullptr, size_t* split_out = nullptr) {
+                                              unsigned char* big = nullptr, size_t* split_out = nullptr) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return r; };
   const int NW = (N + 31) / 32;
@@ -125,27 +130,16 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
   size_t o_oldb = take(size_t((CN + 31) / 32) * 4);
   size_t o_newb = take(size_t((CN + 31) / 32) * 4);
   size_t o_ecls = take(R > 0 ? size_t(CE) : 0);
-  size_t o_loff = take(wilson ? size_t(CN + 1) * 2 : 0);
-  size_t o_ladj = take(wilson ? size_t(2 * CE) * 2 : 0);
-  size_t o_ladje = take(wilson ? size_t(2 * CE) * 2 : 0);
   size_t phase = o;
-  // spanning-tree phase (Boruvka arrays are not needed in Wilson mode and vice versa)
-  size_t o_key = take(wilson ? 0 : size_t(CE) * 4);
-  size_t o_lab = take(wilson ? 0 : size_t(CE) * 4);
-  size_t o_lj = take(wilson ? 0 : size_t(CE) * 2);
-  size_t o_best = take(wilson ? 0 : size_t(CN) * 4);
-  size_t o_bpos = take(wilson ? 0 : size_t(CN) * 4);
-  size_t o_hook = take(wilson ? 0 : size_t(CN) * 2);
-  size_t o_vlA = take(wilson ? 0 : size_t(CN / 2 + 2) * 2);
-  size_t o_vlB = take(wilson ? 0 : size_t(CN / 2 + 2) * 2);
-  size_t o_wtmp = take(wilson ? size_t(CN) * 4 : 0);
-  size_t o_wcnt = take(wilson ? size_t(CN) * 2 : 0);
-  size_t o_wgA = take(wilson ? size_t(CN) * 2 : 0);
-  size_t o_wgB = take(wilson ? size_t(CN) * 2 : 0);
-  size_t o_wmark = take(wilson ? size_t((CN + 31) / 32) * 4 : 0);
-  size_t o_wnx = take(wilson ? size_t(CN) * 2 : 0);
-  size_t o_wst = take(wilson ? size_t(CN) * 8 : 0);
-  size_t o_wtab = take(wilson ? size_t(CN) * 16 : 0);
+  // spanning-tree phase
+  size_t o_key = take(size_t(CE) * 4);
+  size_t o_lab = take(size_t(CE) * 4);
+  size_t o_lj = take(size_t(CE) * 2);
+  size_t o_best = take(size_t(CN) * 4);
+  size_t o_bpos = take(size_t(CN) * 4);
+  size_t o_hook = take(size_t(CN) * 2);
+  size_t o_vlA = take(size_t(CN / 2 + 2) * 2);
+  size_t o_vlB = take(size_t(CN / 2 + 2) * 2);
   size_t end_a = o;
   // Euler phase
   o = phase;
@@ -161,6 +155,7 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
   size_t o_ent = take(size_t(CN) * 2);
   size_t end_b = o;
   if (s) {
+    *s = Smem{};
     s->misc = (int32_t*)(base + o_misc);
     s->mbits = (uint32_t*)(base + o_mbits);
     s->mpref = (lid_t*)(base + o_mpref);
@@ -172,17 +167,6 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
     s->oldb = (uint32_t*)(base + o_oldb);
     s->newb = (uint32_t*)(base + o_newb);
     s->ecls = (uint8_t*)(base + o_ecls);
-    s->loff = (lid_t*)(base + o_loff);
-    s->ladj = (lid_t*)(base + o_ladj);
-    s->ladje = (lid_t*)(base + o_ladje);
-    s->wtmp = (uint32_t*)(base + o_wtmp);
-    s->wcnt = (lid_t*)(base + o_wcnt);
-    s->wgA = (lid_t*)(base + o_wgA);
-    s->wgB = (lid_t*)(base + o_wgB);
-    s->wmark = (uint32_t*)(base + o_wmark);
-    s->wnx = (lid_t*)(base + o_wnx);
-    s->wst = (unsigned long long*)(base + o_wst);
-    s->wtab = (lid_t*)(base + o_wtab);
     s->key = (uint32_t*)(base + o_key);
     s->lab = (uint32_t*)(base + o_lab);
     s->lj = (lid_t*)(base + o_lj);
@@ -206,11 +190,77 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
   return end_a > end_b ? end_a : end_b;
 }
 
+// Wilson kernels.  Tiers: `core` (misc, per-walker bookkeeping and draw rings, membership
+// bitmap + prefix) always in shared memory; `S` - what a walk WRITES at random: one state
+// word per node and walker, and the subtree sums / side bitmaps of the evaluation; `A` - what
+// it READS at random: the pair's adjacency; `cold` - arrays that are only streamed through
+// (populations, the edge list) in the CTA's global block, read through L2.
+//   level 0: core + S + A in shared memory;  level 1 (a pair whose adjacency does not fit):
+// core + S in shared memory, A in the CTA's global block (L2);  level 2: S and A global.
+// Returns the bytes of shared memory for `level`; *glob_out the bytes of the global block
+// (S and/or A), *cold_out the cold bytes.
+__host__ __device__ inline size_t wilson_layout(Smem* s, unsigned char* base, int N, int CN, int CE, int R, int W,
+                                                int nbr_shift, int level, unsigned char* glob, unsigned char* cold,
+                                                size_t* glob_out = nullptr, size_t* cold_out = nullptr) {
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return r; };
+  const int NW = (N + 31) / 32;
+  size_t o_misc = take(128 * 4);
+  size_t o_meta = take(4 * 32 * 4);
+  size_t o_ring = take(size_t(W) * 128 * 4);
+  size_t o_mbits = take(size_t(NW) * 4);
+  size_t o_mpref = take(size_t(NW) * 2);
+  const size_t core = o;
+  size_t o_oldb = take(size_t((CN + 31) / 32) * 4);
+  size_t o_newb = take(size_t((CN + 31) / 32) * 4);
+  size_t o_whas = take(size_t((CN + 31) / 32) * 4);
+  size_t o_wsum = take(size_t(CN) * 4);
+  size_t o_wst = take(size_t(W) * size_t(CN) * 2);
+  const size_t s_end = o;
+  size_t o_nbr = take((size_t(CN + CN / 8) << nbr_shift) * 4);
+  size_t o_wdeg = take(size_t(CN) * 2);
+  const size_t a_end = o;
+  const size_t smem = level == 0 ? a_end : level == 1 ? s_end : core;
+  if (glob_out) *glob_out = a_end - smem;
+  o = 0;
+  size_t c_pop = take(size_t(CN) * 4);
+  size_t c_eu = take(size_t(CE) * 2);
+  size_t c_ev = take(size_t(CE) * 2);
+  size_t c_ecls = take(R > 0 ? size_t(CE) : 0);
+  if (cold_out) *cold_out = o;
+  if (s) {
+    *s = Smem{};
+    s->misc = (int32_t*)(base + o_misc);
+    s->wmeta = (int32_t*)(base + o_meta);
+    s->wring = (uint32_t*)(base + o_ring);
+    s->mbits = (uint32_t*)(base + o_mbits);
+    s->mpref = (lid_t*)(base + o_mpref);
+    // the global block starts where shared memory ends: offsets beyond `smem` move there
+    unsigned char* hs = level == 2 ? glob - smem : base;
+    unsigned char* ha = level == 0 ? base : glob - smem;
+    s->oldb = (uint32_t*)(hs + o_oldb);
+    s->newb = (uint32_t*)(hs + o_newb);
+    s->whas = (uint32_t*)(hs + o_whas);
+    s->wsum = (int32_t*)(hs + o_wsum);
+    s->wtmp = (uint32_t*)(hs + o_wsum);
+    s->wst = (uint16_t*)(hs + o_wst);
+    s->nbr = (uint32_t*)(ha + o_nbr);
+    s->wdeg = (uint16_t*)(ha + o_wdeg);
+    s->pop = (int32_t*)(cold + c_pop);
+    s->eu = (lid_t*)(cold + c_eu);
+    s->ev = (lid_t*)(cold + c_ev);
+    s->ecls = (uint8_t*)(cold + c_ecls);
+  }
+  return smem;
+}
+
 // misc[] slots
 enum { M_WSUM = 0 /* 0..63: two alternating banks of 32 warp sums */,
-       M_ERR = 65, M_PICK, M_CNT, M_TOT, M_NINT, M_SUBSET, M_DELTA, M_NLIVE, M_NBAL, M_TAILLEN, M_NV, M_WALKER /* thread that runs single-thread sections */, M_WQ /* 77..78: Wilson worklist lengths */,
+       M_ERR = 65, M_PICK, M_CNT, M_TOT, M_NINT, M_SUBSET, M_DELTA, M_NLIVE, M_NBAL, M_TAILLEN, M_NV, M_WALKER /* Wilson: the warp whose lanes walk */, M_SPARE0, M_SPARE1 /* 78..79 */,
        M_BEST64 = 80 /* 80..81, 8-byte aligned */, M_TICKET = 82 /* 82..85: two 8-byte slots */,
-       M_WBC = 86 /* 86..87: Wilson, what warp 0 hands back after a stretch of rounds on its own */, M_CTR = 88 /* 88..95 counters */ };
+       M_ROOTKIDS = 86 /* Wilson: children of the tree root */, M_CTR = 88 /* 88..95 counters */ };
+// wmeta[] rows (Wilson, per walker)
+enum { WM_ROOT = 0, WM_DRAWS = 32, WM_ERR = 64 };
 
 #ifdef __CUDACC__
 

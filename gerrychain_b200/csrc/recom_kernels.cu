@@ -10,6 +10,8 @@
 //   relabel + updaters     tree.py:947-964, partition/assignment.py:76-86,
 //                          updaters/tally.py:162-165, updaters/cut_edges.py:118-120
 //   validity / accept      constraints/bounds.py:25-28, accept.py:15, chain.py:185-195
+#include <type_traits>
+
 #include "recom_device.cuh"
 
 namespace rc {
@@ -101,45 +103,71 @@ __device__ int pick_cut_edge(Chain& c, int cut_count, uint32_t prop_no, uint32_t
   return e;
 }
 
-// Wilson only: adjacency lists of the merged pair (loff / ladj / ladje), every row in
-// ascending neighbour id - the order in which the walk's draw indexes the neighbours.
-__device__ void build_local_adjacency(Chain& c, const Step& st) {
+// Wilson only: adjacency of the merged pair for the walks.  Rows of D = 1 << nbr_shift slots;
+// every entry is a neighbour (bits 0-15) TOGETHER WITH THAT NEIGHBOUR'S DEGREE (bits 16-31),
+// rows in ascending neighbour id - the order in which a draw indexes the neighbours.  A walk
+// step is then ONE dependent load: the entry it fetches names the next node and says how
+// many neighbours the next draw chooses from.  Row u < n belongs to node u; the (few) nodes
+// of degree > D keep D - 1 entries there and a link in slot D - 1 to a spare row (index >= n)
+// with the next ones - linked again if those are more than D.
+// entry number idx of node u (degree du): slot idx of a short row, else down the links
+__device__ __forceinline__ uint32_t* nbr_slot(const Smem& s, int u, int du, int idx, int sh) {
+  const int D = 1 << sh;
+  uint32_t* row = s.nbr + ((size_t)u << sh);
+  while (du > D) { if (idx < D - 1) return row + idx; row = s.nbr + ((size_t)row[D - 1] << sh); idx -= D - 1; du -= D - 1; }
+  return row + idx;
+}
+
+__device__ int build_local_adjacency(Chain& c, const Step& st) {
+  const Params& p = *c.p;
   const Smem& s = c.s;
   const int tid = threadIdx.x, T = blockDim.x;
-  const int n = st.n, m = st.m;
+  const int n = st.n, m = st.m, sh = p.nbr_shift, D = 1 << sh;
+  const int rows_cap = p.cap_nodes + p.cap_nodes / 8;
   for (int i = tid; i < n; i += T) s.wtmp[i] = 0;
+  if (tid == 0) s.misc[M_CNT] = n;  // next spare row
   __syncthreads();
   for (int j = tid; j < m; j += T) { atomicAdd(&s.wtmp[s.eu[j]], 1u); atomicAdd(&s.wtmp[s.ev[j]], 1u); }
   __syncthreads();
-  {
-    const int per = odd_chunk(n);
-    const int lo = min(tid * per, n), hi = min(lo + per, n);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += (int)s.wtmp[i];
-    int tot;
-    int run = block_excl_scan(sum, &tot, s.misc, c.par);
-    for (int i = lo; i < hi; ++i) { const int d = (int)s.wtmp[i]; s.loff[i] = (lid_t)run; s.wtmp[i] = (uint32_t)run; run += d; }
-    if (tid == 0) s.loff[n] = (lid_t)(2 * m);
+  for (int i = tid; i < n; i += T) {
+    const int d = (int)s.wtmp[i];
+    s.wdeg[i] = (uint16_t)min(d, 0xffff);
+    if (d > D) {  // chain of spare rows: each full row but the last keeps D - 1 entries + the link
+      // spare rows needed: the d - (D - 1) entries left go into rows of D - 1 (+ link), the last row takes up to D
+      int need = 0;
+      for (int left = d - (D - 1); left > 0; left -= (left > D ? D - 1 : left)) ++need;
+      int r = atomicAdd(&s.misc[M_CNT], need);
+      if (r + need <= rows_cap) {
+        uint32_t* row = s.nbr + ((size_t)i << sh);
+        for (int left = d - (D - 1); left > 0; left -= (left > D ? D - 1 : left)) {
+          row[D - 1] = (uint32_t)r;
+          row = s.nbr + ((size_t)r << sh);
+          ++r;
+        }
+      }
+    }
+    s.wtmp[i] = 0;  // fill cursor
   }
   __syncthreads();
+  if (s.misc[M_CNT] > rows_cap) return RC_ERR_CAPACITY;  // too many high-degree nodes for the spare rows
   for (int j = tid; j < m; j += T) {
     const int u = s.eu[j], v = s.ev[j];
-    const int pu = (int)atomicAdd(&s.wtmp[u], 1u);
-    s.ladj[pu] = (lid_t)v; s.ladje[pu] = (lid_t)j;
-    const int pv = (int)atomicAdd(&s.wtmp[v], 1u);
-    s.ladj[pv] = (lid_t)u; s.ladje[pv] = (lid_t)j;
+    *nbr_slot(s, u, s.wdeg[u], (int)atomicAdd(&s.wtmp[u], 1u), sh) = (uint32_t)v;
+    *nbr_slot(s, v, s.wdeg[v], (int)atomicAdd(&s.wtmp[v], 1u), sh) = (uint32_t)u;
   }
   __syncthreads();
-  for (int i = tid; i < n; i += T) {  // insertion sort of a short row
-    const int r0 = s.loff[i], r1 = s.loff[i + 1];
-    for (int a = r0 + 1; a < r1; ++a) {
-      const lid_t kv = s.ladj[a], ke = s.ladje[a];
+  for (int i = tid; i < n; i += T) {  // insertion sort of a short row, then the neighbours' degrees
+    const int d = s.wdeg[i];
+    for (int a = 1; a < d; ++a) {
+      const uint32_t kv = *nbr_slot(s, i, d, a, sh);
       int b = a - 1;
-      while (b >= r0 && s.ladj[b] > kv) { s.ladj[b + 1] = s.ladj[b]; s.ladje[b + 1] = s.ladje[b]; --b; }
-      s.ladj[b + 1] = kv; s.ladje[b + 1] = ke;
+      while (b >= 0 && *nbr_slot(s, i, d, b, sh) > kv) { *nbr_slot(s, i, d, b + 1, sh) = *nbr_slot(s, i, d, b, sh); --b; }
+      *nbr_slot(s, i, d, b + 1, sh) = kv;
     }
+    for (int a = 0; a < d; ++a) { uint32_t* q = nbr_slot(s, i, d, a, sh); const uint32_t v = *q; *q = v | ((uint32_t)s.wdeg[v] << 16); }
   }
   __syncthreads();
+  return RC_OK;
 }
 
 // ---- P1: gather the merged pair into shared memory ---------------------------------------
@@ -277,7 +305,7 @@ __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
   st.m = m;
   *d_sub_out = s.misc[M_CNT];
   if (m > p.cap_edges || m > 65535) return RC_ERR_CAPACITY;
-  if (kWilson) build_local_adjacency(c, st);
+  if (kWilson) return build_local_adjacency(c, st);
   return RC_OK;
 }
 
@@ -485,399 +513,361 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
   return tree_edge_list(c, st);
 }
 
-// ---- P2b: uniform spanning tree (Wilson, tree.py:97-132) by parallel cycle popping -------
+__device__ __forceinline__ bool balanced(int tree_pop, int total_pop, double ideal, double thr) {
+  // tree.py:412-414, float64 as in the reference
+  return fabs(__dsub_rn((double)tree_pop, ideal)) <= thr &&
+         fabs(__dsub_rn((double)(total_pop - tree_pop), ideal)) <= thr;
+}
+
+// ---- P2b: uniform spanning trees (Wilson, tree.py:97-132): one walker per LANE ------------
 // Every node owns a stack of successor draws: draw j at node u is a pure function of (u, j)
-// (recom_rng.h).  Pointing every node at the top of its stack gives a functional graph; its
-// cycles are popped (every node on a cycle takes its next draw) until none is left.  The
-// popped cycles and the final tree do not depend on the popping order (Wilson 1996), so
-// this is the tree - and the per-node draw counts - of the reference's sequential
-// loop-erased walks fed with the same stacks.  Cycles of up to kHop nodes are found by a
-// look-ahead from the nodes whose pointer just changed; longer ones by pointer doubling
-// over the functional graph.
-//
-// Draws are tabulated: wtab[u] is a ring of 8 successors, draws [hi - 8, hi) of node u at
-// slot (j & 7), filled four at a time (one Philox block) - the first 8 by everybody at the
-// start, the later ones by whoever consumes draw j == hi.  A pop is then one table look-up;
-// the generator runs once per four pops, off the pointer-chasing paths.
-constexpr int kHop = 8;      // a worklist node looks this many pointers ahead for a cycle through itself
-constexpr int kHandoff = 1;  // default RcConfig.wilson_handoff (measured: the parallel rounds beat the lone thread to the very end)
-constexpr int kMaxPasses = 4096;    // safety (disconnected input plans): then phase 3's budget applies
-constexpr int kTab = 8;  // ring of tabulated draws per node
-constexpr int kWarpRoundsEnter = 32;  // worklists this short are handled by warp 0 alone ...
-constexpr int kWarpRoundsExit = 64;   // ... until they outgrow this (multiple of 32)
-constexpr uint32_t kInTree = 0xffffu;  // walk stamp of a node that leads to the root
+// (recom_rng.h), so the tree - and the per-node draw counts - do not depend on the order in
+// which walks are made (Wilson 1996), and the reference's loop (tree.py:116-125) can be run
+// as it is written: walk from every node not yet in the tree, overwrite next[u] at every
+// visit (loop erasure is implicit), retrace the walk to add it to the tree.
+//   The walk is a chain of ~8 n dependent steps; more threads do not shorten it (round 1's
+// parallel cycle popping needed ~580 dependent rounds per 1000-node tree and kept one warp
+// busy for as long as a lone walker needs).  What the SM has in abundance is room for
+// INDEPENDENT chains of steps: a step of bipartition_tree (tree.py:679-718) draws trees
+// t, t+1, ... until one has a balanced cut, and the trees are independent of each other.
+// So lanes 0..W-1 of warp 0 each walk one of the next W trees of this proposal, all on the
+// one adjacency the block gathered (same instruction stream, different tree: full SIMT
+// efficiency), and the block then examines the trees in order; the lowest tree number with
+// a balanced cut wins, exactly as if they had been drawn one after the other.
+//   Per walker and node ONE 32-bit word: successor (bits 0-15) | draws consumed (16-30) |
+// in the tree (31).  A walk step is one Philox block (the draw), two 16-bit loads (row
+// bounds), one load of the successor, one store of the word, one load of the next word.
+constexpr uint32_t kInTree = 0x8000u;  // walker state: successor (bits 0-14) | in the tree (bit 15)
+constexpr uint32_t kNext = 0x7fffu;
+constexpr uint32_t kRing = 128;  // draws per walker's ring (power of two)
 
+// The walks of one batch, all 32 lanes of the walker warp in one loop: lanes 0..n_walk-1
+// walk (tree tree_base + lane), every lane helps to refill the draw rings.
+//   Draw t of a tree's walk (recom_rng.h RC_DRAW_WALK: t counts the successor draws of the
+// tree in the order the loop of tree.py:116-125 makes them - start nodes ascending, every
+// walk to its end) does not depend on where the walk is, so the generator is off the
+// walk's dependency chain: a ring of 64 draws per walker, refilled 32 at a time by the
+// WHOLE warp (one Philox block per lane: 8 lanes per walker) whenever a walker has used up
+// its older half.  What is left on the chain of a step is ONE load: the adjacency entry
+// picked by the draw names the next node and its degree, and the entry after it is
+// requested before the "has the walk reached the tree?" test of the node resolves.
+//   The loop is a function of its own (not inlined: its registers are not shared with the
+// 200 KB of kernel around it) over accessors: in shared memory the arrays are addressed by
+// 32-bit shared-window offsets held in registers with explicit ld/st.shared (the compiler
+// otherwise re-derives the window address - a special-register read - in front of the
+// loads); in spill mode they are global pointers.  scripts/dev/walk_bench.cu has the loop in
+// isolation: 104 cycles per step on B200 (a dependent LDS alone is 34).
+struct WalkArgs {
+  uint64_t seed;
+  uint32_t gchain, tree_base, prop_no;
+  int n, walker, sh, cap_nodes;
+  void *nbr, *wst, *wring, *wdeg;
+  int32_t* wmeta;
+  unsigned long long* timers;  // RC_TIMERS builds
+};
 
-__device__ int wilson_tree(Chain& c, const Step& st, uint32_t tree_no, uint32_t prop_no, long long tree_idx,
-                           int32_t* ctr) {
+struct MemShared {  // level 0: 32-bit shared-window addresses
+  static constexpr int kFirst = 2, kRest = 8;  // burst lengths (steps of straight-line code)
+  uint32_t nbr, S, ring, deg;
+  __device__ __forceinline__ uint32_t ld_nbr(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(nbr + 4u * i) : "memory"); return v; }
+  __device__ __forceinline__ uint32_t ld_ring(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + 4u * i) : "memory"); return v; }
+  __device__ __forceinline__ uint32_t ld_S(uint32_t i) const { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(S + 2u * i) : "memory"); return v; }
+  __device__ __forceinline__ void st_S(uint32_t i, uint32_t v) const { asm volatile("st.shared.u16 [%0], %1;" :: "r"(S + 2u * i), "h"((uint16_t)v) : "memory"); }
+  __device__ __forceinline__ uint32_t ld_deg(uint32_t i) const { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(deg + 2u * i) : "memory"); return v; }
+};
+
+// level 1: the adjacency is read from the CTA's global block (read-only during the walks: plain
+// cached loads, kept in program order by asm volatile), the walker state stays in shared memory
+struct MemMixed {
+  static constexpr int kFirst = 1, kRest = 2;  // a step is an L2 round trip: a wasted one costs more than a branch
+  const uint32_t* nbr; const uint16_t* deg;
+  uint32_t S, ring;
+  __device__ __forceinline__ uint32_t ld_nbr(uint32_t i) const { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(nbr + i) : "memory"); return v; }
+  __device__ __forceinline__ uint32_t ld_ring(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + 4u * i) : "memory"); return v; }
+  __device__ __forceinline__ uint32_t ld_S(uint32_t i) const { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(S + 2u * i) : "memory"); return v; }
+  __device__ __forceinline__ void st_S(uint32_t i, uint32_t v) const { asm volatile("st.shared.u16 [%0], %1;" :: "r"(S + 2u * i), "h"((uint16_t)v) : "memory"); }
+  __device__ __forceinline__ uint32_t ld_deg(uint32_t i) const { return deg[i]; }
+};
+
+struct MemGlobal {  // level 2: state and adjacency in the CTA's global block
+  static constexpr int kFirst = 1, kRest = 2;
+  const uint32_t* nbr; uint16_t* S; const uint16_t* deg;
+  uint32_t ring;
+  __device__ __forceinline__ uint32_t ld_nbr(uint32_t i) const { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(nbr + i) : "memory"); return v; }
+  __device__ __forceinline__ uint32_t ld_ring(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + 4u * i) : "memory"); return v; }
+  __device__ __forceinline__ uint32_t ld_S(uint32_t i) const { uint16_t v; asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(S + i) : "memory"); return v; }
+  __device__ __forceinline__ void st_S(uint32_t i, uint32_t v) const { asm volatile("st.global.u16 [%0], %1;" :: "l"(S + i), "h"((uint16_t)v) : "memory"); }
+  __device__ __forceinline__ uint32_t ld_deg(uint32_t i) const { return deg[i]; }
+};
+
+template <typename Mem, int sh>  // sh: log2 of the adjacency slots per node, a compile-time shift
+__device__ __noinline__ void wilson_walk_loop(const WalkArgs a, Mem M) {
+  const int lane = threadIdx.x & 31;
+  const int n = a.n, w = a.walker;
+  constexpr uint32_t D = 1u << sh;
+  uint32_t* const wring = (uint32_t*)a.wring + w * kRing;
+  // one Philox block per lane: draws [4 b, 4 b + 4) of this walker into its ring
+  auto fill = [&](uint32_t b) {
+    const RcPhilox r = rc_draw(a.seed, a.gchain, RC_DRAW_WALK, b, a.tree_base + (uint32_t)w, a.prop_no, 0);
+    *reinterpret_cast<uint4*>(wring + ((b & (kRing / 4 - 1)) << 2)) = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  };
+  fill((uint32_t)lane);  // kRing / 4 == 32 blocks
+  __syncwarp();
+  // entry of node u (degree du) picked by the random word r
+  auto pick = [&](uint32_t u, uint32_t du, uint32_t r) -> uint32_t {
+    uint32_t idx = rc_below32(r, du);
+    uint32_t row = u << sh;
+    while (du > D) {  // a long row: D - 1 entries, then the link to the next part
+      if (idx < D - 1u) break;
+      row = M.ld_nbr(row + D - 1u) << sh;
+      idx -= D - 1u;
+      du -= D - 1u;
+    }
+    return M.ld_nbr(row + idx);
+  };
+  // Every lane runs the reference's loop as it is written - find the next node outside the
+  // tree, walk until the tree is hit, retrace - and comes back to the top of the outer loop,
+  // where the warp meets for the refill vote, after kQuota draws at the latest (the ring then
+  // still holds them: a refill leaves more than 32 unread).  Lanes in different phases
+  // diverge inside a trip; a lone warp pays ~15-20 cycles for every branch it has to resolve,
+  // so the phases are tight loops of their own rather than cases of a per-event switch.
+  constexpr int kQuota = 58;  // 2 + 7 x 8: below kRing / 2 with the look-ahead of a burst
+  bool live = lane == 0 && a.wmeta[WM_ERR + w] == 0;
+  bool walking = false, first = false;  // a walk is under way (u, e hold its state); its first burst is due
+  int err = 0;
+  uint32_t scan = 0, start = 0, u = 0, e = 0, t = 0, filled = kRing;
+  int budget = n < (1 << 19) ? 2048 * n + 65536 : 0x7fffffff;  // a walk that cannot reach the tree (disconnected input plan)
+#ifdef RC_TIMERS
+  unsigned long long tm_iter = 0;
+  const unsigned long long tm0 = (unsigned long long)clock64();
+#endif
+  while (__any_sync(0xffffffffu, live)) {
+#ifdef RC_TIMERS
+    ++tm_iter;
+#endif
+    {  // refill: once the older half of the ring is used up, 16 lanes make the next kRing / 2 draws
+      const uint32_t fw = __shfl_sync(0xffffffffu, (live && t + kRing / 2 >= filled) ? filled : 0u, 0);
+      if (fw) {
+        if (lane < 16) fill((fw >> 2) + (uint32_t)lane);
+        filled += kRing / 2;
+        __syncwarp();
+      }
+    }
+    if (live) {
+      int quota = kQuota;
+      for (;;) {
+        if (!walking) {  // the next node that is not in the tree starts a walk
+          while (scan < (uint32_t)n && (M.ld_S(scan) & kInTree)) ++scan;
+          if (scan >= (uint32_t)n) { live = false; break; }
+          start = u = scan++;
+          e = pick(u, M.ld_deg(u), M.ld_ring(t & (kRing - 1u)));  // the entry the first step of the walk takes
+          walking = true;
+          first = true;
+        }
+        // state: u = current node (not in the tree), e = the adjacency entry draw t picked at u.
+        // A burst is K steps of straight-line code: the steps behind the one that reaches the
+        // tree are predicated off instead of branched around (a lone warp waits 15-20 cycles
+        // for every branch it resolves), their loads still go out (to valid addresses: e is a
+        // valid entry) and are ignored.  Most walks end within two steps (the tree is next
+        // door once it has grown), the few long ones make most of the draws: a walk starts
+        // with a burst of 2 and goes on in bursts of 8.
+        bool hit = false;
+        auto burst = [&](auto kc) {
+          constexpr int K = decltype(kc)::value;
+          uint32_t rr[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) rr[k] = M.ld_ring((t + 1u + (uint32_t)k) & (kRing - 1u));  // draws t+1 .. t+K
+          bool alive = true;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const uint32_t v = e & 0xffffu;
+            if (alive) M.st_S(u, v);
+            const uint32_t en = pick(v, e >> 16, rr[k]);  // the entry the NEXT step takes (draw t + 1 + k)
+            const uint32_t wv = M.ld_S(v);
+            t += alive ? 1u : 0u;
+            const bool go = alive && !(wv & kInTree);
+            hit = hit || (alive && (wv & kInTree));
+            u = go ? v : u;
+            e = go ? en : e;
+            alive = go;
+          }
+        };
+        if (first) { first = false; burst(std::integral_constant<int, Mem::kFirst>()); quota -= Mem::kFirst; }
+        while (!hit && quota >= Mem::kRest) { burst(std::integral_constant<int, Mem::kRest>()); quota -= Mem::kRest; }
+        if (!hit && quota > 0) quota = 0;
+        if (!hit) break;  // out of draws for this trip, the walk goes on in the next
+        walking = false;
+        for (u = start;;) {  // retrace: the loop-erased walk joins the tree
+          const uint32_t w = M.ld_S(u);
+          if (w & kInTree) break;
+          M.st_S(u, w | kInTree);
+          u = w & kNext;
+        }
+        if (quota <= 0) break;
+      }
+      budget -= kQuota;
+      if (budget < 0) { err = RC_ERR_DISCONNECTED; live = false; }
+    }
+  }
+  if (lane == 0 && a.wmeta[WM_ERR + w] == 0) {
+    a.wmeta[WM_DRAWS + w] = (int)t;
+    a.wmeta[WM_ERR + w] = err;
+  }
+#ifdef RC_TIMERS
+  if (lane == 0 && w == 0) {  // slots 11-12: cycles inside the walk loop, its trips
+    atomicAdd(a.timers + 11, (unsigned long long)clock64() - tm0);
+    atomicAdd(a.timers + 12, tm_iter);
+  }
+#endif
+}
+
+// walker w of the batch (tree tree_base + w) on the calling warp: lane 0 walks, the other
+// lanes help with the draws
+__device__ __forceinline__ void wilson_walk_warp(const Chain& c, const Step& st, uint32_t tree_base, int w,
+                                                 uint32_t prop_no) {
+  const Params& p = *c.p;
+  const Smem& s = c.s;
+  WalkArgs a;
+  a.seed = p.cfg.seed; a.gchain = c.gchain; a.tree_base = tree_base; a.prop_no = prop_no;
+  a.n = st.n; a.walker = w; a.sh = p.nbr_shift; a.cap_nodes = p.cap_nodes;
+  a.nbr = s.nbr; a.wst = s.wst; a.wring = s.wring; a.wdeg = s.wdeg; a.wmeta = s.wmeta;
+  a.timers = reinterpret_cast<unsigned long long*>(s.misc + 96);
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s.wring + w * kRing);
+  if (p.wilson_level == 0) {
+    MemShared M;
+    M.nbr = (uint32_t)__cvta_generic_to_shared(s.nbr);
+    M.S = (uint32_t)__cvta_generic_to_shared(s.wst + (size_t)w * p.cap_nodes);
+    M.ring = ring;
+    M.deg = (uint32_t)__cvta_generic_to_shared(s.wdeg);
+    if (a.sh == 2) wilson_walk_loop<MemShared, 2>(a, M); else wilson_walk_loop<MemShared, 3>(a, M);
+  } else if (p.wilson_level == 1) {
+    MemMixed M;
+    M.nbr = s.nbr; M.deg = s.wdeg; M.ring = ring;
+    M.S = (uint32_t)__cvta_generic_to_shared(s.wst + (size_t)w * p.cap_nodes);
+    if (a.sh == 2) wilson_walk_loop<MemMixed, 2>(a, M); else wilson_walk_loop<MemMixed, 3>(a, M);
+  } else {
+    MemGlobal M;
+    M.nbr = s.nbr; M.S = s.wst + (size_t)w * p.cap_nodes; M.ring = ring; M.deg = s.wdeg;
+    if (a.sh == 2) wilson_walk_loop<MemGlobal, 2>(a, M); else wilson_walk_loop<MemGlobal, 3>(a, M);
+  }
+}
+
+// TEST HOOK: one tree from the reference's recorded stacks (tree.py:119) - visit j of node u
+// takes recorded successor j of u; one thread, visit counts in wsum (free until the tree is
+// evaluated).  Same loop as the reference's: walk, overwrite, retrace.
+__device__ void wilson_walk_recorded(const Chain& c, const Step& st, long long tree_idx) {
+  const Params& p = *c.p;
+  const Smem& s = c.s;
+  const int n = st.n, sh = p.nbr_shift;
+  uint16_t* S = s.wst;
+  int32_t* cnt = s.wsum;
+  const int64_t* sp = p.rp.stack_ptr + tree_idx * ((long long)p.g.N + 1);
+  int err = 0, t = 0;
+  for (int node = 0; node < n && !err; ++node) {
+    int u = node;
+    while (!(S[u] & kInTree)) {
+      const int gu = c.nodes[u], cu = cnt[u], d = s.wdeg[u];
+      int v = -1;
+      if (sp[gu] + (long long)cu < sp[gu + 1]) {
+        const int gv = p.rp.stack_val[sp[gu] + cu];
+        if (gv >= 0 && gv < p.g.N && is_member(s, gv)) {
+          const int lv = local_id(s, gv);
+          for (int q = 0; q < d; ++q) if ((int)(*nbr_slot(s, u, d, q, sh) & 0xffffu) == lv) v = lv;
+        }
+      }
+      if (v < 0) { err = RC_ERR_REPLAY; break; }
+      cnt[u] = cu + 1;
+      ++t;
+      S[u] = (uint16_t)v;
+      u = v;
+    }
+    for (u = node; !err && !(S[u] & kInTree);) { const uint32_t w = S[u]; S[u] = (uint16_t)(w | kInTree); u = (int)(w & kNext); }
+  }
+  s.wmeta[WM_DRAWS] = t;
+  s.wmeta[WM_ERR] = err;
+}
+
+// Trees tree_base .. tree_base + n_walk - 1 of proposal prop_no, one per lane of the walker
+// warp (replay: ONE recorded tree).  On return wst[w] holds tree w as parent pointers (the
+// root points at itself), wmeta its root, draw count and status.
+__device__ void wilson_walk(Chain& c, const Step& st, uint32_t tree_base, int n_walk, uint32_t prop_no,
+                            long long tree_idx_base) {
   const Params& p = *c.p;
   const Smem& s = c.s;
   const int tid = threadIdx.x, T = blockDim.x;
-  const int n = st.n, m = st.m;
+  const int n = st.n, CN = p.cap_nodes;
   const bool replay = p.rp.n_steps > 0;
-  int root;
-  if (replay) {
-    const int gr = p.rp.wilson_root[tree_idx];
-    root = (gr >= 0 && gr < p.g.N && is_member(s, gr)) ? local_id(s, gr) : -1;
-    if (root < 0) return RC_ERR_REPLAY;
-  } else {
-    const RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WROOT, 0, tree_no, prop_no, 0);
-    root = (int)rc_below(r.v[0], r.v[1], (uint32_t)n);
-  }
-  const int64_t* sp = replay ? p.rp.stack_ptr + tree_idx * ((long long)p.g.N + 1) : nullptr;
-  // replay: successor draw j of node u from the recorded stacks (tree.py:119)
-  auto recorded = [&](int u, uint32_t j) {
-    const int r0 = s.loff[u], d = s.loff[u + 1] - r0;
-    const int gu = c.nodes[u];
-    int nn = -1;
-    if (sp[gu] + (long long)j < sp[gu + 1]) {
-      const int gv = p.rp.stack_val[sp[gu] + j];
-      if (gv >= 0 && gv < p.g.N && is_member(s, gv)) {
-        const int lv = local_id(s, gv);
-        for (int q = 0; q < d; ++q) if (s.ladj[r0 + q] == lv) nn = lv;
-      }
-    }
-    if (nn < 0) { s.misc[M_ERR] = RC_ERR_REPLAY; nn = s.ladj[r0]; }
-    return nn;
-  };
-  // free-running: draws 4b .. 4b + 3 of node u into their ring slots (one 64-bit store)
-  auto fill_block = [&](int u, uint32_t b) {
-    const int r0 = s.loff[u];
-    const uint32_t d = (uint32_t)(s.loff[u + 1] - r0);
-    const RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WALK, (uint32_t)u, tree_no, prop_no, b);
-    const uint32_t a0 = s.ladj[r0 + (int)rc_below32(r.v[0], d)], a1 = s.ladj[r0 + (int)rc_below32(r.v[1], d)];
-    const uint32_t a2 = s.ladj[r0 + (int)rc_below32(r.v[2], d)], a3 = s.ladj[r0 + (int)rc_below32(r.v[3], d)];
-    *reinterpret_cast<uint2*>(s.wtab + u * kTab + ((b & 1u) << 2)) = make_uint2(a0 | (a1 << 16), a2 | (a3 << 16));
-  };
-  // node u takes its next draw (one thread per node and round).  The end of the tabulated
-  // draws is implied in phase 1 - max(8, 4 * ceil(j / 4)): blocks beyond the first two are
-  // filled exactly when their first draw is taken
-  auto pop1 = [&](int u) {
-    const uint32_t j = s.wcnt[u];
-    int nn;
+  if (tid < n_walk) {
+    int root, err = 0;
     if (replay) {
-      nn = recorded(u, j);
+      const int gr = p.rp.wilson_root[tree_idx_base + tid];
+      const bool ok = gr >= 0 && gr < p.g.N && is_member(s, gr);
+      root = ok ? local_id(s, gr) : 0;
+      if (!ok) err = RC_ERR_REPLAY;
     } else {
-      if (j >= (uint32_t)kTab && (j & 3u) == 0) fill_block(u, j >> 2);
-      nn = s.wtab[u * kTab + (j & 7u)];
+      const RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_WROOT, 0, tree_base + (uint32_t)tid, prop_no, 0);
+      root = (int)rc_below(r.v[0], r.v[1], (uint32_t)n);
     }
-    s.wnx[u] = (lid_t)nn;
-    s.wcnt[u] = (lid_t)(j + 1);
-  };
-  auto succ_of = [&](int u) { return (int)s.wnx[u]; };  // wnx[root] == root
-  if (tid == 0) s.misc[M_ERR] = 0;
-  for (int u = tid; u < n; u += T) {
-    if (u != root) {
-      if (s.loff[u + 1] == s.loff[u]) { s.misc[M_ERR] = RC_ERR_DISCONNECTED; continue; }
-      if (!replay) { fill_block(u, 0); fill_block(u, 1); }
-      s.wnx[u] = (lid_t)(replay ? recorded(u, 0) : (int)s.wtab[u * kTab]);
-      s.wcnt[u] = 1;
-    } else {
-      s.wnx[u] = (lid_t)u;
-      s.wcnt[u] = 0;
-    }
+    s.wmeta[WM_ROOT + tid] = root;
+    s.wmeta[WM_ERR + tid] = err;
+    s.wmeta[WM_DRAWS + tid] = 0;
   }
-  for (int i = tid; i < (m + 31) >> 5; i += T) s.tflag[i] = 0;
-  for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
+  for (int w = 0; w < n_walk; ++w)
+    for (int i = tid; i < n; i += T) s.wst[(size_t)w * CN + i] = 0;
+  if (replay) for (int i = tid; i < n; i += T) s.wsum[i] = 0;  // visit counts of the recorded walk
   __syncthreads();
-  if (s.misc[M_ERR]) return s.misc[M_ERR];
-  // Phase 1 - pop cycles in parallel, driven by a worklist.  A cycle that was not there
-  // before must run through a node whose pointer just changed, so only the nodes popped in
-  // the previous round are examined: the thread that holds worklist entry u follows the
-  // pointers for up to kHop steps; if that leads back to u it has found a cycle (its members
-  // in registers).  Every worklist member of the cycle finds it; the one that first sets the
-  // bit of the cycle's lowest node pops it - all members take their next draw and form the
-  // next worklist.  Round one examines every node.  Work per round is O(popped), not O(n):
-  // late rounds keep a warp or two busy and leave the SM to the co-resident CTA.
-  //   When the worklist runs dry, what is left are cycles longer than kHop (or none): one
-  // global detection (pointer doubling: after >= n steps every node sits on a cycle or at the
-  // root, and every cycle node is somebody's landing point) pops them and refills the
-  // worklist.  A global detection that finds nothing ends the phase: the tree is complete.
-  // RcConfig.wilson_handoff > 1 ends it earlier (worklist / detection yield below the
-  // threshold) and leaves the rest to the sequential finish - kept as a tuning and test knob.
-  const int kLocalThreshold = p.cfg.wilson_handoff > 0 ? p.cfg.wilson_handoff : kHandoff;
-  const int kFullThreshold = 2 * kLocalThreshold;
-  int walk = 0, passes = 0;
-  lid_t* __restrict__ P = s.wgA;  // worklists alias the pointer-doubling buffers (never live together)
-  lid_t* __restrict__ Q = s.wgB;
-  int32_t* const wq = s.misc + M_WQ;  // wq[0], wq[1]: length of the list being built, by round parity
-  for (int i = tid; i < n - 1; i += T) P[i] = (lid_t)(i + (i >= root));
-  if (tid == 0) { wq[0] = 0; wq[1] = 0; }
-  int np = n - 1, par = 0;
-  __syncthreads();
-  // one worklist entry: look ahead from P[i]; the owner of a cycle appends its members to Q
-  // and returns the cycle's lowest node (whose mark it clears after the round), else kNoCycle
-  constexpr uint32_t kNoCycle = 0xffffffffu;
-  auto detect = [&](const lid_t* __restrict__ Pl, lid_t* __restrict__ Ql, int i, int parity) -> uint32_t {
-    const int u = Pl[i];
-    lid_t mem[kHop];
-    int L = 0, v = u;
-    uint32_t mn = (uint32_t)u;
-#pragma unroll
-    for (int h = 0; h < kHop; ++h) {
-      mem[h] = (lid_t)v;
-      v = succ_of(v);
-      if (v == u) { L = h + 1; break; }
-      if (v == root) break;
-      mn = min(mn, (uint32_t)v);
-    }
-    if (L && !((atomicOr(&s.wmark[mn >> 5], 1u << (mn & 31u)) >> (mn & 31u)) & 1u)) {
-      const int slot = atomicAdd(&wq[parity], L);
-#pragma unroll
-      for (int h = 0; h < kHop; ++h) if (h < L) Ql[slot + h] = mem[h];
-      return mn;
-    }
-    return kNoCycle;
-  };
-  int32_t* const wbc = s.misc + M_WBC;  // what warp 0 hands back to the block: np, rounds done
-  for (;;) {
-    while (np >= kLocalThreshold && passes <= kMaxPasses) {
-      if (np <= kWarpRoundsEnter) {
-        // Short worklists (nearly every round after the first few): warp 0 runs the rounds on
-        // its own, separated by __syncwarp() instead of block barriers, while the other warps
-        // wait at ONE barrier for the whole stretch and issue nothing.  It hands the block back
-        // a worklist that outgrew it (a popped cycle can be longer than the list that found it)
-        // or ran dry.
-        RC_PH(PH_W1);  // timers build: W1 = block-wide rounds, W2 / W3 = detect / pop of warp-0 rounds, slot 14 = global detections
-        if (tid < 32) {
-          int rounds = 0;
-          int npw = np, parw = par;
-          lid_t* Pw = P; lid_t* Qw = Q;
-          while (npw >= kLocalThreshold && npw <= kWarpRoundsExit && passes + rounds <= kMaxPasses) {
-            ++rounds;
-            uint32_t own[kWarpRoundsExit / 32];
-#pragma unroll
-            for (int r = 0; r < kWarpRoundsExit / 32; ++r) {
-              const int i = r * 32 + tid;
-              own[r] = i < npw ? detect(Pw, Qw, i, parw) : kNoCycle;
-            }
-            __syncwarp();
-            RC_PH(PH_W2);
-            const int nq = *(volatile int32_t*)&wq[parw];
-            for (int i = tid; i < nq; i += 32) { pop1(Qw[i]); ++walk; }
-#pragma unroll
-            for (int r = 0; r < kWarpRoundsExit / 32; ++r)
-              if (own[r] != kNoCycle) atomicAnd(&s.wmark[own[r] >> 5], ~(1u << (own[r] & 31u)));
-            if (tid == 0) wq[parw ^ 1] = 0;
-            __syncwarp();
-            RC_PH(PH_W3);
-            npw = nq;
-            parw ^= 1;
-            lid_t* t_ = Pw; Pw = Qw; Qw = t_;
-          }
-          if (tid == 0) { wbc[0] = npw; wbc[1] = rounds; }
-        }
-        __syncthreads();
-        const int rounds = wbc[1];
-        np = wbc[0];
-        passes += rounds;
-        if (rounds & 1) { par ^= 1; lid_t* t_ = P; P = Q; Q = t_; }
-        __syncthreads();  // wbc is rewritten only after everybody has read it
-        if (rounds > 0) continue;
-      }
-      ++passes;
-      for (int i = tid; i < np; i += T) detect(P, Q, i, par);
-      __syncthreads();  // every pointer has been read; Q is complete (a cycle's nodes appear once)
-      const int nq = wq[par];
-      for (int i = tid; i < nq; i += T) { pop1(Q[i]); ++walk; }
-      for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;  // the owners' marks
-      if (tid == 0) wq[par ^ 1] = 0;  // the next round's counter: everybody has read it by now
-      __syncthreads();
-      np = nq;
-      par ^= 1;
-      lid_t* t_ = P; P = Q; Q = t_;
-    }
-    if (passes > kMaxPasses) break;
-    ++passes;
-    RC_PH(PH_W1);
-    // global detection (the worklist is dead: P and Q are free)
-    lid_t* __restrict__ A = s.wgA;
-    lid_t* __restrict__ B = s.wgB;
-    for (int u = tid; u < n; u += T) A[u] = (lid_t)succ_of(u);
-    __syncthreads();
-    if (tid == 0) wq[par ^ 1] = 0;
-    for (int span = 1; span < n; span <<= 1) {
-      for (int u = tid; u < n; u += T) B[u] = A[A[u]];
-      __syncthreads();
-      lid_t* tmp = A; A = B; B = tmp;
-    }
-    for (int u = tid; u < n; u += T) {
-      const int v = A[u];
-      if (v != root) atomicOr(&s.wmark[v >> 5], 1u << (v & 31));
-    }
-    __syncthreads();  // A and B are dead from here on
-    P = s.wgA;
-    Q = s.wgB;
-    for (int u0 = 0; u0 < n; u0 += T) {
-      const int u = u0 + tid;
-      const bool hit = u < n && ((s.wmark[u >> 5] >> (u & 31)) & 1u);
-      if (hit) { pop1(u); ++walk; }
-      // warp-aggregated append to the worklist
-      const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-      if (bal) {
-        int slot = 0;
-        if ((tid & 31) == 0) slot = atomicAdd(&wq[par], __popc(bal));
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (hit) P[slot + __popc(bal & ((1u << (tid & 31)) - 1u))] = (lid_t)u;
-      }
-    }
-    __syncthreads();
-    np = wq[par];
-    par ^= 1;
-    for (int i = tid; i < (n + 31) >> 5; i += T) s.wmark[i] = 0;
-    __syncthreads();
-    RC_PH(PH_N);  // slot 14
-    if (np < kFullThreshold) break;
+  if (tid < n_walk) {
+    const int root = s.wmeta[WM_ROOT + tid];
+    s.wst[(size_t)tid * CN + root] = (uint16_t)((uint32_t)root | kInTree);
   }
-  RC_PH(PH_W1);
-  // A global detection that found no cycle at all means the pointers ARE the tree (the
-  // normal end with the default hand-off threshold): phases 2-3 have nothing to do.
-  const bool complete = np == 0 && passes <= kMaxPasses;
-  if (!complete) {
-  // Phase 2 - which nodes already lead to the root?  After >= n steps of the functional
-  // graph every node sits on a cycle or at the root.
-  for (int u = tid; u < n; u += T) s.wgA[u] = (lid_t)succ_of(u);
+  for (int i = tid; i < n; i += T)  // a node without a neighbour inside the pair: the input plan is not contiguous
+    if (s.wdeg[i] == 0 && n > 1)
+      for (int w = 0; w < n_walk; ++w) s.wmeta[WM_ERR + w] = RC_ERR_DISCONNECTED;
   __syncthreads();
-  lid_t* __restrict__ A = s.wgA;
-  lid_t* __restrict__ B = s.wgB;
-  for (int span = 1; span < n; span <<= 1) {
-    for (int u = tid; u < n; u += T) B[u] = A[A[u]];
-    __syncthreads();
-    lid_t* tmp = A; A = B; B = tmp;
-  }
-  // ... and, for the sequential part, one packed state word per node - successor (bits
-  // 0-15), walk stamp (16-31; kInTree: leads to the root), draws consumed (32-47), end of the
-  // tabulated draws hi (48-63) - with every ring topped up to at least 5 unread draws by all
-  // threads.  One 64-bit load per walk step, one 16-bit look-up per pop.
-  unsigned long long* __restrict__ wst = s.wst;
-  for (int u = tid; u < n; u += T) {
-    const uint32_t cnt = s.wcnt[u];
-    uint32_t hi = cnt > (uint32_t)kTab ? ((cnt + 3u) & ~3u) : (uint32_t)kTab;
-    if (!replay && u != root)
-      while (hi - cnt <= 4u) { fill_block(u, hi >> 2); hi += 4u; }
-    const uint32_t stamp = (int)A[u] == root ? kInTree : 0u;
-    wst[u] = (unsigned long long)s.wnx[u] | ((unsigned long long)stamp << 16) |
-             ((unsigned long long)cnt << 32) | ((unsigned long long)hi << 48);
+  if (replay) {
+    if (tid == 0 && s.wmeta[WM_ERR] == 0) wilson_walk_recorded(c, st, tree_idx_base);
+  } else if ((tid >> 5) < n_walk) {
+    // one walker per warp: warp w issues from scheduler w % 4, the walkers of a CTA (and of
+    // the CTAs sharing the SM) spread over the four of them
+    wilson_walk_warp(c, st, tree_base, tid >> 5, prop_no);
   }
   __syncthreads();
-  RC_PH(PH_W2);
-  // Phase 3 - the remaining cycles hang on a handful of components that pop one after the
-  // other (the long tail of Wilson's algorithm is sequential): one thread finishes them as
-  // loop-erased walks over the current pointers, drawing only where a loop closes.  The
-  // loops are written for a lone thread: the next node's word is requested before the
-  // current one is dealt with, and only the half of a word that changes is stored.
-  if (tid == s.misc[M_WALKER]) {
-    // the walk proper, over accessors: M.ld(u) / M.st(u, w) the 64-bit word of node u,
-    // M.ldlo / M.stlo its low half (successor | stamp), M.tab(i) entry i of the draw rings
-    auto finish = [&](auto M) {
-      auto pop = [&](int v, unsigned long long w) {  // node v takes its next draw; returns new word
-        const uint32_t cnt = (uint32_t)(w >> 32) & 0xffffu;
-        uint32_t hi = (uint32_t)(w >> 48);
-        uint32_t nn;
-        if (replay) {
-          nn = (uint32_t)recorded(v, cnt);
-        } else {
-          if (cnt == hi) { fill_block(v, hi >> 2); hi += 4u; }
-          nn = M.tab(v * kTab + (int)(cnt & 7u));
-        }
-        return (unsigned long long)nn | ((unsigned long long)((cnt + 1u) & 0xffffu) << 32) |
-               ((unsigned long long)(hi & 0xffffu) << 48);  // stamp cleared
-      };
-      // a connected pair needs ~10-20 draws per node; a walk that cannot reach the root
-      // (disconnected input plan) is cut off instead of spinning for ever
-      int left = 2048 * n + 65536;  // n < 65536
-      int pops = 0;
-      for (int node = 0; node < n && left >= 0; ++node) {
-        unsigned long long w = M.ld(node);
-        if ((((uint32_t)w) >> 16) == kInTree) continue;
-        const uint32_t id = (uint32_t)(node % 0xfffe) + 1u;  // 1..0xfffe, never kInTree
-        const uint32_t idbits = id << 16;
-        int u = node;
-        for (;;) {  // w == word of u, u does not lead to the root yet
-          uint32_t lo = (uint32_t)w;
-          if ((lo >> 16) == id) {  // the walk closed a loop at u: pop it
-            int v = u;
-            unsigned long long wv = w;
-            do {
-              const int vn = (int)((uint32_t)wv & 0xffffu);
-              const unsigned long long wn = M.ld(vn);
-              M.st(v, pop(v, wv));
-              ++pops;
-              v = vn;
-              wv = wn;
-            } while (v != u);
-            lo = M.ldlo(u);
-          }
-          const int un = (int)(lo & 0xffffu);
-          w = M.ld(un);
-          M.stlo(u, (lo & 0xffffu) | idbits);
-          u = un;
-          if (--left < 0 || (((uint32_t)w) >> 16) == kInTree) break;
-        }
-        if (left < 0) break;
-        for (u = node;;) {
-          const uint32_t lo = M.ldlo(u);
-          if ((lo >> 16) == kInTree) break;
-          M.stlo(u, lo | 0xffff0000u);
-          u = (int)(lo & 0xffffu);
-        }
-      }
-      walk += pops;
-      if (left < 0 && !s.misc[M_ERR]) s.misc[M_ERR] = RC_ERR_DISCONNECTED;
-    };
-    if (__isShared(wst)) {
-      // shared-window offsets pinned in registers and explicit ld/st.shared: the loop must not
-      // re-derive the window address (a special-register read) in front of every load
-      struct Sh {
-        uint32_t w, t;
-        __device__ __forceinline__ unsigned long long ld(int u) const {
-          unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(w + 8u * (uint32_t)u) : "memory"); return v; }
-        __device__ __forceinline__ void st(int u, unsigned long long v) const {
-          asm volatile("st.shared.u64 [%0], %1;" :: "r"(w + 8u * (uint32_t)u), "l"(v) : "memory"); }
-        __device__ __forceinline__ uint32_t ldlo(int u) const {
-          uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(w + 8u * (uint32_t)u) : "memory"); return v; }
-        __device__ __forceinline__ void stlo(int u, uint32_t v) const {
-          asm volatile("st.shared.u32 [%0], %1;" :: "r"(w + 8u * (uint32_t)u), "r"(v) : "memory"); }
-        __device__ __forceinline__ uint32_t tab(int i) const {
-          uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(t + 2u * (uint32_t)i) : "memory"); return v; }
-      } M;
-      M.w = (uint32_t)__cvta_generic_to_shared(wst);
-      M.t = (uint32_t)__cvta_generic_to_shared(s.wtab);
-      asm volatile("" : "+r"(M.w), "+r"(M.t));
-      finish(M);
-    } else {  // spill mode: the arrays live in this CTA's global scratch
-      struct Gl {
-        unsigned long long* w; const lid_t* t;
-        __device__ __forceinline__ unsigned long long ld(int u) const { return w[u]; }
-        __device__ __forceinline__ void st(int u, unsigned long long v) const { w[u] = v; }
-        __device__ __forceinline__ uint32_t ldlo(int u) const { return reinterpret_cast<const uint32_t*>(w)[2 * u]; }
-        __device__ __forceinline__ void stlo(int u, uint32_t v) const { reinterpret_cast<uint32_t*>(w)[2 * u] = v; }
-        __device__ __forceinline__ uint32_t tab(int i) const { return t[i]; }
-      } M;
-      M.w = wst;
-      M.t = s.wtab;
-      finish(M);
+}
+
+// Subtree populations of tree w (parent pointers): every node adds its population to all
+// its proper ancestors.  O(n * depth) shared-memory atomics - a uniform spanning tree of a
+// planar pair is ~n^(5/8) deep - against the ~8 n dependent steps of the walk that made it.
+// Also: whas (nodes with a child), M_ROOTKIDS, and the number of balanced tree edges
+// (tree.py:411-423: the edge above u is balanced when the two sides are).
+__device__ int wilson_eval(Chain& c, const Step& st, int w, double ideal, double thr) {
+  const Params& p = *c.p;
+  const Smem& s = c.s;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int n = st.n;
+  const uint16_t* __restrict__ S = s.wst + (size_t)w * p.cap_nodes;
+  const int root = s.wmeta[WM_ROOT + w];
+  for (int i = tid; i < n; i += T) s.wsum[i] = s.pop[i];
+  for (int i = tid; i < (n + 31) >> 5; i += T) s.whas[i] = 0;
+  if (tid == 0) { s.misc[M_ROOTKIDS] = 0; s.misc[M_NBAL] = 0; }
+  __syncthreads();
+  for (int i = tid; i < n; i += T) {
+    if (i == root) continue;
+    const int x = s.pop[i];
+    int q = (int)(S[i] & kNext);
+    atomicOr(&s.whas[q >> 5], 1u << (q & 31));
+    if (q == root) atomicAdd(&s.misc[M_ROOTKIDS], 1);
+    while (q != root) {
+      atomicAdd(&s.wsum[q], x);
+      q = (int)(S[q] & kNext);
     }
   }
-  RC_PH(PH_W3);
   __syncthreads();
-  if (s.misc[M_ERR]) return s.misc[M_ERR];
-  }  // !complete
-  // the tree: edge (u, successor of u) for every node but the root; the slot of the
-  // successor in u's row gives the edge
-  for (int u = tid; u < n; u += T) {
-    walk += (u != root);  // the first draw of every node
-    if (u == root) continue;
-    const int nn = complete ? succ_of(u) : (int)(s.wst[u] & 0xffffu);
-    int j = -1;
-    for (int q = s.loff[u]; q < s.loff[u + 1]; ++q)
-      if (s.ladj[q] == nn) { j = s.ladje[q]; break; }
-    if (j >= 0) atomicOr(&s.tflag[j >> 5], 1u << (j & 31));  // else: tree_edge_list reports it
-  }
-  walk = warp_sum(walk);
-  if ((tid & 31) == 0 && walk) atomicAdd(&ctr[RC_CTR_WALK], walk);
+  int cnt = 0;
+  for (int i = tid; i < n; i += T) cnt += (i != root && balanced(s.wsum[i], st.tot, ideal, thr)) ? 1 : 0;
+  cnt = warp_sum(cnt);
+  if ((tid & 31) == 0 && cnt) atomicAdd(&s.misc[M_NBAL], cnt);
   __syncthreads();
-  return tree_edge_list(c, st);
+  return s.misc[M_NBAL];
 }
 
 // ---- P3: root the tree and compute every subtree population ----------------------------
@@ -1019,12 +1009,6 @@ __device__ int select_kth(Chain& c, int count, int kth, Pred pred) {
   return r;
 }
 
-__device__ __forceinline__ bool balanced(int tree_pop, int total_pop, double ideal, double thr) {
-  // tree.py:412-414, float64 as in the reference
-  return fabs(__dsub_rn((double)tree_pop, ideal)) <= thr &&
-         fabs(__dsub_rn((double)(total_pop - tree_pop), ideal)) <= thr;
-}
-
 // ---- P5: region-aware cut choice (tree.py:501-578); returns tree edge index --------------
 __device__ int choose_cut_by_weight(Chain& c, const Step& st, int policy, uint32_t tree_no,
                                     uint32_t prop_no, const uint32_t* rrank, double ideal, double thr) {
@@ -1097,6 +1081,74 @@ struct ProposalResult {
   int nbal;       // balanced cuts of the last tree
 };
 
+// Wilson: is local edge j an edge of the tree S (parent pointers)?  Returns the child
+// endpoint or -1.  (Two adjacent nodes cannot point at each other: the root points at itself.)
+__device__ __forceinline__ int wilson_tree_child(const Smem& s, const uint16_t* __restrict__ S, int j) {
+  const int a = s.eu[j], b = s.ev[j];
+  if ((int)(S[a] & kNext) == b) return a;
+  if ((int)(S[b] & kNext) == a) return b;
+  return -1;
+}
+
+// Commit of a proposal whose new side bitmap is in newb (bit i: node i takes the higher id b):
+// optional cut-edge acceptance (accept.py:19-35), labels, cut-edge bitmask, Tally.
+// Returns true when the proposal was committed.
+__device__ bool commit_proposal(Chain& c, const Step& st, int cut_count, long long pop_a, long long pop_b,
+                                uint32_t prop_no) {
+  const Params& p = *c.p;
+  const Smem& s = c.s;
+  const int tid = threadIdx.x, T = blockDim.x;
+  if (p.cfg.accept_rule == RC_ACCEPT_CUT_EDGE) {
+    // accept.py:19-35: the number of cut edges the proposal WOULD have, before anything is
+    // written; a rejected proposal leaves the state alone but still counts as a step
+    if (tid == 0) s.misc[M_DELTA] = 0;
+    __syncthreads();
+    int d = 0;
+    for (int j = tid; j < st.m; j += T) {
+      const int u = s.eu[j], v = s.ev[j];
+      const int was = ((s.oldb[u >> 5] >> (u & 31)) ^ (s.oldb[v >> 5] >> (v & 31))) & 1u;
+      const int now = ((s.newb[u >> 5] >> (u & 31)) ^ (s.newb[v >> 5] >> (v & 31))) & 1u;
+      d += now - was;
+    }
+    d = warp_sum(d);
+    if ((tid & 31) == 0 && d) atomicAdd(&s.misc[M_DELTA], d);
+    __syncthreads();
+    const int new_count = cut_count + s.misc[M_DELTA];
+    __syncthreads();
+    const double ratio = __ddiv_rn((double)cut_count, (double)new_count);
+    const RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_ACCEPT, 0, 0, prop_no, 0);
+    if (!(rc_unit_double(r.v[0], r.v[1]) < (ratio < 1.0 ? ratio : 1.0))) return false;  // step consumed, old state kept
+  }
+  if (tid == 0) s.misc[M_DELTA] = 0;
+  for (int i = tid; i < st.n; i += T) {  // partition/assignment.py:76-86
+    const bool nb = (s.newb[i >> 5] >> (i & 31)) & 1u, ob = (s.oldb[i >> 5] >> (i & 31)) & 1u;
+    if (nb != ob) c.assign[c.nodes[i]] = (uint8_t)(nb ? st.b : st.a);
+  }
+  __syncthreads();
+  int delta = 0;
+  for (int j = tid; j < st.m; j += T) {  // updaters/cut_edges.py:118-120
+    const int u = s.eu[j], v = s.ev[j];
+    const bool was = ((s.oldb[u >> 5] >> (u & 31)) ^ (s.oldb[v >> 5] >> (v & 31))) & 1u;
+    const bool now = ((s.newb[u >> 5] >> (u & 31)) ^ (s.newb[v >> 5] >> (v & 31))) & 1u;
+    if (now != was) {
+      const int eid = c.eids[j];
+      atomicXor(c.mask + (eid >> 5), 1u << (eid & 31));
+      delta += (int)now - (int)was;
+    }
+  }
+  delta = warp_sum(delta);
+  if ((tid & 31) == 0 && delta) atomicAdd(&s.misc[M_DELTA], delta);
+  __syncthreads();
+  if (tid == 0) {
+    c.tally[st.a] = pop_a;  // updaters/tally.py:162-165
+    c.tally[st.b] = pop_b;
+    p.st.d_cut_count[c.chain] = cut_count + s.misc[M_DELTA];
+    if (p.st.d_last_pair) { p.st.d_last_pair[2 * c.chain] = st.a; p.st.d_last_pair[2 * c.chain + 1] = st.b; }
+  }
+  __syncthreads();
+  return true;
+}
+
 // One recom proposal + validity + commit (tree_proposals.py:36-146, chain.py:186-195).
 template <bool kWilson>
 __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep* rs,
@@ -1125,8 +1177,9 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
   const uint32_t t0 = (rs && nr == 0 && n_rec > 0) ? (uint32_t)(n_rec - 1) : 0u;
   const int r0 = 0;  // tour root: local node 0 (any node will do)
   int tstar = -1, root = -1;
+  int wsel = 0, cut_child = -1;  // Wilson: winning walker, child endpoint of the chosen cut
   for (uint32_t retry = 0;; ++retry) {  // tree_proposals.py:103-138
-  if (resel && n_bad >= k * (k - 1) / 2) { res.status = RC_ERR_ALL_PAIRS_BAD; return res; }
+  if (resel && (n_bad >= k * (k - 1) / 2 || retry >= 64u * (uint32_t)(k * k))) { res.status = RC_ERR_ALL_PAIRS_BAD; return res; }
   // ---- P0
   int e;
   if (rs) {
@@ -1151,6 +1204,7 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
   if (res.status) return res;
   const int n = st.n, nt = n - 1;
   bool reselect = false;
+  uint32_t batch_lo = t0, batch_hi = t0;  // Wilson: trees [batch_lo, batch_hi) have been walked
   for (uint32_t tree_no = t0;; ++tree_no) {
     // tree.py:679-700 attempt accounting (see oracle/recom_oracle.c rco_bipartition)
     const long long attempts = nr > 0 ? (long long)tree_no * nr : (tree_no == t0 ? 0 : max_attempts);
@@ -1164,40 +1218,65 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
       return res;
     }
     if (rs && (int)tree_no >= n_rec) { res.status = RC_ERR_REPLAY; return res; }
-    constexpr bool wilson = kWilson;
-    const uint32_t* rrank = (rs && !wilson) ? p.rp.weight_rank + (rs->first_tree + tree_no) * (long long)p.g.E : nullptr;
-    // ---- P2
-    int rounds = 0;
-    if (wilson) res.status = wilson_tree(c, st, tree_no, prop_no, rs ? rs->first_tree + tree_no : 0, ctr);
-    else res.status = boruvka_mst(c, st, tree_no, prop_no, rrank, &rounds);
-    RC_PH(PH_TREE);
-    if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_ROUNDS] += rounds; }
-    res.trees = (int)tree_no + 1;
-    if (res.status) return res;
-    // tree.py:377: the root is drawn among tree nodes of degree > 1 (none: IndexError);
-    // only the two-node tree has none
-    if (n < 3) { res.status = RC_ERR_NO_ROOT; return res; }
-    // ---- P3
-    euler_subtree_pops(c, st, r0);
-    RC_PH(PH_EULER);
-    // ---- P4: balanced tree edges (cur[t] = population below edge t)
-    auto is_bal = [&](int t) { return balanced(s.cur[t], st.tot, ideal, thr); };
-    {
+    int nbal;
+    if constexpr (kWilson) {
+      // ---- P2b: the next batch of trees, one per lane of warp 0; examined in order
+      if (tree_no >= batch_hi) {
+        long long nw = p.walkers > 0 ? p.walkers : 1;
+        if (rs) nw = 1;  // a recorded tree is walked by one thread (wilson_walk_recorded)
+        if (nr > 0) nw = min(nw, (max_attempts - attempts + nr - 1) / nr);  // trees beyond max_attempts are never examined
+        else nw = 1;
+        wilson_walk(c, st, tree_no, (int)nw, prop_no, rs ? rs->first_tree + tree_no : 0);
+        batch_lo = tree_no;
+        batch_hi = tree_no + (uint32_t)nw;
+        if (tid == 0) ctr[RC_CTR_ROUNDS] += 1;  // Wilson: batches of concurrent walks
+        RC_PH(PH_TREE);
+      }
+      wsel = (int)(tree_no - batch_lo);
+      res.status = s.wmeta[WM_ERR + wsel];
+      if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_WALK] += s.wmeta[WM_DRAWS + wsel]; }
+      res.trees = (int)tree_no + 1;
+      if (res.status) return res;
+      if (n < 3) { res.status = RC_ERR_NO_ROOT; return res; }  // tree.py:377: no node of degree > 1
+      nbal = wilson_eval(c, st, wsel, ideal, thr);
+      RC_PH(PH_EULER);
+    } else {
+      const uint32_t* rrank = rs ? p.rp.weight_rank + (rs->first_tree + tree_no) * (long long)p.g.E : nullptr;
+      // ---- P2a
+      int rounds = 0;
+      res.status = boruvka_mst(c, st, tree_no, prop_no, rrank, &rounds);
+      RC_PH(PH_TREE);
+      if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_ROUNDS] += rounds; }
+      res.trees = (int)tree_no + 1;
+      if (res.status) return res;
+      // tree.py:377: the root is drawn among tree nodes of degree > 1 (none: IndexError);
+      // only the two-node tree has none
+      if (n < 3) { res.status = RC_ERR_NO_ROOT; return res; }
+      // ---- P3
+      euler_subtree_pops(c, st, r0);
+      RC_PH(PH_EULER);
+      // ---- P4: balanced tree edges (cur[t] = population below edge t)
       if (tid == 0) s.misc[M_NBAL] = 0;
       __syncthreads();
       int cnt = 0;
-      for (int t = tid; t < nt; t += T) cnt += is_bal(t) ? 1 : 0;
+      for (int t = tid; t < nt; t += T) cnt += balanced(s.cur[t], st.tot, ideal, thr) ? 1 : 0;
       cnt = warp_sum(cnt);
       if ((tid & 31) == 0 && cnt) atomicAdd(&s.misc[M_NBAL], cnt);
       __syncthreads();
+      nbal = s.misc[M_NBAL];
     }
-    const int nbal = s.misc[M_NBAL];
     RC_PH(PH_BALANCE);
     res.nbal = nbal;
     if (nbal > 0) {
       const bool last_rec = rs && (int)tree_no == n_rec - 1;
       if (rs && !last_rec) { res.status = RC_ERR_REPLAY; return res; }
-      auto internal = [&](int i) { return s.nxt[s.head[i]] != kNone; };  // tree degree > 1
+      const uint16_t* __restrict__ S = kWilson ? s.wst + (size_t)wsel * p.cap_nodes : nullptr;
+      const int wroot = kWilson ? s.wmeta[WM_ROOT + wsel] : 0;
+      const int rootkids = kWilson ? s.misc[M_ROOTKIDS] : 0;
+      auto internal = [&](int i) {  // tree degree > 1
+        if constexpr (kWilson) return i == wroot ? rootkids >= 2 : (bool)((s.whas[i >> 5] >> (i & 31)) & 1u);
+        else return s.nxt[s.head[i]] != kNone;
+      };
       // ---- root (tree.py:377): uniform over tree nodes of degree > 1, ascending node index
       if (last_rec) {
         const int gr = rs->root;
@@ -1216,16 +1295,38 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
         root = select_kth(c, n, (int)rc_below(r.v[0], r.v[1], (uint32_t)n_int), internal);
       }
       // ---- P5
-      const int policy = kWilson ? RC_CUT_UNIFORM : p.cfg.cut_policy;
-      if (rs && rs->cut_edge >= 0) {
-        const int want = rs->cut_edge;
-        tstar = select_kth(c, nt, 0, [&](int t) { return c.eids[s.te[t]] == want && is_bal(t); });
-        if (tstar < 0) { res.status = RC_ERR_REPLAY; return res; }
-      } else if (policy == RC_CUT_UNIFORM) {
-        RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_CUT, 0, tree_no, prop_no, 0);
-        tstar = select_kth(c, nt, (int)rc_below(r.v[0], r.v[1], (uint32_t)nbal), is_bal);
+      if constexpr (kWilson) {
+        // no random_weight and no node attributes on the Wilson tree: every branch of the
+        // reference's cut choice degenerates to a uniform pick (tree.py:540-545), taken in
+        // ascending edge id like the oracle's canonical order
+        auto bal_edge = [&](int j) {
+          const int ch = wilson_tree_child(s, S, j);
+          return ch >= 0 && balanced(s.wsum[ch], st.tot, ideal, thr);
+        };
+        int jstar;
+        if (rs && rs->cut_edge >= 0) {
+          const int want = rs->cut_edge;
+          jstar = select_kth(c, st.m, 0, [&](int j) { return c.eids[j] == want && bal_edge(j); });
+        } else {
+          RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_CUT, 0, tree_no, prop_no, 0);
+          jstar = select_kth(c, st.m, (int)rc_below(r.v[0], r.v[1], (uint32_t)nbal), bal_edge);
+        }
+        if (jstar < 0) { res.status = RC_ERR_REPLAY; return res; }
+        cut_child = wilson_tree_child(s, S, jstar);
       } else {
-        tstar = choose_cut_by_weight(c, st, policy, tree_no, prop_no, rrank, ideal, thr);
+        const uint32_t* rrank = rs ? p.rp.weight_rank + (rs->first_tree + tree_no) * (long long)p.g.E : nullptr;
+        auto is_bal = [&](int t) { return balanced(s.cur[t], st.tot, ideal, thr); };
+        const int policy = p.cfg.cut_policy;
+        if (rs && rs->cut_edge >= 0) {
+          const int want = rs->cut_edge;
+          tstar = select_kth(c, nt, 0, [&](int t) { return c.eids[s.te[t]] == want && is_bal(t); });
+          if (tstar < 0) { res.status = RC_ERR_REPLAY; return res; }
+        } else if (policy == RC_CUT_UNIFORM) {
+          RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_CUT, 0, tree_no, prop_no, 0);
+          tstar = select_kth(c, nt, (int)rc_below(r.v[0], r.v[1], (uint32_t)nbal), is_bal);
+        } else {
+          tstar = choose_cut_by_weight(c, st, policy, tree_no, prop_no, rrank, ideal, thr);
+        }
       }
       if (tid == 0) {
         ctr[RC_CTR_ATTEMPTS] += (int)min(attempts + 1, 0x7fffffffLL);
@@ -1244,13 +1345,39 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
   }  // pair loop
   RC_PH(PH_CHOOSE);
   // ---- P6: the side holding the reference's root keeps the lower id (tree.py:421, :947-950)
-  const int pa = s.P[2 * tstar], pb = s.P[2 * tstar + 1];
-  const int pd = min(pa, pb), pu = max(pa, pb);
-  auto below = [&](int i) { const int en = s.ent[i]; return en != 0xffff && en >= pd && en <= pu; };
-  const bool root_below = below(root);
-  const int child_pop = s.cur[tstar];
+  bool root_below;
+  int child_pop;
+  if constexpr (kWilson) {
+    const uint16_t* __restrict__ S = s.wst + (size_t)wsel * p.cap_nodes;
+    const int wroot = s.wmeta[WM_ROOT + wsel];
+    // below(i): i lies in the subtree under the cut edge - climb until the cut's child or the root
+    auto below = [&](int i) {
+      int q = i;
+      while (q != cut_child && q != wroot) q = (int)(S[q] & kNext);
+      return q == cut_child;
+    };
+    root_below = below(root);
+    child_pop = s.wsum[cut_child];
+    for (int i0 = 0; i0 < st.n; i0 += T) {  // side(i): cut away from the root's side -> higher id b
+      const int i = i0 + tid;
+      const uint32_t bal = __ballot_sync(0xffffffffu, i < st.n && (below(i) != root_below));
+      if (i < st.n && (tid & 31) == 0) s.newb[i >> 5] = bal;
+    }
+  } else {
+    const int pa = s.P[2 * tstar], pb = s.P[2 * tstar + 1];
+    const int pd = min(pa, pb), pu = max(pa, pb);
+    auto below = [&](int i) { const int en = s.ent[i]; return en != 0xffff && en >= pd && en <= pu; };
+    root_below = below(root);
+    child_pop = s.cur[tstar];
+    for (int i0 = 0; i0 < st.n; i0 += T) {
+      const int i = i0 + tid;
+      const uint32_t bal = __ballot_sync(0xffffffffu, i < st.n && (below(i) != root_below));
+      if (i < st.n && (tid & 31) == 0) s.newb[i >> 5] = bal;
+    }
+  }
   const long long pop_a = root_below ? (long long)child_pop : (long long)st.tot - child_pop;
   const long long pop_b = (long long)st.tot - pop_a;
+  __syncthreads();
   bool valid = true;
   if (p.cfg.pop_lower <= p.cfg.pop_upper) {  // constraints/bounds.py:25-28
     const double lo = (double)min(pop_a, pop_b), hi = (double)max(pop_a, pop_b);
@@ -1260,69 +1387,7 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
     if (tid == 0) ctr[RC_CTR_INVALID] += 1;
     return res;
   }
-  // side(i): node i is cut away from the root's side and takes the higher id b
-  auto side = [&](int i) { return below(i) != root_below; };
-  if (p.cfg.accept_rule == RC_ACCEPT_CUT_EDGE) {
-    // accept.py:19-35: the number of cut edges the proposal WOULD have, before anything is
-    // written; a rejected proposal leaves the state alone but still counts as a step
-    if (tid == 0) s.misc[M_DELTA] = 0;
-    for (int i0 = 0; i0 < st.n; i0 += T) {
-      const int i = i0 + tid;
-      const uint32_t bal = __ballot_sync(0xffffffffu, i < st.n && side(i));
-      if (i < st.n && (tid & 31) == 0) s.newb[i >> 5] = bal;
-    }
-    __syncthreads();
-    int d = 0;
-    for (int j = tid; j < st.m; j += T) {
-      const int u = s.eu[j], v = s.ev[j];
-      const int was = ((s.oldb[u >> 5] >> (u & 31)) ^ (s.oldb[v >> 5] >> (v & 31))) & 1u;
-      const int now = ((s.newb[u >> 5] >> (u & 31)) ^ (s.newb[v >> 5] >> (v & 31))) & 1u;
-      d += now - was;
-    }
-    d = warp_sum(d);
-    if ((tid & 31) == 0 && d) atomicAdd(&s.misc[M_DELTA], d);
-    __syncthreads();
-    const int new_count = cut_count + s.misc[M_DELTA];
-    __syncthreads();
-    const double ratio = __ddiv_rn((double)cut_count, (double)new_count);
-    const RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_ACCEPT, 0, 0, prop_no, 0);
-    if (!(rc_unit_double(r.v[0], r.v[1]) < (ratio < 1.0 ? ratio : 1.0))) {
-      res.accepted = 1;  // step consumed, old state kept
-      return res;
-    }
-  }
-  if (tid == 0) s.misc[M_DELTA] = 0;
-  for (int i0 = 0; i0 < st.n; i0 += T) {  // partition/assignment.py:76-86
-    const int i = i0 + tid;
-    const bool sd = i < st.n && side(i);
-    const uint32_t bal = __ballot_sync(0xffffffffu, sd);
-    if (i < st.n) {
-      if ((tid & 31) == 0) s.newb[i >> 5] = bal;
-      if (sd != (bool)((s.oldb[i >> 5] >> (i & 31)) & 1u)) c.assign[c.nodes[i]] = (uint8_t)(sd ? st.b : st.a);
-    }
-  }
-  __syncthreads();
-  int delta = 0;
-  for (int j = tid; j < st.m; j += T) {  // updaters/cut_edges.py:118-120
-    const int u = s.eu[j], v = s.ev[j];
-    const bool was = ((s.oldb[u >> 5] >> (u & 31)) ^ (s.oldb[v >> 5] >> (v & 31))) & 1u;
-    const bool now = ((s.newb[u >> 5] >> (u & 31)) ^ (s.newb[v >> 5] >> (v & 31))) & 1u;
-    if (now != was) {
-      const int eid = c.eids[j];
-      atomicXor(c.mask + (eid >> 5), 1u << (eid & 31));
-      delta += (int)now - (int)was;
-    }
-  }
-  delta = warp_sum(delta);
-  if ((tid & 31) == 0 && delta) atomicAdd(&s.misc[M_DELTA], delta);
-  __syncthreads();
-  if (tid == 0) {
-    c.tally[st.a] = pop_a;  // updaters/tally.py:162-165
-    c.tally[st.b] = pop_b;
-    p.st.d_cut_count[c.chain] = cut_count + s.misc[M_DELTA];
-    if (p.st.d_last_pair) { p.st.d_last_pair[2 * c.chain] = st.a; p.st.d_last_pair[2 * c.chain + 1] = st.b; }
-  }
-  __syncthreads();
+  commit_proposal(c, st, cut_count, pop_a, pop_b, prop_no);
   RC_PH(PH_COMMIT);
   res.accepted = 1;
   return res;
@@ -1386,41 +1451,48 @@ __device__ ProposalResult propose_reversible(Chain& c, uint32_t prop_no, int32_t
   res.status = gather_pair<true>(c, st, &d_sub);
   if (tid == 0) { ctr[RC_CTR_NODES] += st.n; ctr[RC_CTR_SLOTS] += d_sub; }
   if (res.status) return res;
-  const int n = st.n, nt = n - 1;
+  const int n = st.n;
   if (n < 3) { res.status = RC_ERR_NO_ROOT; return res; }
-  res.status = wilson_tree(c, st, 0, prop_no, 0, ctr);
-  if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_ATTEMPTS] += 1; }
+  wilson_walk(c, st, 0, 1, prop_no, 0);
+  res.status = s.wmeta[WM_ERR];
+  if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_ATTEMPTS] += 1; ctr[RC_CTR_WALK] += s.wmeta[WM_DRAWS]; }
   res.trees = 1;
   if (res.status) return res;
-  euler_subtree_pops(c, st, 0);
   const double ideal = p.cfg.pop_target;
   const double thr = __dmul_rn(ideal, p.cfg.epsilon);
-  auto is_bal = [&](int t) { return balanced(s.cur[t], st.tot, ideal, thr); };
-  if (tid == 0) { s.misc[M_NBAL] = 0; s.misc[M_NINT] = 0; }
+  const int nbal = wilson_eval(c, st, 0, ideal, thr);
+  const uint16_t* __restrict__ S = s.wst;
+  const int wroot = s.wmeta[WM_ROOT];
+  const int rootkids = s.misc[M_ROOTKIDS];
+  auto internal = [&](int i) { return i == wroot ? rootkids >= 2 : (bool)((s.whas[i >> 5] >> (i & 31)) & 1u); };
+  if (tid == 0) s.misc[M_NINT] = 0;
   __syncthreads();
-  auto internal = [&](int i) { return s.nxt[s.head[i]] != kNone; };
   {
-    int cb = 0, ci = 0;
-    for (int t = tid; t < nt; t += T) cb += is_bal(t) ? 1 : 0;
+    int ci = 0;
     for (int i = tid; i < n; i += T) ci += internal(i) ? 1 : 0;
-    cb = warp_sum(cb);
     ci = warp_sum(ci);
-    if ((tid & 31) == 0) { if (cb) atomicAdd(&s.misc[M_NBAL], cb); if (ci) atomicAdd(&s.misc[M_NINT], ci); }
+    if ((tid & 31) == 0 && ci) atomicAdd(&s.misc[M_NINT], ci);
   }
   __syncthreads();
-  const int nbal = s.misc[M_NBAL], n_int = s.misc[M_NINT];
+  const int n_int = s.misc[M_NINT];
   res.nbal = nbal;
   if (nbal > M) { res.status = RC_ERR_REVERSIBILITY; return res; }  // tree_proposals.py:205-209
   if (nbal == 0) return res;                                           // self-loop: no balance edge
   const RcPhilox rr = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_ROOT, 0, 0, prop_no, 0);
   const int root = select_kth(c, n, (int)rc_below(rr.v[0], rr.v[1], (uint32_t)n_int), internal);
   const RcPhilox rc_ = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_CUT, 0, 0, prop_no, 0);
-  const int tstar = select_kth(c, nt, (int)rc_below(rc_.v[0], rc_.v[1], (uint32_t)nbal), is_bal);
-  const int pa = s.P[2 * tstar], pb = s.P[2 * tstar + 1];
-  const int pd = min(pa, pb), pu = max(pa, pb);
-  auto below = [&](int i) { const int en = s.ent[i]; return en != 0xffff && en >= pd && en <= pu; };
+  const int jstar = select_kth(c, st.m, (int)rc_below(rc_.v[0], rc_.v[1], (uint32_t)nbal), [&](int j) {
+    const int ch = wilson_tree_child(s, S, j);
+    return ch >= 0 && balanced(s.wsum[ch], st.tot, ideal, thr);
+  });
+  const int cut_child = wilson_tree_child(s, S, jstar);
+  auto below = [&](int i) {
+    int q = i;
+    while (q != cut_child && q != wroot) q = (int)(S[q] & kNext);
+    return q == cut_child;
+  };
   const bool root_below = below(root);
-  const int child_pop = s.cur[tstar];
+  const int child_pop = s.wsum[cut_child];
   const long long pop_root = root_below ? (long long)child_pop : (long long)st.tot - child_pop;
   const long long pop_other = (long long)st.tot - pop_root;
   // new side bitmap: bit = node carries st.b afterwards
@@ -1493,12 +1565,16 @@ __device__ __forceinline__ void st_release(int32_t* p, int v) {
 // and a slow step delays only its own chain.  Replay mode (TEST HOOK) is one CTA walking one
 // chain through the record.
 template <bool kWilson, bool kSpill>
-__global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
+__global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_step_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Chain c;
   c.p = &p;
-  smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R, kWilson,
-              kSpill ? p.spill + (size_t)blockIdx.x * p.spill_stride : nullptr);
+  if constexpr (kWilson)
+    wilson_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R, p.walkers, p.nbr_shift, p.wilson_level,
+                  p.spill + (size_t)blockIdx.x * p.spill_stride, p.cold + (size_t)blockIdx.x * p.cold_stride);
+  else
+    smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R,
+                kSpill ? p.spill + (size_t)blockIdx.x * p.spill_stride : nullptr);
   const int tid = threadIdx.x;
   c.nodes = p.nodes + (size_t)blockIdx.x * p.cap_nodes;
   c.eids = p.eids + (size_t)blockIdx.x * p.cap_edges;
@@ -1509,15 +1585,12 @@ __global__ void __launch_bounds__(512, 2) recom_step_kernel(const Params p) {
 #endif
   int32_t* ctr = c.s.misc + M_CTR;  // [RC_N_COUNTERS]
   if (tid < RC_N_COUNTERS) ctr[tid] = 0;
-  if (tid == 0) {
-    // Long single-thread sections (Wilson's sequential tail) run in a different warp in each
-    // of the CTAs that share an SM: warp w issues from scheduler w % 4, and lone threads of
-    // co-resident CTAs that all sit in warp 0 would queue on one scheduler.
+  if (kWilson && tid == 0) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     const int slot = atomicAdd(p.sm_slots + (smid & 1023u), 1);
     const int n_warps = (int)blockDim.x >> 5;
-    c.s.misc[M_WALKER] = 32 * (slot % (n_warps < 4 ? n_warps : 4));
+    c.s.misc[M_WALKER] = slot % (n_warps < 4 ? n_warps : 4);
   }
   __syncthreads();
   const bool replay = p.rp.n_steps > 0;
@@ -1640,7 +1713,7 @@ __global__ void __launch_bounds__(512, 2) seed_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Chain c;
   c.p = &p;
-  smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R, false,
+  smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R,
               kSpill ? p.spill + (size_t)blockIdx.x * p.spill_stride : nullptr);
   const Smem& s = c.s;
   const int tid = threadIdx.x, T = blockDim.x;

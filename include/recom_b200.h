@@ -111,9 +111,10 @@ typedef struct RcConfig {
   int32_t accept_rule;        /* RC_ACCEPT_*: MarkovChain(accept=)  chain.py:192        */
   int32_t proposal_kind;      /* RC_PROPOSAL_*                                          */
   int32_t rev_M;              /* reversible_recom(M=): bound on the number of balanced cuts */
-  int32_t wilson_handoff;     /* RC_TREE_WILSON tuning / test knob: hand the tree to the sequential
-                               * finish once a parallel pass pops cycles on fewer threads than this;
-                               * 0 = default (2: the parallel passes run to the end)              */
+  int32_t wilson_walkers;     /* RC_TREE_WILSON: spanning trees t, t+1, ... of one bipartition_tree
+                               * call (tree.py:679-718) drawn concurrently, one random walk per warp;
+                               * the lowest tree number with a balanced cut wins, so the result does
+                               * not depend on it.  1..8; 0 = engine picks                        */
 } RcConfig;
 
 /* ---- chain state, resident in HBM, owned by the caller --------------------------- */
@@ -272,6 +273,8 @@ typedef struct RcEngineInfo {
   int32_t cap_nodes, cap_edges, threads_per_cta, ctas_per_sm, n_sms, grid;
   int64_t smem_bytes, scratch_bytes;
   int64_t kernel_launches; /* launches of this library's kernels so far              */
+  int32_t wilson_walkers;  /* RC_TREE_WILSON: trees walked concurrently per chain-step  */
+  int32_t spill;           /* 1: a merged pair's working arrays live in global scratch  */
 } RcEngineInfo;
 int rc_engine_info(RcEngine* e, RcEngineInfo* out);
 

@@ -32,10 +32,14 @@ enum {
   RC_DRAW_CUT = 4,    /* random.choice(cuts) (tree.py:545)                              */
   RC_DRAW_WROOT = 5,  /* Wilson root (tree.py:112)                                      */
   RC_DRAW_ACCEPT = 7, /* accept.py:35 random.random() of cut_edge_accept                 */
-  RC_DRAW_WALK = 6    /* Wilson successor draw j at node u (tree.py:119): index = rank of u
-                         among the nodes of the merged pair (ascending node index),
-                         sub = j >> 2, word j & 3; the value picks among u's neighbours
-                         inside the pair in ascending node index                       */
+  RC_DRAW_WALK = 6    /* Wilson successor draws (tree.py:119): draw t of a tree, t counting the
+                         draws in the order the loop of tree.py:116-125 makes them when the
+                         start nodes are taken in ascending node index and every walk runs to
+                         its end: index = t >> 2, word t & 3; the value picks among the current
+                         node's neighbours inside the pair in ascending node index.  (The walk
+                         is a sequential chain on any machine - the device runs one walk per
+                         lane - so the draw need not be a function of the node, which keeps the
+                         generator off the walk's dependency chain.)                    */
 };
 
 typedef struct RcPhilox { uint32_t v[4]; } RcPhilox;

@@ -249,8 +249,8 @@ static int sub_neighbors(const RcGraph* g, const RcoWork* w, int i, int32_t* out
   return d;
 }
 
-/* tree.py:112-132 uniform_spanning_tree (Wilson).  Draw j at node u is a function of
- * (u, j) only, so the visiting order of the outer loop is immaterial. */
+/* tree.py:112-132 uniform_spanning_tree (Wilson).  Free-running: successor draw t of the
+ * tree (recom_rng.h RC_DRAW_WALK), start nodes in ascending node index. */
 static int rco_wilson(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t chain,
                       uint32_t tree_no, uint32_t prop_no, const RcReplay* rp, int64_t tree_idx,
                       int64_t* walk_draws) {
@@ -267,6 +267,7 @@ static int rco_wilson(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t 
   memset(w->in_tree, 0, (size_t)n);
   memset(w->draws, 0, (size_t)n * 4);
   w->in_tree[root] = 1; w->next[root] = -1;
+  uint32_t t = 0;
   for (int node = 0; node < n; ++node) {
     int u = node;
     while (!w->in_tree[u]) {
@@ -281,9 +282,9 @@ static int rco_wilson(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t 
       } else {
         int d = sub_neighbors(g, w, u, nb, NULL);
         if (d > 512) return RC_ERR_CAPACITY;
-        RcPhilox p = rc_draw(c->seed, chain, RC_DRAW_WALK, (uint32_t)u, tree_no,
-                             prop_no, j >> 2);
-        v = nb[rc_below32(p.v[j & 3], (uint32_t)d)];
+        RcPhilox p = rc_draw(c->seed, chain, RC_DRAW_WALK, t >> 2, tree_no, prop_no, 0);
+        v = nb[rc_below32(p.v[t & 3], (uint32_t)d)];
+        ++t;
       }
       ++*walk_draws;
       w->next[u] = v;

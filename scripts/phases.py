@@ -18,13 +18,22 @@ ap.add_argument("--chain-steps", type=int, default=8)
 ap.add_argument("--cap-nodes", type=int, default=0)
 ap.add_argument("--cap-edges", type=int, default=0)
 ap.add_argument("--wilson", action="store_true")
+ap.add_argument("--seed", type=int, default=5)
+ap.add_argument("--walkers", type=int, default=0)
+ap.add_argument("--threads", type=int, default=0)
 a = ap.parse_args()
-kw = dict(n_chains=a.chains, seed=5, cap_nodes=a.cap_nodes, cap_edges=a.cap_edges)
+kw = dict(n_chains=a.chains, seed=a.seed, cap_nodes=a.cap_nodes, cap_edges=a.cap_edges)
+if a.walkers:
+    kw["wilson_walkers"] = a.walkers
+if a.threads:
+    kw["threads_per_cta"] = a.threads
 if a.wilson:
     kw["tree_kind"] = _abi.RC_TREE_WILSON
 csr, plan, cfg = getattr(workloads, a.workload)(**kw)
 eng = Engine(csr, cfg, plan)
 eng.run(4).synchronize()
+ctr0 = eng.counters.sum(0).cpu().numpy()
+step0 = eng.step_no.sum().item()
 eng.run(a.chain_steps).synchronize()
 ms = eng.last_run_ms()
 out = (C.c_ulonglong * 16)()
@@ -34,8 +43,11 @@ names = ["to-pick", "pick", "gather", "tree", "euler", "balance", "choose", "com
 tot = sum(out[:14]) or 1
 info = eng.info()
 steps = a.chains * a.chain_steps
-ctr = eng.counters.sum(0).cpu().numpy()
-print("  trees/step %.2f  walk draws/tree %.0f  mean n_sub %.0f" % (ctr[0] / max(eng.step_no.sum().item(), 1), ctr[6] / max(ctr[0], 1), ctr[2] / max(eng.step_no.sum().item(), 1)))
+ctr = eng.counters.sum(0).cpu().numpy() - ctr0
+if a.wilson:
+    print("  walk loop: %.1f cycles per trip, %d trips per batch" % (out[11] / max(out[12], 1), out[12] / max(ctr[7], 1)))
+    print("  walk batches %d, tree-phase cycles per batch %.0f, per draw of one lane %.1f" % (ctr[7], out[3] / max(ctr[7], 1), out[3] / max(ctr[7], 1) / max(ctr[6] / max(ctr[0], 1), 1)))
+print("  trees/step %.2f  walk draws/tree %.0f  mean n_sub %.0f" % (ctr[0] / max(eng.step_no.sum().item() - step0, 1), ctr[6] / max(ctr[0], 1), ctr[2] / max(eng.step_no.sum().item() - step0, 1)))
 print(f"{a.workload} wilson={a.wilson} chains={a.chains} steps/chain={a.chain_steps}: {ms:.2f} ms, "
       f"{steps / ms * 1e3:.0f} steps/s, smem {info.smem_bytes} B, ctas/sm {info.ctas_per_sm}, grid {info.grid}")
 names.append("wilson global detections" if a.wilson else "slot14")

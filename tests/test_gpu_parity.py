@@ -45,14 +45,14 @@ def test_replay_bit_exact_with_reference(name):
                  eng.cut_mask.cpu().numpy(), eng.cut_count.cpu().numpy())
 
 
-@pytest.mark.parametrize("handoff", [0, 100000])
+@pytest.mark.parametrize("walkers", [0, 1])
 @pytest.mark.parametrize("name", _golden.names("wilson"))
-def test_wilson_replay_bit_exact_with_reference(name, handoff):
+def test_wilson_replay_bit_exact_with_reference(name, walkers):
     """uniform_spanning_tree (tree.py:97-132): the reference's recorded per-node successor
-    draws, replayed through the device's parallel cycle popping, give the reference's
-    assignment after every step (handoff = 100000: through the sequential finish alone)."""
+    draws, replayed through the device's lane walkers (the recorded trees of a step walked
+    concurrently, or one at a time), give the reference's assignment after every step."""
     g = _golden.load(name)
-    g.cfg.wilson_handoff = handoff
+    g.cfg.wilson_walkers = walkers
     eng = _engine(g.csr, g.cfg, g.init_assignment)
     trace, info = eng.replay(g.rec)
     assert (info[:, 3] == 0).all(), [_abi.STATUS_NAMES.get(int(x)) for x in info[:, 3]]
@@ -66,17 +66,16 @@ def test_wilson_replay_bit_exact_with_reference(name, handoff):
                  eng.cut_mask.cpu().numpy(), eng.cut_count.cpu().numpy())
 
 
-@pytest.mark.parametrize("handoff", [0, 16, 100000])
-@pytest.mark.parametrize("name", _golden.names("wilson"))
-def test_wilson_free_run_bit_exact_with_oracle(name, handoff):
-    """handoff: parallel cycle popping to the end (default), an early hand-over to the
-    sequential finish, and (no parallel pass ever pops enough) the sequential finish alone -
-    the tree and the per-node draw counts are the same whatever the popping order."""
+@pytest.mark.parametrize("walkers", [0, 1, 7])
+@pytest.mark.parametrize("name", [n for n in _golden.names("wilson") if "200000" not in n])
+def test_wilson_free_run_bit_exact_with_oracle(name, walkers):
+    """walkers: how many trees of one bipartition_tree call are walked concurrently - the
+    state after every step, the tree counts and the per-tree draw counts are the same."""
     g = _golden.load(name)
     cfg = g.cfg
     cfg.n_chains = 16
     cfg.seed = 4321
-    cfg.wilson_handoff = handoff
+    cfg.wilson_walkers = walkers
     eng = _free_run_vs_oracle(g.csr, g.init_assignment, cfg, 30)
     from oracle import oracle  # walk-step counts agree as well
 
@@ -84,10 +83,10 @@ def test_wilson_free_run_bit_exact_with_oracle(name, handoff):
     assert np.array_equal(eng.counters.cpu().numpy()[:, _abi.RC_CTR_WALK], ora.counters[:, _abi.RC_CTR_WALK])
 
 
-@pytest.mark.parametrize("handoff", [0, 32])
-def test_wilson_free_run_config3(handoff):
+@pytest.mark.parametrize("walkers", [0, 2])
+def test_wilson_free_run_config3(walkers):
     csr, plan, cfg = workloads.config3(n_chains=16, seed=21, tree_kind=_abi.RC_TREE_WILSON,
-                                       wilson_handoff=handoff)
+                                       wilson_walkers=walkers)
     _free_run_vs_oracle(csr, plan, cfg, 10)
 
 
