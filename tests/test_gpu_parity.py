@@ -270,7 +270,19 @@ def test_spill_mode_bit_exact_with_oracle():
         csr, plan, cfg = workloads.config3(n_chains=24, seed=31, tree_kind=tree_kind,
                                            cap_nodes=9000, cap_edges=26976)
         eng = _free_run_vs_oracle(csr, plan, cfg, 12)
-        assert eng.info().smem_bytes < 16 * 1024  # only the membership bitmap stays on chip
+        if tree_kind == _abi.RC_TREE_MST:
+            assert eng.info().smem_bytes < 16 * 1024  # only the membership bitmap stays on chip
+        else:
+            assert eng.info().spill == 1  # walker state on chip, the adjacency in the CTA's L2 block
+
+
+def test_wilson_all_in_l2_bit_exact_with_oracle():
+    """Merged pairs of 30k nodes (a 240 x 250 grid in quadrants): neither the adjacency nor the
+    walkers' state fits shared memory (placement level 2); the walks run from the CTA's global block."""
+    csr, plan, cfg = workloads.grid_workload(240, 250, 4, 0.1, 4, seed=5, tree_kind=_abi.RC_TREE_WILSON,
+                                             cap_nodes=32000, cap_edges=65000)
+    eng = _free_run_vs_oracle(csr, plan, cfg, 2)
+    assert eng.info().spill == 2
 
 
 def test_config4_wilson_200k_nodes():
