@@ -2,7 +2,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <new>
+#include <vector>
 
 #include "recom_kernels.cu"
 #include "recom_stats.cu"
@@ -141,10 +143,29 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   // caps: merged pair of two districts, with head-room (RC_ERR_CAPACITY if exceeded)
   const int k = cfg->n_districts;
   int cap_nodes = cfg->cap_nodes > 0 ? cfg->cap_nodes : (int)(2.4 * N / k) + 32;
+  int maxdeg = 0;
+  for (int v = 0; v < N; ++v) maxdeg = g->row_ptr[v + 1] - g->row_ptr[v] > maxdeg ? g->row_ptr[v + 1] - g->row_ptr[v] : maxdeg;
+  bool tight = false;
+  if (cfg->cap_nodes <= 0 && cfg->pop_lower <= cfg->pop_upper) {
+    // With the chain's population Bounds in force no district ever holds more nodes than fit
+    // under pop_upper when the smallest populations are taken first: a rigorous cap (it is the
+    // one that binds on a grid of unit populations: 2 x 1050 nodes at BASELINE config 2, where
+    // the 2.4 N / k rule allows 2432), and every KB of shared memory decides how many CTAs fit
+    std::vector<int32_t> ps(g->pop, g->pop + N);
+    std::sort(ps.begin(), ps.end());
+    double acc = 0.0;
+    int cnt = 0;
+    while (cnt < N && acc + (double)ps[cnt] <= cfg->pop_upper) acc += (double)ps[cnt++];
+    if (2 * cnt + 8 < cap_nodes) { cap_nodes = 2 * cnt + 8; tight = true; }
+  }
   if (cap_nodes > N) cap_nodes = N;
   if (cap_nodes > rc::kMaxLocal) cap_nodes = rc::kMaxLocal;
   int cap_edges = cfg->cap_edges > 0 ? cfg->cap_edges
                                      : (int)(1.02 * cap_nodes * ((double)E / N)) + 64;
+  if (cfg->cap_edges <= 0 && tight) {  // a pair of cap_nodes nodes has at most cap_nodes * maxdeg / 2 edges
+    const long long by_deg = (long long)cap_nodes * maxdeg / 2;
+    if (by_deg < cap_edges) cap_edges = (int)by_deg;
+  }
   if (cap_edges > E) cap_edges = E;
   if (cap_edges > 65535) cap_edges = 65535;
   cap_nodes = (cap_nodes + 7) & ~7;
@@ -168,8 +189,6 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
     // (P(a tree has a balanced cut) ~ 0.25-0.5).  reversible_recom draws ONE tree per proposal.
     // adjacency slots per node kept in the hot tier: enough for every node of a grid (4), else 8
     // (a planar triangulation has mean degree < 6; longer rows are read from the cold tier)
-    int maxdeg = 0;
-    for (int v = 0; v < N; ++v) maxdeg = g->row_ptr[v + 1] - g->row_ptr[v] > maxdeg ? g->row_ptr[v + 1] - g->row_ptr[v] : maxdeg;
     const int sh = maxdeg <= 4 ? 2 : 3;
     p.nbr_shift = sh;
     int W = cfg->wilson_walkers > 0 ? cfg->wilson_walkers : 4;
@@ -192,7 +211,8 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
     total += glob;
     e->cold_bytes = (cold + 255) & ~size_t(255);
   } else {
-    total = rc::smem_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R, nullptr, &split);
+    total = rc::smem_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R, nullptr, nullptr, &split, &cold);
+    e->cold_bytes = (cold + 255) & ~size_t(255);
   }
   // a merged pair that does not fit an SM's shared memory keeps its working arrays in a
   // per-CTA global scratch block instead (L2 resident): same code, generic pointers

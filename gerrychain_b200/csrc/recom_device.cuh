@@ -63,9 +63,8 @@ struct Smem {
   // whole step
   uint32_t* mbits;   // [NW] membership bitmap of the merged pair over global node ids
   lid_t* mpref;      // [NW] exclusive prefix popcount: local id = mpref[w] + popc(below)
-  int32_t* pop;      // [CN]
-  lid_t* eu;         // [CE]
-  lid_t* ev;         // [CE]
+  int32_t* pop;      // [CN]   population of local node i                      (cold tier)
+  uint32_t* euv;     // [CE]   local edge j = (u | v << 16), u < v, ascending edge id  (cold tier)
   uint32_t* tflag;   // [CE/32] tree-edge bitmap over local edges
   uint32_t* oldb;    // [CN/32] bit i: local node i carries the higher district id b
   uint32_t* newb;    // [CN/32] the same after the proposed cut
@@ -94,6 +93,7 @@ struct Smem {
   lid_t* vlB;        // [CN/2+2] live components, pong
   // Euler-tour phase (aliases the spanning-tree phase)
   lid_t* te;         // [CN] local edge index of tree edge t (ascending)
+  uint32_t* tuv;     // [CN] its endpoints (u | v << 16): the tour never goes back to the edge list
   uint32_t* head;    // [CN] first out-arc of a node (linked adjacency)
   lid_t* nxt;        // [2CN] next out-arc of the same node
   lid_t* succ;       // [2CN] tour successor of an arc
@@ -108,13 +108,18 @@ struct Smem {
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
-// N: nodes of the whole graph, CN/CE: caps of a merged pair, R: region columns.
-// The first three arrays (misc, membership bitmap, its prefix) always live in shared memory
-// at `base`; the rest follows them there, or - when a merged pair does not fit the 227 KB
-// of an SM (spill mode) - sits in a per-CTA global scratch block at `big` (L2 resident).
-// Returns the total size; *split = size of the always-shared part.  (MST kernels.)
+// N: nodes of the whole graph, CN/CE: caps of a merged pair, R: region columns.  (MST kernels.)
+// Tiers: `core` (misc, membership bitmap + prefix) always in shared memory at `base`; `hot` -
+// the spanning-tree and Euler-tour arrays, which alias each other - in shared memory behind
+// the core, or - when a merged pair does not fit the 227 KB of an SM (spill mode) - in a
+// per-CTA global scratch block at `big` (L2 resident); `cold` - what is only streamed
+// through, in edge or node order (populations, the pair's edge list, region classes) - in the
+// CTA's global block at `cold`, read through L2: every KB of shared memory not spent on
+// them is a step closer to one more resident CTA, and the step is latency bound.
+// Returns core + hot; *split_out = core, *cold_out = the cold bytes.
 __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int N, int CN, int CE, int R,
-                                              unsigned char* big = nullptr, size_t* split_out = nullptr) {
+                                              unsigned char* big, unsigned char* cold,
+                                              size_t* split_out = nullptr, size_t* cold_out = nullptr) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return r; };
   const int NW = (N + 31) / 32;
@@ -123,13 +128,9 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
   size_t o_mpref = take(size_t(NW) * 2);
   const size_t split = o;
   if (split_out) *split_out = split;
-  size_t o_pop = take(size_t(CN) * 4);
-  size_t o_eu = take(size_t(CE) * 2);
-  size_t o_ev = take(size_t(CE) * 2);
   size_t o_tfl = take(size_t((CE + 31) / 32) * 4);
   size_t o_oldb = take(size_t((CN + 31) / 32) * 4);
   size_t o_newb = take(size_t((CN + 31) / 32) * 4);
-  size_t o_ecls = take(R > 0 ? size_t(CE) : 0);
   size_t phase = o;
   // spanning-tree phase
   size_t o_key = take(size_t(CE) * 4);
@@ -145,28 +146,29 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
   o = phase;
   const int spCap = (2 * CN) / 8 + 4;
   size_t o_te = take(size_t(CN) * 2);
+  size_t o_tuv = take(size_t(CN) * 4);
   size_t o_head = take(size_t(CN) * 4);
   size_t o_nxt = take(size_t(2 * CN) * 2);
   size_t o_succ = take(size_t(2 * CN) * 2);
   size_t o_P = take(size_t(2 * CN) * 2);
   size_t o_W = take(size_t(2 * CN) * 4);
   size_t o_spX = take(size_t(2 * spCap) * 4);
-  size_t o_spY = take(size_t(2 * spCap) * 4);
-  size_t o_ent = take(size_t(CN) * 2);
+  size_t o_spY = take(size_t(2 * spCap) * 4);  // ent (2 CN bytes, written when the ranking is done) aliases it
   size_t end_b = o;
+  o = 0;
+  size_t c_pop = take(size_t(CN) * 4);
+  size_t c_euv = take(size_t(CE) * 4);
+  size_t c_ecls = take(R > 0 ? size_t(CE) : 0);
+  if (cold_out) *cold_out = o;
   if (s) {
     *s = Smem{};
     s->misc = (int32_t*)(base + o_misc);
     s->mbits = (uint32_t*)(base + o_mbits);
     s->mpref = (lid_t*)(base + o_mpref);
     if (big) base = big - split;  // the offsets below are relative to the start of the layout
-    s->pop = (int32_t*)(base + o_pop);
-    s->eu = (lid_t*)(base + o_eu);
-    s->ev = (lid_t*)(base + o_ev);
     s->tflag = (uint32_t*)(base + o_tfl);
     s->oldb = (uint32_t*)(base + o_oldb);
     s->newb = (uint32_t*)(base + o_newb);
-    s->ecls = (uint8_t*)(base + o_ecls);
     s->key = (uint32_t*)(base + o_key);
     s->lab = (uint32_t*)(base + o_lab);
     s->lj = (lid_t*)(base + o_lj);
@@ -176,6 +178,7 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
     s->vlA = (lid_t*)(base + o_vlA);
     s->vlB = (lid_t*)(base + o_vlB);
     s->te = (lid_t*)(base + o_te);
+    s->tuv = (uint32_t*)(base + o_tuv);
     s->head = (uint32_t*)(base + o_head);
     s->nxt = (lid_t*)(base + o_nxt);
     s->succ = (lid_t*)(base + o_succ);
@@ -184,8 +187,11 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
     s->W = (int32_t*)(base + o_W);
     s->spX = (uint32_t*)(base + o_spX);
     s->spY = (int32_t*)(base + o_spY);
-    s->ent = (lid_t*)(base + o_ent);
+    s->ent = (lid_t*)(base + o_spY);
     s->spCap = spCap;
+    s->pop = (int32_t*)(cold + c_pop);
+    s->euv = (uint32_t*)(cold + c_euv);
+    s->ecls = (uint8_t*)(cold + c_ecls);
   }
   return end_a > end_b ? end_a : end_b;
 }
@@ -224,8 +230,7 @@ __host__ __device__ inline size_t wilson_layout(Smem* s, unsigned char* base, in
   if (glob_out) *glob_out = a_end - smem;
   o = 0;
   size_t c_pop = take(size_t(CN) * 4);
-  size_t c_eu = take(size_t(CE) * 2);
-  size_t c_ev = take(size_t(CE) * 2);
+  size_t c_euv = take(size_t(CE) * 4);
   size_t c_ecls = take(R > 0 ? size_t(CE) : 0);
   if (cold_out) *cold_out = o;
   if (s) {
@@ -247,8 +252,7 @@ __host__ __device__ inline size_t wilson_layout(Smem* s, unsigned char* base, in
     s->nbr = (uint32_t*)(ha + o_nbr);
     s->wdeg = (uint16_t*)(ha + o_wdeg);
     s->pop = (int32_t*)(cold + c_pop);
-    s->eu = (lid_t*)(cold + c_eu);
-    s->ev = (lid_t*)(cold + c_ev);
+    s->euv = (uint32_t*)(cold + c_euv);
     s->ecls = (uint8_t*)(cold + c_ecls);
   }
   return smem;

@@ -127,7 +127,7 @@ __device__ int build_local_adjacency(Chain& c, const Step& st) {
   for (int i = tid; i < n; i += T) s.wtmp[i] = 0;
   if (tid == 0) s.misc[M_CNT] = n;  // next spare row
   __syncthreads();
-  for (int j = tid; j < m; j += T) { atomicAdd(&s.wtmp[s.eu[j]], 1u); atomicAdd(&s.wtmp[s.ev[j]], 1u); }
+  for (int j = tid; j < m; j += T) { const uint32_t uv = s.euv[j]; atomicAdd(&s.wtmp[uv & 0xffffu], 1u); atomicAdd(&s.wtmp[uv >> 16], 1u); }
   __syncthreads();
   for (int i = tid; i < n; i += T) {
     const int d = (int)s.wtmp[i];
@@ -151,7 +151,8 @@ __device__ int build_local_adjacency(Chain& c, const Step& st) {
   __syncthreads();
   if (s.misc[M_CNT] > rows_cap) return RC_ERR_CAPACITY;  // too many high-degree nodes for the spare rows
   for (int j = tid; j < m; j += T) {
-    const int u = s.eu[j], v = s.ev[j];
+    const uint32_t uv = s.euv[j];
+    const int u = (int)(uv & 0xffffu), v = (int)(uv >> 16);
     *nbr_slot(s, u, s.wdeg[u], (int)atomicAdd(&s.wtmp[u], 1u), sh) = (uint32_t)v;
     *nbr_slot(s, v, s.wdeg[v], (int)atomicAdd(&s.wtmp[v], 1u), sh) = (uint32_t)u;
   }
@@ -266,8 +267,7 @@ __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
     m += tot;
     if (cnt && j + cnt <= p.cap_edges) {
       auto emit = [&](int sl, int h, int eid) {
-        s.eu[j] = (lid_t)i;
-        s.ev[j] = (lid_t)local_id(s, h);
+        s.euv[j] = (uint32_t)i | ((uint32_t)local_id(s, h) << 16);
         c.eids[j] = eid;
         if (R > 0) {  // tree.py:80-87: surcharged when the labels differ or either is None
           uint32_t cls = 0;
@@ -340,6 +340,9 @@ __device__ int tree_edge_list(Chain& c, const Step& st) {
     while (x) { s.te[t++] = (lid_t)(u * 8 + (__ffs(x) - 1)); x &= x - 1; }
   }
   __syncthreads();
+  // endpoints of the tree edges, fetched once (L2, independent loads) for the whole tour
+  for (int q = threadIdx.x; q < nt; q += blockDim.x) s.tuv[q] = s.euv[s.te[q]];
+  __syncthreads();
   return RC_OK;
 }
 
@@ -372,7 +375,7 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
       }
     }
   }
-  for (int j = tid; j < m; j += T) { s.lab[j] = (uint32_t)s.eu[j] | ((uint32_t)s.ev[j] << 16); s.lj[j] = (lid_t)j; }
+  for (int j = tid; j < m; j += T) { s.lab[j] = s.euv[j]; s.lj[j] = (lid_t)j; }
   for (int i = tid; i < n; i += T) { s.best[i] = 0xffffffffu; s.bpos[i] = 0xffffffffu; s.hook[i] = (lid_t)i; }
   for (int i = tid; i < (m + 31) >> 5; i += T) s.tflag[i] = 0;
   if (tid == 0) { s.misc[M_NLIVE] = 0; s.misc[M_NV] = 0; }
@@ -895,22 +898,26 @@ __device__ void euler_subtree_pops(Chain& c, const Step& st, int root) {
   for (int i = tid; i < n; i += T) s.head[i] = kNone;
   __syncthreads();
   for (int t = tid; t < nt; t += T) {
-    const int j = s.te[t];
-    s.nxt[2 * t] = (lid_t)atomicExch(&s.head[s.eu[j]], (uint32_t)(2 * t));
-    s.nxt[2 * t + 1] = (lid_t)atomicExch(&s.head[s.ev[j]], (uint32_t)(2 * t + 1));
+    const uint32_t uv = s.tuv[t];
+    s.nxt[2 * t] = (lid_t)atomicExch(&s.head[uv & 0xffffu], (uint32_t)(2 * t));
+    s.nxt[2 * t + 1] = (lid_t)atomicExch(&s.head[uv >> 16], (uint32_t)(2 * t + 1));
   }
   __syncthreads();
   // E3: successor of arc a = the out-arc after reverse(a) around head(a); arc weights
   const int first = (int)s.head[root];
   for (int a = tid; a < L; a += T) {
-    const int j = s.te[a >> 1];
-    const int x = (a & 1) ? s.eu[j] : s.ev[j];  // node the arc enters
+    const uint32_t uv = s.tuv[a >> 1];
+    const int x = (a & 1) ? (int)(uv & 0xffffu) : (int)(uv >> 16);  // node the arc enters
     const uint32_t hx = s.head[x];
     uint32_t nx = s.nxt[a ^ 1];
     if (nx == kNone) nx = hx;
     s.succ[a] = (lid_t)((int)nx == first ? a : (int)nx);  // the arc that closes the tour ends the list
-    s.W[a] = ((uint32_t)(a ^ 1) == hx && x != root) ? s.pop[x] : 0;
+    if (!((uint32_t)(a ^ 1) == hx && x != root)) s.W[a] = 0;
   }
+  // ... and the arcs that carry a population: the reverse of the first out-arc of every node
+  // but the root (node order: the populations stream in from the cold tier)
+  for (int x = tid; x < n; x += T)
+    if (x != root) s.W[s.head[x] ^ 1u] = s.pop[x];
   __syncthreads();
   // E5: walk 1 - length and weight of every sublist.  A walk stops in front of the next
   // splitter (every kStride-th arc, or the tour head) or at the arc that ends the tour.
@@ -971,14 +978,14 @@ __device__ void euler_subtree_pops(Chain& c, const Step& st, int root) {
       a = nx;
     }
   }
-  if (tid == 0) s.ent[root] = 0xffffu;
   __syncthreads();
-  // E8: population below every tree edge (cur aliases succ, which is dead now)
+  // E8: population below every tree edge (cur aliases succ, ent the sublist weights: both dead now)
+  if (tid == 0) s.ent[root] = 0xffffu;
   for (int t = tid; t < nt; t += T) {
-    const int j = s.te[t];
+    const uint32_t uv = s.tuv[t];
     const int p0 = s.P[2 * t], p1 = s.P[2 * t + 1];
     const bool down0 = p0 < p1;  // arc 2t (eu -> ev) points away from the root
-    const int child = down0 ? s.ev[j] : s.eu[j];
+    const int child = down0 ? (int)(uv >> 16) : (int)(uv & 0xffffu);
     s.ent[child] = (lid_t)(down0 ? p0 : p1);
     const int w0 = s.W[2 * t], w1 = s.W[2 * t + 1];
     s.cur[t] = down0 ? w1 - w0 : w0 - w1;
@@ -1043,7 +1050,8 @@ __device__ int choose_cut_by_weight(Chain& c, const Step& st, int policy, uint32
   // tree.py:552-561: a cut "crosses" a region column when its endpoints' labels differ
   // (None == None there, unlike the weight loop)
   auto crossed = [&](int j) {
-    const int gu = c.nodes[s.eu[j]], gv = c.nodes[s.ev[j]];
+    const uint32_t uv = s.euv[j];
+    const int gu = c.nodes[uv & 0xffffu], gv = c.nodes[uv >> 16];
     int cm = 0;
     for (int r = 0; r < R && r < 3; ++r)
       if (p.g.region_ids[(size_t)r * p.g.N + gu] != p.g.region_ids[(size_t)r * p.g.N + gv]) cm |= 1 << r;
@@ -1084,7 +1092,8 @@ struct ProposalResult {
 // Wilson: is local edge j an edge of the tree S (parent pointers)?  Returns the child
 // endpoint or -1.  (Two adjacent nodes cannot point at each other: the root points at itself.)
 __device__ __forceinline__ int wilson_tree_child(const Smem& s, const uint16_t* __restrict__ S, int j) {
-  const int a = s.eu[j], b = s.ev[j];
+  const uint32_t uv = s.euv[j];
+  const int a = (int)(uv & 0xffffu), b = (int)(uv >> 16);
   if ((int)(S[a] & kNext) == b) return a;
   if ((int)(S[b] & kNext) == a) return b;
   return -1;
@@ -1105,7 +1114,8 @@ __device__ bool commit_proposal(Chain& c, const Step& st, int cut_count, long lo
     __syncthreads();
     int d = 0;
     for (int j = tid; j < st.m; j += T) {
-      const int u = s.eu[j], v = s.ev[j];
+      const uint32_t uv = s.euv[j];
+      const int u = (int)(uv & 0xffffu), v = (int)(uv >> 16);
       const int was = ((s.oldb[u >> 5] >> (u & 31)) ^ (s.oldb[v >> 5] >> (v & 31))) & 1u;
       const int now = ((s.newb[u >> 5] >> (u & 31)) ^ (s.newb[v >> 5] >> (v & 31))) & 1u;
       d += now - was;
@@ -1127,7 +1137,8 @@ __device__ bool commit_proposal(Chain& c, const Step& st, int cut_count, long lo
   __syncthreads();
   int delta = 0;
   for (int j = tid; j < st.m; j += T) {  // updaters/cut_edges.py:118-120
-    const int u = s.eu[j], v = s.ev[j];
+    const uint32_t uv = s.euv[j];
+    const int u = (int)(uv & 0xffffu), v = (int)(uv >> 16);
     const bool was = ((s.oldb[u >> 5] >> (u & 31)) ^ (s.oldb[v >> 5] >> (v & 31))) & 1u;
     const bool now = ((s.newb[u >> 5] >> (u & 31)) ^ (s.newb[v >> 5] >> (v & 31))) & 1u;
     if (now != was) {
@@ -1507,7 +1518,8 @@ __device__ ProposalResult propose_reversible(Chain& c, uint32_t prop_no, int32_t
   __syncthreads();
   int seam = 0, delta = 0;
   for (int j = tid; j < st.m; j += T) {
-    const int u = s.eu[j], v = s.ev[j];
+    const uint32_t uv = s.euv[j];
+    const int u = (int)(uv & 0xffffu), v = (int)(uv >> 16);
     const int was = ((s.oldb[u >> 5] >> (u & 31)) ^ (s.oldb[v >> 5] >> (v & 31))) & 1u;
     const int now = ((s.newb[u >> 5] >> (u & 31)) ^ (s.newb[v >> 5] >> (v & 31))) & 1u;
     seam += now;
@@ -1535,7 +1547,8 @@ __device__ ProposalResult propose_reversible(Chain& c, uint32_t prop_no, int32_t
     if (nb != ob) c.assign[c.nodes[i]] = (uint8_t)(nb ? st.b : st.a);
   }
   for (int j = tid; j < st.m; j += T) {
-    const int u = s.eu[j], v = s.ev[j];
+    const uint32_t uv = s.euv[j];
+    const int u = (int)(uv & 0xffffu), v = (int)(uv >> 16);
     const int was = ((s.oldb[u >> 5] >> (u & 31)) ^ (s.oldb[v >> 5] >> (v & 31))) & 1u;
     const int now = ((s.newb[u >> 5] >> (u & 31)) ^ (s.newb[v >> 5] >> (v & 31))) & 1u;
     if (now != was) { const int eid = c.eids[j]; atomicXor(c.mask + (eid >> 5), 1u << (eid & 31)); }
@@ -1574,7 +1587,8 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
                   p.spill + (size_t)blockIdx.x * p.spill_stride, p.cold + (size_t)blockIdx.x * p.cold_stride);
   else
     smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R,
-                kSpill ? p.spill + (size_t)blockIdx.x * p.spill_stride : nullptr);
+                kSpill ? p.spill + (size_t)blockIdx.x * p.spill_stride : nullptr,
+                p.cold + (size_t)blockIdx.x * p.cold_stride);
   const int tid = threadIdx.x;
   c.nodes = p.nodes + (size_t)blockIdx.x * p.cap_nodes;
   c.eids = p.eids + (size_t)blockIdx.x * p.cap_edges;
@@ -1714,7 +1728,8 @@ __global__ void __launch_bounds__(512, 2) seed_kernel(const Params p) {
   Chain c;
   c.p = &p;
   smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R,
-              kSpill ? p.spill + (size_t)blockIdx.x * p.spill_stride : nullptr);
+              kSpill ? p.spill + (size_t)blockIdx.x * p.spill_stride : nullptr,
+              p.cold + (size_t)blockIdx.x * p.cold_stride);
   const Smem& s = c.s;
   const int tid = threadIdx.x, T = blockDim.x;
   c.nodes = p.nodes + (size_t)blockIdx.x * p.cap_nodes;

@@ -19,36 +19,45 @@ static bool disjoint(const std::vector<Span>& v, const char* what) {
 
 static bool check(int N, int CN, int CE, int R) {
   using namespace rc;
-  static unsigned char dummy[1];
+  static unsigned char dummy[1], coldbuf[1];
   unsigned char* base = dummy;  // offsets only: nothing is dereferenced
   Smem s;
-  size_t split = 0;
-  const size_t total = smem_layout(&s, base, N, CN, CE, R, nullptr, &split);
+  size_t split = 0, cold = 0;
+  const size_t total = smem_layout(&s, base, N, CN, CE, R, nullptr, coldbuf, &split, &cold);
   auto off = [&](const void* p) { return (size_t)((const unsigned char*)p - base); };
   const int NW = (N + 31) / 32, CW = (CN + 31) / 32, EW = (CE + 31) / 32;
 #define SP(ptr, bytes) Span{#ptr, off(s.ptr), off(s.ptr) + (size_t)(bytes)}
-  std::vector<Span> fixed = {SP(misc, 512), SP(mbits, 4 * NW), SP(mpref, 2 * NW), SP(pop, 4 * CN), SP(eu, 2 * CE),
-                             SP(ev, 2 * CE), SP(tflag, 4 * EW), SP(oldb, 4 * CW), SP(newb, 4 * CW),
-                             SP(ecls, R > 0 ? CE : 0)};
+  std::vector<Span> fixed = {SP(misc, 512), SP(mbits, 4 * NW), SP(mpref, 2 * NW), SP(tflag, 4 * EW), SP(oldb, 4 * CW),
+                             SP(newb, 4 * CW)};
   std::vector<Span> tree = fixed;
   for (Span x : {SP(key, 4 * CE), SP(lab, 4 * CE), SP(lj, 2 * CE), SP(best, 4 * CN), SP(bpos, 4 * CN),
                  SP(hook, 2 * CN), SP(vlA, 2 * (CN / 2 + 2)), SP(vlB, 2 * (CN / 2 + 2))}) tree.push_back(x);
-  std::vector<Span> euler = fixed;
-  for (Span x : {SP(te, 2 * CN), SP(head, 4 * CN), SP(nxt, 4 * CN), SP(succ, 4 * CN), SP(P, 4 * CN), SP(W, 8 * CN),
-                 SP(spX, 8 * s.spCap), SP(spY, 8 * s.spCap), SP(ent, 2 * CN)}) euler.push_back(x);
+  // Euler phase: the sublist ranking (spX, spY) is dead when ent is written; ent aliases spY
+  std::vector<Span> euler = fixed, euler2 = fixed;
+  for (Span x : {SP(te, 2 * CN), SP(tuv, 4 * CN), SP(head, 4 * CN), SP(nxt, 4 * CN), SP(succ, 4 * CN), SP(P, 4 * CN),
+                 SP(W, 8 * CN)}) { euler.push_back(x); euler2.push_back(x); }
+  for (Span x : {SP(spX, 8 * s.spCap), SP(spY, 8 * s.spCap)}) euler.push_back(x);
+  euler2.push_back(SP(ent, 2 * CN));
 #undef SP
-  if (!disjoint(tree, "tree phase") || !disjoint(euler, "euler phase")) return false;
-  for (const auto& v : {tree, euler})
+  if (!disjoint(tree, "tree phase") || !disjoint(euler, "euler phase") || !disjoint(euler2, "euler phase (ent)")) return false;
+  for (const auto& v : {tree, euler, euler2})
     for (const Span& x : v)
       if (x.hi > total) { printf("%s ends at %zu > total %zu\n", x.name, x.hi, total); return false; }
   if ((const void*)s.cur != (const void*)s.succ) { printf("cur must alias succ\n"); return false; }
-  if (split != off(s.pop)) { printf("split %zu != first spilled array %zu\n", split, off(s.pop)); return false; }
+  if ((const void*)s.ent != (const void*)s.spY) { printf("ent must alias spY\n"); return false; }
+  if (split != off(s.tflag)) { printf("split %zu != first array behind the core %zu\n", split, off(s.tflag)); return false; }
+  // cold tier: pop, euv, ecls disjoint inside the cold block
+  std::vector<Span> cl = {Span{"pop", (size_t)((unsigned char*)s.pop - coldbuf), (size_t)((unsigned char*)s.pop - coldbuf) + 4 * (size_t)CN},
+                          Span{"euv", (size_t)((unsigned char*)s.euv - coldbuf), (size_t)((unsigned char*)s.euv - coldbuf) + 4 * (size_t)CE},
+                          Span{"ecls", (size_t)((unsigned char*)s.ecls - coldbuf), (size_t)((unsigned char*)s.ecls - coldbuf) + (R > 0 ? (size_t)CE : 0)}};
+  if (!disjoint(cl, "cold tier")) return false;
+  for (const Span& x : cl) if (x.hi > cold) { printf("%s ends at %zu > cold %zu\n", x.name, x.hi, cold); return false; }
   // spill mode: the shared part is exactly [0, split); the rest is addressed relative to big
   static unsigned char bigbuf[1];
   Smem t;
-  smem_layout(&t, base, N, CN, CE, R, bigbuf, nullptr);
+  smem_layout(&t, base, N, CN, CE, R, bigbuf, coldbuf, nullptr, nullptr);
   if ((unsigned char*)t.misc != base || off(t.mpref) + 2 * (size_t)NW > split) { printf("spill: shared part wrong\n"); return false; }
-  if ((unsigned char*)t.pop != bigbuf) { printf("spill: pop must start the scratch block\n"); return false; }
+  if ((unsigned char*)t.tflag != bigbuf) { printf("spill: tflag must start the scratch block\n"); return false; }
   if ((size_t)((unsigned char*)t.ent - bigbuf) + 2 * (size_t)CN > total - split) { printf("spill: ent beyond the scratch block\n"); return false; }
   return true;
 }
@@ -77,7 +86,7 @@ static bool check_wilson(int N, int CN, int CE, int R, int W, int sh) {
     put("oldb", s.oldb, 4 * (size_t)CW, 1); put("newb", s.newb, 4 * (size_t)CW, 1); put("whas", s.whas, 4 * (size_t)CW, 1);
     put("wsum", s.wsum, 4 * (size_t)CN, 1); put("wst", s.wst, 2 * (size_t)W * CN, 1);
     put("nbr", s.nbr, 4 * ((size_t)(CN + CN / 8) << sh), 2); put("wdeg", s.wdeg, 2 * (size_t)CN, 2);
-    put("pop", s.pop, 4 * (size_t)CN, 3); put("eu", s.eu, 2 * (size_t)CE, 3); put("ev", s.ev, 2 * (size_t)CE, 3);
+    put("pop", s.pop, 4 * (size_t)CN, 3); put("euv", s.euv, 4 * (size_t)CE, 3);
     put("ecls", s.ecls, R > 0 ? (size_t)CE : 0, 3);
     if (!disjoint(in_sm, "wilson shared") || !disjoint(in_gl, "wilson global") || !disjoint(in_co, "wilson cold")) return false;
     for (const Span& x : in_sm) if (x.hi > smem) { printf("level %d: %s ends at %zu > smem %zu\n", level, x.name, x.hi, smem); return false; }
