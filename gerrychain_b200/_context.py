@@ -78,6 +78,20 @@ class GraphContext:
                             "engine tallies integers only")
         return col.astype(np.int64)
 
+    def float_column(self, fields):
+        """The float64 column of ``fields`` when the device cannot tally it exactly (non-integer
+        values, NaN, or |sum| >= 2^31), else None (integer column: device path)."""
+        key = ("float", tuple(fields))
+        if key not in self._region_codes:
+            g = self.graph
+            col = np.zeros(self.n_nodes, dtype=np.float64)
+            for f in fields:
+                col += np.array([g.nodes[lab][f] for lab in self.labels], dtype=np.float64)
+            finite = col[~np.isnan(col)]
+            exact = (not np.isnan(col).any()) and np.all(finite == np.floor(finite)) and np.abs(finite).sum() < 2**31
+            self._region_codes[key] = (None if exact else col, 0)
+        return self._region_codes[key][0]
+
     def csr(self, fields, region_surcharge=None) -> GraphCSR:
         if isinstance(fields, str):
             fields = (fields,)
@@ -144,6 +158,29 @@ class GraphContext:
             eng = Engine(csr, cfg, np.zeros(self.n_nodes, dtype=np.uint8))
             self._engines[full] = eng
         return eng
+
+    def grow_engine(self, eng):
+        """Replace a single-chain engine whose merged-pair caps were too small (RC_ERR_CAPACITY)
+        by one with doubled caps - up to the whole graph, where the engine spills to its L2
+        scratch instead of failing.  Same configuration and Philox key: the step that failed is
+        simply taken again.  Returns the new engine, or None when the caps cannot grow."""
+        from dataclasses import replace
+
+        from .engine import Engine
+
+        info = eng.info()
+        csr, cfg = eng.csr, eng.cfg
+        limit_n, limit_e = min(csr.n_nodes, 32760), min(csr.n_edges, 65535)
+        if info.cap_nodes >= limit_n and info.cap_edges >= limit_e:
+            return None
+        new_cfg = replace(cfg, cap_nodes=min(2 * info.cap_nodes, limit_n), cap_edges=min(2 * info.cap_edges, limit_e))
+        new = Engine(csr, new_cfg, np.zeros(self.n_nodes, dtype=np.uint8))
+        new.proposal_no.copy_(eng.proposal_no)  # the Philox position of the chain carries over
+        for key, val in list(self._engines.items()):
+            if val is eng:
+                self._engines[key] = new
+        eng.close()
+        return new
 
     def scan(self, vec: np.ndarray, fields, k: int):
         """First-time Tally + cut_edges of a plan (rc_engine_init_state):

@@ -271,7 +271,12 @@ class BatchedMarkovChain:
         if self.engine is None:
             self._build()
         else:
+            # a second pass starts from the initial plans again but NOT from the same random
+            # numbers: the chains keep their position in the Philox streams, as the reference's
+            # chain keeps drawing from Python's global `random` when it is iterated again
+            position = self.engine.proposal_no.clone()
             self.engine.set_assignment(self.initial_state._vec if self._plans is None else self._plans)
+            self.engine.proposal_no.copy_(position)
         self.counter = 0
         return self
 

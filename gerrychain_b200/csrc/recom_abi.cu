@@ -130,9 +130,13 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   p.g.edge_uv = e->d_edge_uv; p.g.pop = e->d_pop; p.g.region_ids = e->d_region;
   uint64_t sfix_total = 0;
   for (int r = 0; r < R; ++r) {
-    if (!(g->surcharges[r] >= 0.0) || g->surcharges[r] > 1e6) {
+    // Free-running keys are (raw + surcharges) rescaled into 32 bits: their resolution shrinks by
+    // 1 + the summed surcharge, and exact ties fall to the lower edge id (p(tie in a tree) ~
+    // m^2 (1 + sum) / 2^33).  The reference's tutorials use surcharges <= 1; beyond 256 the
+    // ties would no longer be negligible, so such values are refused rather than biased.
+    if (!(g->surcharges[r] >= 0.0) || g->surcharges[r] > 256.0) {
       rc_engine_destroy(e);
-      return fail(RC_ERR_INVALID_ARG, "region surcharges must be in [0, 1e6]");
+      return fail(RC_ERR_INVALID_ARG, "region surcharges must be in [0, 256]");
     }
     p.g.surcharge[r] = g->surcharges[r];
     p.g.sfix[r] = rc_surcharge_fix(g->surcharges[r]);

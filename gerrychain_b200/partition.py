@@ -310,7 +310,22 @@ class Partition:
     def _tally(self, fields: Tuple[str, ...]) -> np.ndarray:
         fields = tuple(fields)
         if fields not in self._dev_tally:
-            self._scan(fields)
+            col = self._ctx.float_column(fields)
+            if col is None:
+                self._scan(fields)
+            else:
+                # A column the device cannot tally exactly (floats - e.g. the `area` of
+                # GeographicPartition's default updaters - NaNs, or a total beyond int32): summed
+                # on the host over the dense plan.  The reference's Tally sums whatever the node
+                # attribute holds and skips NaN with a warning (updaters/tally.py:118-141).
+                import warnings
+
+                bad = np.isnan(col)
+                for i in np.nonzero(bad)[0].tolist():
+                    warnings.warn("ignoring nan encountered at node '{}' for attribute '{}'".format(
+                        self._ctx.labels[i], fields[0]))
+                self._dev_tally[fields] = np.bincount(self._vec[~bad], weights=col[~bad],
+                                                      minlength=len(self._district_labels))
         return self._dev_tally[fields]
 
     def _region_stats(self, reg_attr: str):

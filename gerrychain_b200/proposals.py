@@ -131,7 +131,7 @@ def recom(partition, pop_col: str, pop_target: Union[int, float], epsilon: float
     rkey = tuple(region_surcharge.items()) if region_surcharge else ()
     key = ("recom", rkey) + tuple(sorted((kk, vv) for kk, vv in ekw.items()))
     eng = ctx.engine(key, pop_col, k, region_surcharge, **ekw)  # Bounds are checked by the caller's Validator
-    h_assign, h_tally, h_cut = _run_one_step(partition, pop_col, eng, ekw["max_attempts"])
+    eng, h_assign, h_tally, h_cut = _run_one_step(partition, pop_col, eng, ekw["max_attempts"])
     if not eng._api_warned and int(eng.flags[0].item()) & _abi.RC_FLAG_WARNED:  # tree.py:703-710
         eng._api_warned = True
         warnings.warn(_WARNING_TEXT.format(ekw["warn_attempts"]), BipartitionWarning)
@@ -159,8 +159,15 @@ def _run_one_step(partition, pop_col, eng, max_attempts):
     h_assign, h_tally, h_cut, h_status = bufs
     h_assign[0].numpy()[:] = partition._vec
     eng.step_host(h_assign, 1, h_assign, h_tally, h_cut, h_status)
+    if int(h_status[0]) == _abi.RC_ERR_CAPACITY:
+        # A merged pair larger than the engine's caps (2.4 N / k nodes by default; districts of
+        # very uneven node counts exceed it): the reference has no such limit, so the step is
+        # taken again on an engine with doubled caps instead of surfacing an engine error.
+        bigger = partition._ctx.grow_engine(eng)
+        if bigger is not None:
+            return _run_one_step(partition, pop_col, bigger, max_attempts)
     raise_for_status(int(h_status[0]), max_attempts, k * (k - 1) / 2)
-    return h_assign, h_tally, h_cut
+    return eng, h_assign, h_tally, h_cut
 
 
 def reversible_recom(partition, pop_col: str, pop_target: Union[int, float], epsilon: float,
@@ -177,7 +184,7 @@ def reversible_recom(partition, pop_col: str, pop_target: Union[int, float], eps
     ekw = reversible_engine_kwargs(pop_target, epsilon, M, repeat_until_valid)
     key = ("reversible",) + tuple(sorted(ekw.items()))
     eng = ctx.engine(key, pop_col, k, None, **ekw)
-    h_assign, h_tally, h_cut = _run_one_step(partition, pop_col, eng, 1)
+    eng, h_assign, h_tally, h_cut = _run_one_step(partition, pop_col, eng, 1)
     new_vec = h_assign[0].numpy()
     if np.array_equal(new_vec, partition._vec):
         return partition  # self-loop (no adjacency, no balance edge, or rejected)

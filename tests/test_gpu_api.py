@@ -376,3 +376,52 @@ def test_record_and_replay_a_recom_chain(tmp_path):
         assert state.assignment.mapping == mapping
         assert set(state["cut_edges"]) == cuts
         assert dict(state["population"]) == pops
+
+
+def test_recom_grows_the_engine_caps_instead_of_failing():
+    """Districts of very uneven node counts: the merged pair of the two large ones exceeds the
+    engine's default caps (2.4 N / k nodes).  The reference has no such limit; the host API
+    takes the step again on an engine with doubled caps (RC_ERR_CAPACITY is not surfaced)."""
+    g = networkx.grid_2d_graph(20, 20)
+    plan = {}
+    for (i, j) in g.nodes:
+        d = 0 if i < 8 else 1 if i < 16 else 2 if i < 18 else 3
+        plan[(i, j)] = d
+        g.nodes[(i, j)]["population"] = 1 if d < 2 else 4  # 160 / 160 / 160 / 160 people
+    random.seed(3)
+    p = Partition(g, plan, {"population": Tally("population"), "cut_edges": cut_edges})
+    proposal = functools.partial(recom, pop_col="population", pop_target=160, epsilon=0.3, node_repeats=1)
+    chain = MarkovChain(proposal, [within_percent_of_ideal_population(p, 0.3)], always_accept, p, total_steps=40)
+    merged_big_pair = False
+    for state in chain:
+        assert _contiguous(state)
+        assert state["cut_edges"] == _naive_cut_edges(state)
+        assert state["population"] == _naive_tally(state, "population")
+        if state.flips:
+            merged_big_pair = merged_big_pair or len(state.flips) > 272
+    assert merged_big_pair, "the test never merged the two large districts"
+
+
+def test_tally_of_a_float_column_and_polsby_popper():
+    """GeographicPartition-style float attributes (areas): Tally falls back to the host sum
+    (the device tallies integers), NaN is skipped with the reference's warning."""
+    g = networkx.grid_2d_graph(6, 6)
+    rng = np.random.default_rng(0)
+    for v in g.nodes:
+        g.nodes[v]["population"] = 1
+        g.nodes[v]["area"] = float(rng.random()) + 0.5
+    plan = {(i, j): (0 if i < 3 else 1) for (i, j) in g.nodes}
+    p = Partition(g, plan, {"area": Tally("area", dtype=float), "population": Tally("population")})
+    want = _naive_tally(p, "area")
+    assert p["area"].keys() == want.keys()
+    for d in want:
+        assert abs(p["area"][d] - want[d]) < 1e-9
+    a00 = g.nodes[(0, 0)]["area"]
+    g2 = g.copy()  # node attributes are read once per graph (the reference freezes its graphs too)
+    g2.nodes[(0, 0)]["area"] = float("nan")
+    q = Partition(g2, plan, {"area": Tally("area", dtype=float)})
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        got = q["area"]
+    assert any("ignoring nan" in str(x.message) for x in w)
+    assert abs(got[0] - (want[0] - a00)) < 1e-9 and abs(got[1] - want[1]) < 1e-9
