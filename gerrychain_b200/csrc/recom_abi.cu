@@ -1,6 +1,7 @@
 // recom_abi.cu - host side of the C ABI declared in include/recom_b200.h.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <new>
@@ -55,10 +56,12 @@ struct RcEngine {
   int device = 0;
   rc::Params p{};
   bool bound = false;
-  int grid = 0, threads = 0, ctas_per_sm = 0, n_sms = 0;
+  int grid = 0, capacity = 0, threads = 0, ctas_per_sm = 0, n_sms = 0;
   size_t smem = 0, scratch_bytes = 0, sched_bytes = 0, spill_bytes = 0, cold_bytes = 0;
   bool spill = false;
   const void* kernel = nullptr;
+  const void* kernel_share = nullptr;  // the build with shared retries
+  int share_mode = 2;                  // RECOM_B200_SHARE: 0 never, 1 always, 2 (default) short launches / spare CTAs
   int64_t launches = 0;
   // owned device memory
   int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_slot_edge = nullptr, *d_edge_uv = nullptr,
@@ -256,8 +259,20 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
     rc_engine_destroy(e);
     return fail(RC_ERR_INVALID_ARG, "threads_per_cta must be a multiple of 32 in [64, %d] (0 = automatic)", wilson ? 256 : 512);
   }
-  e->kernel = wilson ? (const void*)rc::recom_step_kernel<true, false>  // the placement level is a run-time parameter
-                     : (e->spill ? (const void*)rc::recom_step_kernel<false, true> : (const void*)rc::recom_step_kernel<false, false>);
+  // two builds of the chain-step kernel: the plain one, and one with shared retries (CTAs without a
+  // chain draw the later trees of steps in flight), which costs the step path ~20 % in registers
+  // and barriers and is launched where it pays: few steps per launch or fewer chains than CTAs
+  e->kernel = wilson ? (const void*)rc::recom_step_kernel<true, false, false>  // the placement level is a run-time parameter
+                     : (e->spill ? (const void*)rc::recom_step_kernel<false, true, false> : (const void*)rc::recom_step_kernel<false, false, false>);
+  e->kernel_share = wilson ? (const void*)rc::recom_step_kernel<true, false, true>
+                           : (e->spill ? (const void*)rc::recom_step_kernel<false, true, true> : (const void*)rc::recom_step_kernel<false, false, true>);
+  CUDA_OK_E(cudaFuncSetAttribute(e->kernel_share, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  if (const char* sm = getenv("RECOM_B200_SHARE")) e->share_mode = sm[0] == '0' ? 0 : sm[0] == '1' ? 1 : 2;
+  p.help_win = rc::kHelpWin;
+  if (const char* hw = getenv("RECOM_B200_HELP_WIN")) {  // test knob: a tiny window makes every shared step slide it
+    const int v = atoi(hw);
+    if (v >= 1 && v <= rc::kHelpWin) p.help_win = v;
+  }
   CUDA_OK_E(cudaFuncSetAttribute(e->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   CUDA_OK_E(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->ctas_per_sm, e->kernel, e->threads, e->smem));
   if (e->ctas_per_sm < 1) { rc_engine_destroy(e); return fail(RC_ERR_CAPACITY, "kernel does not fit an SM"); }
@@ -272,14 +287,28 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
     if (fit < e->n_sms) fit = e->n_sms;
     if (e->grid > fit) e->grid = (int)fit;
   }
-  if (e->grid > cfg->n_chains) e->grid = cfg->n_chains;
+  {
+    // fewer chains than CTAs: the spare CTAs have no chain of their own, but with shared retries
+    // (recom_kernels.cu) they draw the later spanning trees of the steps in flight - what a
+    // single-chain MarkovChain driver gets out of the GPU; without them they would only wait
+    const bool share = !(cfg->allow_pair_reselection || cfg->proposal_kind == RC_PROPOSAL_REVERSIBLE || cfg->node_repeats < 1);
+    e->capacity = e->grid;
+    if (!share && e->grid > cfg->n_chains) e->grid = cfg->n_chains;
+  }
   // scratch
   size_t b_nodes = (size_t)e->grid * cap_nodes * sizeof(int32_t);
   size_t b_eids = (size_t)e->grid * cap_edges * sizeof(int32_t);
   size_t b_bad = cfg->allow_pair_reselection ? (size_t)e->grid * 2048 * sizeof(uint32_t) : 0;
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
   // pop/push indices, phase timers, progress words, ring of ready chains, CTAs counted per SM
-  size_t b_prog = 512 + 2 * (size_t)cfg->n_chains * sizeof(int32_t) + 1024 * sizeof(int32_t);
+  // the ring of ready chains has a slot for every chain AND for every waiting CTA: two tickets
+  // must never wait on the same slot (with shared retries the grid may exceed the chain count)
+  const int ring_cap = cfg->n_chains > e->grid ? cfg->n_chains : e->grid;
+  size_t b_prog = 512 + ((size_t)cfg->n_chains + (size_t)ring_cap) * sizeof(int32_t) + 1024 * sizeof(int32_t);
+  // + shared-retry board: one record and one window of status words per chain
+  const size_t o_help = (b_prog + 63) & ~size_t(63);
+  const size_t o_hstat = o_help + (size_t)cfg->n_chains * sizeof(rc::HelpRec);
+  b_prog = o_hstat + (size_t)cfg->n_chains * rc::kHelpWin * sizeof(unsigned long long);
   size_t b_spill = (size_t)e->grid * e->spill_bytes;
   size_t b_cold = (size_t)e->grid * e->cold_bytes;
   e->scratch_bytes = al(b_nodes) + al(b_eids) + al(b_bad) + al(b_prog) + al(b_spill) + al(b_cold);
@@ -292,8 +321,13 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   p.timers = (unsigned long long*)(base + 256);
   p.progress = (int32_t*)(base + 512);
   p.ring = p.progress + cfg->n_chains;
-  p.ring_cap = cfg->n_chains;
-  p.sm_slots = p.ring + cfg->n_chains;
+  p.ring_cap = ring_cap;
+  p.sm_slots = p.ring + ring_cap;
+  p.idle = (int32_t*)(base + 64);
+  p.steps_done = (unsigned long long*)(base + 128);
+  p.help = (rc::HelpRec*)(base + o_help);
+  p.help_status = (unsigned long long*)(base + o_hstat);
+  p.share = (cfg->allow_pair_reselection || cfg->proposal_kind == RC_PROPOSAL_REVERSIBLE || cfg->node_repeats < 1) ? 0 : 1;
   base += al(b_prog);
   p.spill = b_spill ? (unsigned char*)base : nullptr;
   p.spill_stride = (int64_t)e->spill_bytes;
@@ -349,7 +383,15 @@ int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream) {
   CUDA_OK(cudaEventRecord(e->ev0, s));
   CUDA_OK(cudaMemsetAsync(p.work_counter, 0, e->sched_bytes, s));
   void* args[] = {(void*)&p};
-  CUDA_OK(cudaLaunchKernel(e->kernel, dim3(e->grid), dim3(e->threads), args, e->smem, s));
+  // shared retries where the tail of the launch matters: few steps per chain, or spare CTAs
+  const int n_chains = e->p.cfg.n_chains;
+  // Measured on B200 (config 3, 1024 chains): 32 steps per launch 0.26 M -> 1.11 M steps/s with shared
+  // retries, 512 steps per launch 2.48 M -> 2.30 M (the build costs the step path registers and a
+  // bigger loop), and with fewer chains than CTAs the polling helpers cost more than the rare
+  // stuck step returns.  Hence: short launches of a full grid only (RECOM_B200_SHARE=0/1 forces it).
+  const bool share = p.share && e->share_mode != 0 && (e->share_mode == 1 || (n_steps < 128 && n_chains >= e->grid));
+  const int grid = share ? e->grid : (n_chains < e->grid ? n_chains : e->grid);
+  CUDA_OK(cudaLaunchKernel(share ? e->kernel_share : e->kernel, dim3(grid), dim3(e->threads), args, e->smem, s));
   e->launches++;
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(e->ev1, s));

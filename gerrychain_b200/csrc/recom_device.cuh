@@ -28,6 +28,23 @@ struct DevGraph {
   uint64_t smult;             // rc_key_mult(sum sfix, R); 0 when R == 0
 };
 
+// Shared retries (recom_kernels.cu shared_retry / help_once): CTAs with no ready chain compute
+// spanning trees t, t + 1, ... of a chain-step another CTA is retrying (tree.py:679-718).
+struct HelpRec {
+  int32_t epoch;     // odd: help wanted; bumped by the owner on publish, window slide and retirement
+  int32_t session;   // bumped per publish: same session = same merged pair (a helper's gather is still good)
+  int32_t pair;      // a | b << 16
+  uint32_t prop_no;
+  uint32_t t_first;  // tree number of unit 0
+  int32_t unit;      // trees per unit (1 for MST, the walker count for Wilson)
+  int32_t limit;     // units >= limit lie beyond max_attempts
+  int32_t base;      // first unit of the status window
+  int32_t next;      // next unit to hand out (atomic)
+  int32_t won;       // lowest unit with a balanced cut so far (atomicMin)
+  int32_t pad[6];
+};
+constexpr int kHelpWin = 256;  // status words per chain: units [base, base + kHelpWin)
+
 struct Params {
   DevGraph g;
   RcConfig cfg;
@@ -55,6 +72,12 @@ struct Params {
   int32_t walkers;        // Wilson: spanning trees drawn concurrently per chain-step (lanes of one warp)
   int32_t nbr_shift;      // Wilson: log2 of the adjacency slots per node kept in the hot tier
   int32_t wilson_level;   // Wilson: 0 = state and adjacency in shared memory, 1 = adjacency in L2, 2 = both in L2
+  HelpRec* help;                       // [n_chains]
+  unsigned long long* help_status;     // [n_chains][kHelpWin]
+  int32_t* idle;                       // CTAs of this launch that have no chain to step
+  unsigned long long* steps_done;      // chain-steps completed in this launch
+  int32_t share;                       // 0: no shared retries
+  int32_t help_win;                    // units per status window (<= kHelpWin)
 };
 
 // ---- shared-memory carve-up -------------------------------------------------------

@@ -1160,8 +1160,232 @@ __device__ bool commit_proposal(Chain& c, const Step& st, int cut_count, long lo
   return true;
 }
 
-// One recom proposal + validity + commit (tree_proposals.py:36-146, chain.py:186-195).
+// =========================================================================================
+// Shared retries.  bipartition_tree (tree.py:679-718) draws trees t = 0, 1, 2, ... until one
+// has a balanced cut; the trees are independent of each other (tree t is a pure function of
+// chain, proposal and t), so CTAs that have no chain to step - the tail of a launch, or a
+// launch with fewer chains than CTAs - draw the later trees of a step another CTA is
+// working on.  The lowest tree number with a balanced cut wins, whoever found it: the chain
+// is bit-identical to one that drew the trees one after the other.
+//   A UNIT is one tree (MST) or one batch of concurrent walks (Wilson).  The owner of the
+// step publishes a record (HelpRec) and from then on takes its units from the same atomic
+// counter as the helpers.  Everybody reports a unit in ONE 64-bit status word - epoch tag,
+// outcome, tree / draw counts - so a word is either valid for the current window or taken
+// for "pending"; a pending unit below the lowest success is simply computed again by the
+// owner (the result cannot differ), which is why the owner never waits for anybody and no
+// helper can stall a chain.  The owner alone touches the chain: when the lowest success is
+// final it retires the record, draws the winning tree again if it is not the one in its
+// shared memory, and goes on to the cut as if it had found the tree itself.
+struct UnitResult { int status, first_ok, nbal; uint32_t value; };  // value: Boruvka rounds / walk draws
+constexpr int kHelpAfter = 8;  // failed trees before a step is shared
+
+// status word: epoch (24) | kind (2) | first_ok (6) | value (32)
+enum { HK_FAIL = 1, HK_OK = 2, HK_ERR = 3 };
+__device__ __forceinline__ unsigned long long help_pack(int epoch, int kind, int first_ok, uint32_t value) {
+  return ((unsigned long long)(epoch & 0xffffff) << 40) | ((unsigned long long)kind << 38) |
+         ((unsigned long long)(first_ok & 63) << 32) | (unsigned long long)value;
+}
+__device__ __forceinline__ int ld_acquire(const int32_t* p);
+__device__ __forceinline__ void st_release(int32_t* p, int v);
+__device__ __forceinline__ void st_release64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Trees tree_first .. tree_first + nw - 1 in order until one has a balanced cut; on success
+// shared memory holds that tree, rooted and summed, ready for the cut choice.
 template <bool kWilson>
+__device__ UnitResult eval_unit(Chain& c, const Step& st, uint32_t tree_first, int nw, uint32_t prop_no,
+                                double ideal, double thr) {
+  const Smem& s = c.s;
+  UnitResult r = {RC_OK, -1, 0, 0u};
+  if constexpr (kWilson) {
+    wilson_walk(c, st, tree_first, nw, prop_no, 0);
+    for (int w = 0; w < nw; ++w) {
+      r.status = s.wmeta[WM_ERR + w];
+      r.value += (uint32_t)s.wmeta[WM_DRAWS + w];
+      if (r.status) return r;
+      if (st.n < 3) { r.status = RC_ERR_NO_ROOT; return r; }
+      r.nbal = wilson_eval(c, st, w, ideal, thr);
+      if (r.nbal > 0) { r.first_ok = w; return r; }
+    }
+  } else {
+    const int tid = threadIdx.x, T = blockDim.x, nt = st.n - 1;
+    int rounds = 0;
+    r.status = boruvka_mst(c, st, tree_first, prop_no, nullptr, &rounds);
+    r.value = (uint32_t)rounds;
+    if (r.status) return r;
+    if (st.n < 3) { r.status = RC_ERR_NO_ROOT; return r; }
+    euler_subtree_pops(c, st, 0);
+    if (tid == 0) s.misc[M_NBAL] = 0;
+    __syncthreads();
+    int cnt = 0;
+    for (int t = tid; t < nt; t += T) cnt += balanced(s.cur[t], st.tot, ideal, thr) ? 1 : 0;
+    cnt = warp_sum(cnt);
+    if ((tid & 31) == 0 && cnt) atomicAdd(&s.misc[M_NBAL], cnt);
+    __syncthreads();
+    r.nbal = s.misc[M_NBAL];
+    __syncthreads();
+    if (r.nbal > 0) r.first_ok = 0;
+  }
+  return r;
+}
+
+struct SharedOut {
+  int status;        // RC_OK, the error of the first decisive unit, or -1: no unit below the limit has a cut
+  uint32_t tree_no;  // the winning tree
+  int wsel, nbal;
+  long long trees, value;  // trees drawn and rounds / draws from t_first up to and including the winner
+  long long units;         // units up to and including the winner's (all of them when none won)
+};
+
+// block sum of the value fields of status words [0, cnt) (all valid for the current epoch)
+__device__ long long help_value_sum(const Smem& s, const unsigned long long* ST, int cnt) {
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(&s.misc[M_BEST64]);
+  if (threadIdx.x == 0) *acc = 0ull;
+  __syncthreads();
+  unsigned long long v = 0;
+  for (int j = threadIdx.x; j < cnt; j += blockDim.x) v += (unsigned long long)(uint32_t)__ldcg(ST + j);
+  if (v) atomicAdd(acc, v);
+  __syncthreads();
+  const long long r = (long long)*acc;
+  __syncthreads();
+  return r;
+}
+
+// The owner's side: trees t_first, t_first + 1, ... of proposal prop_no, `unit` trees per unit;
+// only units below `limit` exist (max_attempts), the last of them may hold fewer trees
+// (trees_cap trees in all).
+template <bool kWilson>
+__device__ __noinline__ SharedOut shared_retry(Chain& c, const Step& st, uint32_t t_first, int unit, long long limit_ll,
+                                  long long trees_cap, uint32_t prop_no, double ideal, double thr) {
+  const Params& p = *c.p;
+  const Smem& s = c.s;
+  const int tid = threadIdx.x, T = blockDim.x;
+  constexpr int kInf = 0x7fffffff;
+  HelpRec* R = p.help + c.chain;
+  unsigned long long* ST = p.help_status + (size_t)c.chain * kHelpWin;
+  const int win = p.help_win;  // units per status window (kHelpWin; smaller only in tests, to exercise the slide)
+  const int limit = (int)min(limit_ll, 0x3fffffffLL);
+  SharedOut out = {-1, 0u, 0, 0, 0, 0, 0};
+  int32_t* bc = s.misc + M_SPARE0;  // broadcast: M_SPARE0, M_SPARE1
+  int32_t* lo_ok = &s.misc[M_PICK];
+  int32_t* lo_pend = &s.misc[M_CNT];
+  int32_t* lo_err = &s.misc[M_SUBSET];
+  if (tid == 0) {
+    const int e = R->epoch + 1;  // odd from here on
+    __threadfence();  // (the retirement of the last session is out before its fields change)
+    R->session += 1; R->pair = st.a | (st.b << 16); R->prop_no = prop_no; R->t_first = t_first; R->unit = unit;
+    R->limit = limit; R->base = 0; R->next = 0; R->won = kInf;
+    __threadfence();
+    st_release(&R->epoch, e);
+    bc[0] = e;
+  }
+  __syncthreads();
+  int epoch = bc[0];
+  __syncthreads();
+  int base = 0, have = -1, have_first = -1, have_nbal = 0, winner = -1;
+  long long acc_value = 0;  // of the windows slid past (all their units failed)
+  auto unit_trees = [&](int u) { return (int)min((long long)unit, trees_cap - (long long)u * unit); };
+  int known_dec = kInf;  // lowest deciding unit seen so far (R->won is only a hint for the helpers)
+  for (long long spin = 0;; ++spin) {
+    if (spin > (1LL << 24)) { winner = -1; out.status = RC_ERR_INVALID_ARG; break; }  // cannot happen; never hang a launch
+    // 1. a fresh unit, if there is one worth taking
+    if (tid == 0) {
+      int u = -1;
+      const int nx = *(volatile int32_t*)&R->next;
+      if (nx < base + win && nx < limit && nx <= known_dec) {
+        u = atomicAdd(&R->next, 1);
+        if (!(u >= base && u < base + win && u < limit && u <= known_dec)) u = -1;
+      }
+      R->won = known_dec;
+      bc[0] = u;
+      bc[1] = min(min(*(volatile int32_t*)&R->next, base + win), limit) - base;  // units of the window handed out
+      *lo_ok = kInf; *lo_pend = kInf; *lo_err = kInf;
+    }
+    __syncthreads();
+    int u = bc[0];
+    const int cnt = bc[1];
+    // 2. where does the window stand?  lowest success, lowest error, lowest unit not reported
+    for (int j = tid; j < cnt; j += T) {
+      if (base + j == u) continue;  // about to be drawn here
+      const unsigned long long w = __ldcg(ST + j);
+      const int kind = ((int)(w >> 40) == (epoch & 0xffffff)) ? (int)((w >> 38) & 3u) : 0;
+      if (kind == HK_OK) atomicMin(lo_ok, j);
+      else if (kind == HK_ERR) atomicMin(lo_err, j);
+      else if (kind == 0) atomicMin(lo_pend, j);
+    }
+    __syncthreads();
+    const int low_pend = *lo_pend, low_dec = min(*lo_ok, *lo_err);  // low_dec: the lowest unit that decides the step
+    __syncthreads();
+    known_dec = low_dec == kInf ? kInf : base + low_dec;
+    if (low_dec != kInf && low_pend > low_dec && (u < 0 || base + low_dec < u)) { winner = base + low_dec; break; }
+    if (u < 0) {
+      if (low_pend != kInf && low_pend < low_dec) {
+        u = base + low_pend;  // handed out but not reported (yet): draw it here, the outcome is the same
+      } else if (low_dec == kInf && low_pend == kInf && cnt == min(win, limit - base)) {
+        // every unit of the window failed: slide it, or give up at the limit
+        acc_value += help_value_sum(s, ST, cnt);
+        out.units = (long long)base + cnt;
+        if (base + win >= limit) break;
+        base += win;
+        if (tid == 0) {
+          st_release(&R->epoch, epoch + 1);  // nobody reads fields under an even epoch
+          __threadfence();
+          R->base = base; R->next = base; R->won = kInf;
+          __threadfence();
+          st_release(&R->epoch, epoch + 2);
+        }
+        epoch += 2;
+        known_dec = kInf;
+        __syncthreads();
+        continue;
+      } else {
+        continue;  // a unit was handed out between the two reads of `next`: look again
+      }
+    }
+    // 3. draw unit u and report it
+    const UnitResult r = eval_unit<kWilson>(c, st, t_first + (uint32_t)u * (uint32_t)unit, unit_trees(u), prop_no, ideal, thr);
+    have = r.first_ok >= 0 ? u : -1;
+    have_first = r.first_ok;
+    have_nbal = r.nbal;
+    if (tid == 0) {
+      const int kind = r.status ? HK_ERR : (r.first_ok >= 0 ? HK_OK : HK_FAIL);
+      st_release64(ST + (u - base), help_pack(epoch, kind, r.first_ok >= 0 ? r.first_ok : 0, r.value));
+      if (kind != HK_FAIL) atomicMin(&R->won, u);
+    }
+    __syncthreads();
+  }
+  // retire the record: helpers drop what they are doing for it
+  if (tid == 0) { __threadfence(); st_release(&R->epoch, epoch + 1); }
+  __syncthreads();
+  out.value = acc_value;
+  out.trees = min((long long)out.units * unit, trees_cap);
+  if (winner < 0) return out;  // status -1 (or the spin guard's error)
+  // every unit below the winner failed with all its trees
+  acc_value += help_value_sum(s, ST, winner - base);
+  if (have != winner) {  // found by a helper (or overwritten since): the same tree again, into this CTA's shared memory
+    const UnitResult r = eval_unit<kWilson>(c, st, t_first + (uint32_t)winner * (uint32_t)unit, unit_trees(winner), prop_no, ideal, thr);
+    out.units = (long long)winner + 1;
+    out.trees = (long long)winner * unit + (r.first_ok >= 0 ? r.first_ok + 1 : unit_trees(winner));
+    out.value = acc_value + r.value;
+    if (r.status) { out.status = r.status; return out; }
+    if (r.first_ok < 0) { out.status = RC_ERR_INVALID_ARG; return out; }  // cannot happen: a unit is a pure function
+    have_first = r.first_ok;
+    have_nbal = r.nbal;
+  } else {
+    out.value = acc_value + (long long)(uint32_t)__ldcg(ST + (winner - base));
+  }
+  out.status = RC_OK;
+  out.tree_no = t_first + (uint32_t)winner * (uint32_t)unit + (uint32_t)have_first;
+  out.wsel = have_first;
+  out.nbal = have_nbal;
+  out.units = (long long)winner + 1;
+  out.trees = (long long)winner * unit + have_first + 1;
+  return out;
+}
+
+// One recom proposal + validity + commit (tree_proposals.py:36-146, chain.py:186-195).
+template <bool kWilson, bool kShare>
 __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep* rs,
                                   int32_t* ctr /* smem counters */) {
   const Params& p = *c.p;
@@ -1215,10 +1439,14 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
   if (res.status) return res;
   const int n = st.n, nt = n - 1;
   bool reselect = false;
+  if constexpr (kShare) {  // are there CTAs without a chain?  (read again while every tree is drawn)
+    if (tid == 0) s.misc[M_SPARE0] = *(volatile int32_t*)p.idle > 0;
+    __syncthreads();
+  }
   uint32_t batch_lo = t0, batch_hi = t0;  // Wilson: trees [batch_lo, batch_hi) have been walked
   for (uint32_t tree_no = t0;; ++tree_no) {
     // tree.py:679-700 attempt accounting (see oracle/recom_oracle.c rco_bipartition)
-    const long long attempts = nr > 0 ? (long long)tree_no * nr : (tree_no == t0 ? 0 : max_attempts);
+    long long attempts = nr > 0 ? (long long)tree_no * nr : (tree_no == t0 ? 0 : max_attempts);
     if (attempts >= max_attempts) {
       if (tid == 0) {
         ctr[RC_CTR_ATTEMPTS] += (int)min(max_attempts, 0x7fffffffLL);
@@ -1230,7 +1458,47 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
     }
     if (rs && (int)tree_no >= n_rec) { res.status = RC_ERR_REPLAY; return res; }
     int nbal;
-    if constexpr (kWilson) {
+    // CTAs without a chain to step?  Then the rest of this search is shared with them
+    // (shared_retry above); checked once per tree / batch, at a point where nothing is in flight
+    bool go_shared = false;
+    if constexpr (kShare) {
+      // only a step that has already failed kHelpAfter trees asks for help: the common step
+      // (a handful of trees) is not worth a helper's gather, and helpers share SMs with owners
+      if (!rs && !resel && tree_no >= t0 + (uint32_t)kHelpAfter && (!kWilson || tree_no >= batch_hi)) {
+        // thread 0 looked at the idle counter while the previous tree was drawn (no barrier of
+        // its own: the ones of the tree lie in between); it looks again for the next one
+        go_shared = s.misc[M_SPARE0] != 0;
+        __syncthreads();
+        if (tid == 0) s.misc[M_SPARE0] = *(volatile int32_t*)p.idle > 0;
+      }
+    }
+    if (kShare && go_shared) {
+      const int unit = kWilson ? (p.walkers > 0 ? p.walkers : 1) : 1;
+      const long long trees_cap = (max_attempts - attempts + nr - 1) / nr;  // trees from tree_no on that may still be examined
+      // (a copy of the chain descriptor goes to the out-of-line function: the original stays in registers)
+      Chain cc = c;
+      const Step stc = st;
+      const SharedOut so = shared_retry<kWilson>(cc, stc, tree_no, unit, (trees_cap + unit - 1) / unit, trees_cap, prop_no, ideal, thr);
+      c.par = cc.par;
+      if (tid == 0) {
+        ctr[RC_CTR_TREES] += (int)so.trees;
+        ctr[kWilson ? RC_CTR_WALK : RC_CTR_ROUNDS] += (int)so.value;
+        if (kWilson) ctr[RC_CTR_ROUNDS] += (int)so.units;
+      }
+      res.trees = (int)(tree_no + (uint32_t)so.trees);
+      if (so.status > 0) { res.status = so.status; return res; }
+      if (so.status < 0) {  // no tree below max_attempts has a balanced cut: the check at the top of the loop reports it
+        tree_no += (uint32_t)trees_cap - 1u;
+        continue;
+      }
+      tree_no = so.tree_no;
+      res.trees = (int)tree_no + 1;
+      attempts = (long long)tree_no * nr;
+      nbal = so.nbal;
+      wsel = so.wsel;
+      batch_lo = tree_no - (uint32_t)so.wsel;
+      batch_hi = batch_lo + (uint32_t)unit;
+    } else if constexpr (kWilson) {
       // ---- P2b: the next batch of trees, one per lane of warp 0; examined in order
       if (tree_no >= batch_hi) {
         long long nw = p.walkers > 0 ? p.walkers : 1;
@@ -1573,11 +1841,107 @@ __device__ __forceinline__ void st_release(int32_t* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// The helper's side of a shared retry (see shared_retry): one unit of somebody else's step.
+// `hc` remembers the pair gathered last, so that staying with a chain costs one gather.
+struct HelpCache { int chain, session; Step st; };
+
+template <bool kWilson>
+__device__ __noinline__ void help_once(Chain& c, HelpCache& hc) {
+  const Params& p = *c.p;
+  const Smem& s = c.s;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int n_chains = p.cfg.n_chains;
+  constexpr int kInf = 0x7fffffff;
+  int32_t* bc = s.misc + M_SPARE0;
+  // a chain that wants help: the first one at or after a CTA-specific start (spreads the helpers)
+  if (tid == 0) s.misc[M_PICK] = kInf;
+  __syncthreads();
+  const int start = (int)(blockIdx.x % (unsigned)n_chains);
+  for (int i = tid; i < n_chains; i += T) {
+    int ch = start + i;
+    if (ch >= n_chains) ch -= n_chains;
+    if (__ldcg(&p.help[ch].epoch) & 1) { atomicMin(&s.misc[M_PICK], i); break; }
+  }
+  __syncthreads();
+  const int pick = s.misc[M_PICK];
+  __syncthreads();
+  if (pick == kInf) { __nanosleep(8000); return; }
+  int ch = start + pick;
+  if (ch >= n_chains) ch -= n_chains;
+  HelpRec* R = p.help + ch;
+  // The record is read under ONE epoch value: every change of it (publish, window slide,
+  // retirement) bumps the epoch, the owner fences between the bump and the next change of a
+  // field, so fields read between two equal reads of the epoch belong to that epoch.  All that
+  // follows - the unit taken, the status word written - is tagged with it and dropped as soon
+  // as the epoch has moved on.
+  if (tid == 0) {
+    const int e = ld_acquire(&R->epoch);
+    s.misc[M_CNT] = __ldcg(&R->pair);
+    s.misc[M_SUBSET] = (int)__ldcg(&R->prop_no);
+    s.misc[M_DELTA] = (int)__ldcg(&R->t_first);
+    s.misc[M_NINT] = __ldcg(&R->unit);
+    s.misc[M_NLIVE] = __ldcg(&R->limit);
+    s.misc[M_NBAL] = __ldcg(&R->base);
+    bc[1] = __ldcg(&R->session);
+    __threadfence();
+    bc[0] = (ld_acquire(&R->epoch) == e && (e & 1)) ? e : 0;
+  }
+  __syncthreads();
+  const int epoch = bc[0], session = bc[1], pair = s.misc[M_CNT], unit = s.misc[M_NINT];
+  const int limit = s.misc[M_NLIVE], base = s.misc[M_NBAL];
+  const uint32_t prop_no = (uint32_t)s.misc[M_SUBSET], t_first = (uint32_t)s.misc[M_DELTA];
+  __syncthreads();
+  if (epoch == 0) return;
+  c.chain = ch;
+  c.gchain = (uint32_t)(ch + p.cfg.chain_offset);
+  c.assign = p.st.d_assignment + (size_t)ch * p.st.assign_stride;
+  c.mask = p.st.d_cut_mask + (size_t)ch * p.st.mask_stride;
+  c.tally = p.st.d_tally + (size_t)ch * p.cfg.n_districts;
+  if (hc.chain != ch || hc.session != session) {
+    // the chain's plan is stable while its record is live (the owner retires it before the commit)
+    hc.chain = -1;
+    Step st;
+    st.a = pair & 0xffff; st.b = pair >> 16;
+    int d_sub = 0;
+    const int rc = gather_pair<kWilson>(c, st, &d_sub);
+    __threadfence();
+    if (tid == 0) bc[0] = ld_acquire(&R->epoch);
+    __syncthreads();
+    const int still = bc[0];
+    __syncthreads();
+    if (rc != RC_OK || still != epoch) return;  // retired (or slid) meanwhile: the plan may have moved under the gather
+    hc.chain = ch; hc.session = session; hc.st = st;
+  }
+  // take a unit
+  if (tid == 0) {
+    int u = -1;
+    const int nx = *(volatile int32_t*)&R->next, won = *(volatile int32_t*)&R->won;
+    if (ld_acquire(&R->epoch) == epoch && nx < base + p.help_win && nx < limit && nx <= won) {
+      u = atomicAdd(&R->next, 1);
+      if (!(u >= base && u < base + p.help_win && u < limit)) u = -1;
+    }
+    bc[0] = u;
+  }
+  __syncthreads();
+  const int u = bc[0];
+  __syncthreads();
+  if (u < 0) { __nanosleep(1000); return; }
+  const double ideal = p.cfg.pop_target;
+  const double thr = __dmul_rn(ideal, p.cfg.epsilon);
+  const UnitResult r = eval_unit<kWilson>(c, hc.st, t_first + (uint32_t)u * (uint32_t)unit, unit, prop_no, ideal, thr);
+  if (tid == 0 && ld_acquire(&R->epoch) == epoch) {
+    const int kind = r.status ? HK_ERR : (r.first_ok >= 0 ? HK_OK : HK_FAIL);
+    st_release64(p.help_status + (size_t)ch * kHelpWin + (u - base), help_pack(epoch, kind, r.first_ok >= 0 ? r.first_ok : 0, r.value));
+    if (kind != HK_FAIL) atomicMin(&R->won, u);
+  }
+  __syncthreads();
+}
+
 // Free-running mode is a persistent grid over a ring of READY chains (see the loop below):
 // every SM stays busy whatever the number of chains and however unevenly the retries fall,
 // and a slow step delays only its own chain.  Replay mode (TEST HOOK) is one CTA walking one
 // chain through the record.
-template <bool kWilson, bool kSpill>
+template <bool kWilson, bool kSpill, bool kShare>
 __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_step_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Chain c;
@@ -1621,6 +1985,15 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
   unsigned long long rt = 0;  // replay: steps are taken in order
   const unsigned long long cap = (unsigned long long)p.ring_cap;
   int flip = 0;
+  // A CTA whose ticket has no ready chain yet (the tail of a launch, or fewer chains than CTAs)
+  // does not sleep on its ring slot: between two looks at the slot it draws one unit of a
+  // step some other CTA is retrying (help_once).  A ticket beyond the last step turns the
+  // CTA into a helper for the rest of the launch, i.e. until every chain-step is done.
+  const bool share = kShare && p.share != 0 && !replay;
+  HelpCache hc;
+  hc.chain = -1; hc.session = 0;
+  unsigned long long ticket = ~0ull;  // ~0: none
+  bool idle = false;
   for (;;) {
     unsigned long long t;
     int chain;
@@ -1629,25 +2002,42 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
       chain = p.rp.chain;
     } else {
       if (tid == 0) {
-        const unsigned long long h = atomicAdd(p.work_counter, 1ull);
-        int ch = -1;
-        if (h < total) {
-          if (h < (unsigned long long)n_chains) {
-            ch = (int)h;
+        if (ticket == ~0ull) ticket = atomicAdd(p.work_counter, 1ull);
+        int ch = -1;  // -1: nothing to step right now, -2: the launch is over
+        if (ticket < total) {
+          if (ticket < (unsigned long long)n_chains) {
+            ch = (int)ticket;
           } else {
-            int32_t* slot = p.ring + (h - (unsigned long long)n_chains) % cap;
-            int v;
-            while ((v = ld_acquire(slot)) == 0) __nanosleep(32);
-            st_release(slot, 0);  // the slot may be refilled cap pushes later
-            ch = v - 1;
+            int32_t* slot = p.ring + (ticket - (unsigned long long)n_chains) % cap;
+            int v = ld_acquire(slot);
+            if (!share) while (v == 0) { __nanosleep(32); v = ld_acquire(slot); }
+            if (v != 0) {
+              st_release(slot, 0);  // the slot may be refilled cap pushes later
+              ch = v - 1;
+            }
           }
+        } else if (!share || *(volatile unsigned long long*)p.steps_done >= total) {
+          ch = -2;
         }
+        if (ch >= 0) ticket = ~0ull;
+        if (share && (ch == -1) != idle) atomicAdd(p.idle, ch == -1 ? 1 : -1);
         tslot[flip] = ch;
       }
       __syncthreads();
       chain = tslot[flip];
       flip ^= 1;
       RC_PH(PH_TICKET);
+      if (chain == -1) {
+        idle = true;
+        if constexpr (kShare) {
+          Chain cc = c;  // out-of-line: keeps the step path's registers out of it
+          help_once<kWilson>(cc, hc);
+          c.par = cc.par;
+        }
+        continue;
+      }
+      idle = false;
+      hc.chain = -1;  // this CTA's shared memory is about to hold another pair
       t = chain < 0 ? total : 0;
     }
     if (t >= total) break;
@@ -1666,9 +2056,9 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
       for (int streak = 0; streak < streak_cap; ++streak) {
         if constexpr (kWilson) {
           if (p.cfg.proposal_kind == RC_PROPOSAL_REVERSIBLE && !replay) r = propose_reversible(c, prop_no, ctr);
-          else r = propose<kWilson>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
+          else r = propose<kWilson, kShare>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
         } else {
-          r = propose<kWilson>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
+          r = propose<kWilson, kShare>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
         }
         ++prop_no;
         __syncthreads();
@@ -1700,6 +2090,7 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
     if (!replay && tid == 0) {
       const int done = __ldcg(p.progress + chain) + 1;  // this CTA owns the chain until it is pushed back
       p.progress[chain] = done;
+      atomicAdd(p.steps_done, 1ull);
       if (done < p.n_steps) {
         const unsigned long long q = atomicAdd(p.work_counter + 1, 1ull);
         int32_t* slot = p.ring + q % cap;

@@ -182,6 +182,31 @@ def test_node_repeats_and_tight_bounds():
     assert eng.counters.cpu().numpy()[:, _abi.RC_CTR_INVALID].sum() > 0
 
 
+def test_shared_retries_bit_exact_with_oracle(monkeypatch):
+    """Shared retries: CTAs with no chain to step draw the later spanning trees of a step
+    another CTA is retrying (tree.py:679-718); the lowest tree with a balanced cut wins, so the
+    chains - and their tree / attempt / draw counters - must not change.  Forced on for every
+    launch (RECOM_B200_SHARE=1): a full grid with a tail (config 3, 640 chains, heavy-tailed
+    retries), a status window of 3 units instead of 256 (RECOM_B200_HELP_WIN: every shared step
+    slides it), a handful of chains with hundreds of helpers, and Wilson batches."""
+    monkeypatch.setenv("RECOM_B200_SHARE", "1")
+    csr, plan, cfg = workloads.config3(n_chains=640, seed=77)
+    _free_run_vs_oracle(csr, plan, cfg, 12)
+    monkeypatch.setenv("RECOM_B200_HELP_WIN", "3")
+    csr, plan, cfg = workloads.config3(n_chains=24, seed=9)
+    eng = _free_run_vs_oracle(csr, plan, cfg, 30)
+    assert eng.counters.cpu().numpy()[:, _abi.RC_CTR_TREES].max() > 150  # steps of more than 8 + 3 trees happened
+    monkeypatch.delenv("RECOM_B200_HELP_WIN")
+    csr, plan, cfg = workloads.config3(n_chains=3, seed=78)
+    _free_run_vs_oracle(csr, plan, cfg, 40)
+    csr, plan, cfg = workloads.config3(n_chains=40, seed=79, tree_kind=_abi.RC_TREE_WILSON)
+    eng = _free_run_vs_oracle(csr, plan, cfg, 12)
+    from oracle import oracle
+
+    ora = oracle.OracleChains(csr, cfg, plan).run(12, n_threads=8)
+    assert np.array_equal(eng.counters.cpu().numpy()[:, _abi.RC_CTR_WALK], ora.counters[:, _abi.RC_CTR_WALK])
+
+
 def test_max_attempts_status():
     # reference tests/test_region_aware.py:102-112: max_attempts=1 -> RuntimeError
     csr, plan, cfg = workloads.config1(n_chains=8, seed=5, max_attempts=1)
