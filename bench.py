@@ -47,6 +47,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 REF_SHIM = os.path.join(ROOT, "oracle", "refshim")
 WORKLOADS = ["config1", "config2", "config3", "config4", "config5"]
+N_CUT_BINS = 1 << 15  # cut-edge histogram bins (config 4 plans have ~12k cut edges)
 
 
 def parse():
@@ -65,7 +66,7 @@ def parse():
                     help="--impl reference: the Python reference (oracle/_ref) or the C oracle port")
     ap.add_argument("--extras", default="default",
                     help="comma list of extra workloads timed in the same process "
-                         "(config3,config5,config3_strong,config3_wilson,config4), 'default' or 'none'")
+                         "(config3,config5,config3_strong,config3_short,config3_wilson,config4), 'default' or 'none'")
     ap.add_argument("--threads-per-cta", type=int, default=0)
     ap.add_argument("--wilson", action="store_true", help="uniform_spanning_tree instead of random_spanning_tree")
     ap.add_argument("--cap-nodes", type=int, default=0)
@@ -446,7 +447,7 @@ def measure(D, flush, workload, chains, S, steps, warmup, seed, wilson=False, e2
         flush.fill_(1)
         eng.run(S)
         ms_k = eng.last_run_ms()  # CUDA events around the chain-step kernel on its stream
-        cut_hist, dev_hist = eng.histograms(4096, 64, 0.001)  # the checkpoint: ensemble histograms ...
+        cut_hist, dev_hist = eng.histograms(N_CUT_BINS, 64, 0.001)  # the checkpoint: ensemble histograms ...
         D.all_reduce(cut_hist)                                 # ... all-reduced over the ranks (NCCL)
         D.all_reduce(dev_hist)
         return ms_k
@@ -493,7 +494,7 @@ def measure(D, flush, workload, chains, S, steps, warmup, seed, wilson=False, e2
         "bytes_total": bytes_total, "tot": tot,
         # per GPU: bytes of this rank's launches / this rank's kernel time == total/world / kernel_ms
         "achieved_gbs": bytes_total / D.world / (kernel_ms * 1e-3) / 1e9,
-        "mean_cut_edges": float((cut_hist.cpu().numpy() * np.arange(4096)).sum() / max(int(cut_hist.sum()), 1)),
+        "mean_cut_edges": float((cut_hist.cpu().numpy() * np.arange(N_CUT_BINS)).sum() / max(int(cut_hist.sum()), 1)),
         "chains_in_histogram": int(cut_hist.sum()),
     }
     if e2e:
@@ -563,10 +564,13 @@ EXTRAS = {
     "config3": ("config3", False, lambda w: 1024, 512, 5, "weak"),
     "config5": ("config5", False, lambda w: 1024, 512, 5, "weak"),
     "config3_strong": ("config3", False, lambda w: 8192 // w, 64, 5, "strong"),
-    "config3_wilson": ("config3", True, lambda w: 1024, 64, 4, "weak"),
+    # short launches (a checkpoint every 32 steps): the heavy-tailed retries of a few chains set
+    # the pace unless the CTAs that run out of chains help (shared retries)
+    "config3_short": ("config3", False, lambda w: 1024, 32, 8, "weak"),
+    "config3_wilson": ("config3", True, lambda w: 1024, 256, 4, "weak"),
     "config4": ("config4", True, lambda w: 1024, 8, 3, "weak"),
 }
-DEFAULT_EXTRAS = ["config3", "config5", "config3_strong", "config3_wilson", "config4"]
+DEFAULT_EXTRAS = ["config3", "config5", "config3_strong", "config3_short", "config3_wilson", "config4"]
 
 
 def run_b200(args):

@@ -284,7 +284,7 @@ __host__ __device__ inline size_t wilson_layout(Smem* s, unsigned char* base, in
 // misc[] slots
 enum { M_WSUM = 0 /* 0..63: two alternating banks of 32 warp sums */,
        M_ERR = 65, M_PICK, M_CNT, M_TOT, M_NINT, M_SUBSET, M_DELTA, M_NLIVE, M_NBAL, M_TAILLEN, M_NV, M_WALKER /* Wilson: the warp whose lanes walk */, M_SPARE0, M_SPARE1 /* 78..79 */,
-       M_BEST64 = 80 /* 80..81, 8-byte aligned */, M_TICKET = 82 /* 82..85: two 8-byte slots */,
+       M_BEST64 = 80 /* 80..81, 8-byte aligned */, M_TICKET = 82 /* 82..83 */,
        M_ROOTKIDS = 86 /* Wilson: children of the tree root */, M_CTR = 88 /* 88..95 counters */ };
 // wmeta[] rows (Wilson, per walker)
 enum { WM_ROOT = 0, WM_DRAWS = 32, WM_ERR = 64 };

@@ -192,6 +192,10 @@ __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
     const int w = w0 + tid;
     uint32_t bits = 0;
     if (w < NW) {
+      // (the row is the one contiguous slice of the step; a single 1-D bulk copy of it into shared
+      // memory - cp.async.bulk + mbarrier - was measured against these loads, scripts/dev/tma_bench.cu:
+      // 1142 vs 740 cycles for a 10 KB row alone on the SM, 1576 vs 1697 with 3 CTAs per SM, i.e.
+      // +-0.1 % of a step - not worth the staging buffer)
       const uint4* src = reinterpret_cast<const uint4*>(c.assign + (size_t)w * 32);
       bits = match16(__ldcg(src), a4, b4);
       if (w * 32 + 16 < N) bits |= match16(__ldcg(src + 1), a4, b4) << 16;
