@@ -204,14 +204,18 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
     // the walkers' state in shared memory and the adjacency in L2; else both in L2
     size_t glob = 0;
     int level = 0;
+    const int msh = N >= 65536 ? 2 : 0;  // large graphs: a popcount prefix per four bitmap words
+    p.mpref_shift = msh;
     for (;;) {
-      total = rc::wilson_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R, W, sh, level, nullptr, nullptr, &glob, &cold);
+      total = rc::wilson_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R, W, sh, level, msh, nullptr, nullptr, &glob, &cold);
       if (total <= smem_max) break;
       if (cfg->wilson_walkers == 0 && W > 2 && level < 2) { W >>= 1; continue; }
       if (level == 2) break;
       ++level;
       W = cfg->wilson_walkers > 0 ? cfg->wilson_walkers : (cfg->proposal_kind == RC_PROPOSAL_REVERSIBLE ? 1 : 4);
     }
+    // (level 1, config 4: two CTAs per SM with two walkers each were measured against one CTA with
+    // four - 5.1 k vs 5.7 k steps/s: the second CTA's adjacency pushes the first one's out of L2)
     p.walkers = W;
     p.wilson_level = level;
     split = total;
@@ -281,7 +285,7 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   if (e->spill) {
     // spill mode: every step of a walk is a round trip to the CTA's scratch block; keep the
     // blocks of the resident CTAs inside L2 (126 MB) rather than have more CTAs wait on DRAM
-    const size_t per_cta = e->spill_bytes + e->cold_bytes + (size_t)(cap_nodes + cap_edges) * 4;
+    const size_t per_cta = e->spill_bytes + (e->cold_bytes + (size_t)(cap_nodes + cap_edges) * 4) / 4;  // the streamed arrays are touched once
     long long fit = (long long)((size_t)96 << 20) / (long long)(per_cta ? per_cta : 1);
     fit = fit / e->n_sms * e->n_sms;
     if (fit < e->n_sms) fit = e->n_sms;

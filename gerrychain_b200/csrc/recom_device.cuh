@@ -72,6 +72,7 @@ struct Params {
   int32_t walkers;        // Wilson: spanning trees drawn concurrently per chain-step (lanes of one warp)
   int32_t nbr_shift;      // Wilson: log2 of the adjacency slots per node kept in the hot tier
   int32_t wilson_level;   // Wilson: 0 = state and adjacency in shared memory, 1 = adjacency in L2, 2 = both in L2
+  int32_t mpref_shift;    // Wilson: Smem.msh
   HelpRec* help;                       // [n_chains]
   unsigned long long* help_status;     // [n_chains][kHelpWin]
   int32_t* idle;                       // CTAs of this launch that have no chain to step
@@ -85,7 +86,8 @@ struct Smem {
   int32_t* misc;     // [128]
   // whole step
   uint32_t* mbits;   // [NW] membership bitmap of the merged pair over global node ids
-  lid_t* mpref;      // [NW] exclusive prefix popcount: local id = mpref[w] + popc(below)
+  lid_t* mpref;      // [NW >> msh] exclusive prefix popcount of every (1 << msh)-th word: local id = prefix + popc(below)
+  int msh;           // 0: a prefix per bitmap word; 2: per four words (Wilson on large graphs: 3/4 of the array saved)
   int32_t* pop;      // [CN]   population of local node i                      (cold tier)
   uint32_t* euv;     // [CE]   local edge j = (u | v << 16), u < v, ascending edge id  (cold tier)
   uint32_t* tflag;   // [CE/32] tree-edge bitmap over local edges
@@ -229,7 +231,7 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
 // Returns the bytes of shared memory for `level`; *glob_out the bytes of the global block
 // (S and/or A), *cold_out the cold bytes.
 __host__ __device__ inline size_t wilson_layout(Smem* s, unsigned char* base, int N, int CN, int CE, int R, int W,
-                                                int nbr_shift, int level, unsigned char* glob, unsigned char* cold,
+                                                int nbr_shift, int level, int msh, unsigned char* glob, unsigned char* cold,
                                                 size_t* glob_out = nullptr, size_t* cold_out = nullptr) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return r; };
@@ -238,7 +240,7 @@ __host__ __device__ inline size_t wilson_layout(Smem* s, unsigned char* base, in
   size_t o_meta = take(4 * 32 * 4);
   size_t o_ring = take(size_t(W) * 128 * 4);
   size_t o_mbits = take(size_t(NW) * 4);
-  size_t o_mpref = take(size_t(NW) * 2);
+  size_t o_mpref = take(size_t((NW >> msh) + 1) * 2);
   const size_t core = o;
   size_t o_oldb = take(size_t((CN + 31) / 32) * 4);
   size_t o_newb = take(size_t((CN + 31) / 32) * 4);
@@ -263,6 +265,7 @@ __host__ __device__ inline size_t wilson_layout(Smem* s, unsigned char* base, in
     s->wring = (uint32_t*)(base + o_ring);
     s->mbits = (uint32_t*)(base + o_mbits);
     s->mpref = (lid_t*)(base + o_mpref);
+    s->msh = msh;
     // the global block starts where shared memory ends: offsets beyond `smem` move there
     unsigned char* hs = level == 2 ? glob - smem : base;
     unsigned char* ha = level == 0 ? base : glob - smem;

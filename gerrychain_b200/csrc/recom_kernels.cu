@@ -39,7 +39,10 @@ struct Chain {
 // ---- membership of a global node in the merged pair, and its local id ---------------------
 __device__ __forceinline__ bool is_member(const Smem& s, int g) { return (s.mbits[g >> 5] >> (g & 31)) & 1u; }
 __device__ __forceinline__ int local_id(const Smem& s, int g) {
-  return (int)s.mpref[g >> 5] + __popc(s.mbits[g >> 5] & ((1u << (g & 31)) - 1u));
+  const int w = g >> 5;
+  int id = (int)s.mpref[w >> s.msh] + __popc(s.mbits[w] & ((1u << (g & 31)) - 1u));
+  for (int k = (w >> s.msh) << s.msh; k < w; ++k) id += __popc(s.mbits[k]);  // msh == 0: none
+  return id;
 }
 
 // 4 assignment bytes -> 4 bits (byte k == a or == b)
@@ -205,7 +208,7 @@ __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
     }
     int tot;
     const int ex = block_excl_scan(__popc(bits), &tot, s.misc, c.par);
-    if (w < NW) s.mpref[w] = (lid_t)min(n + ex, 0xffff);
+    if (w < NW && (w & ((1 << s.msh) - 1)) == 0) s.mpref[w >> s.msh] = (lid_t)min(n + ex, 0xffff);
     if (use_tab) {
       int o = n + ex;
       for (uint32_t x = bits; x; x &= x - 1, ++o)
@@ -235,13 +238,14 @@ __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
       if (use_tab) {
         g = (int)l2g[i];
       } else {
-        int lo = 0, hi = NW;  // first word whose prefix exceeds i
+        int lo = 0, hi = (NW + (1 << s.msh) - 1) >> s.msh;  // first prefix entry that exceeds i
         while (lo < hi) {
           const int mid = (lo + hi) >> 1;
           if ((int)s.mpref[mid] > i) hi = mid; else lo = mid + 1;
         }
-        const int w = lo - 1;
-        g = w * 32 + (int)__fns(s.mbits[w], 0, i - (int)s.mpref[w] + 1);
+        int w = (lo - 1) << s.msh, rem = i - (int)s.mpref[lo - 1];
+        for (int pc; rem >= (pc = __popc(s.mbits[w])); ++w) rem -= pc;
+        g = w * 32 + (int)__fns(s.mbits[w], 0, rem + 1);
       }
       r0 = __ldg(p.g.row_ptr + g);
       r1 = __ldg(p.g.row_ptr + g + 1);
@@ -1951,7 +1955,7 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
   Chain c;
   c.p = &p;
   if constexpr (kWilson)
-    wilson_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R, p.walkers, p.nbr_shift, p.wilson_level,
+    wilson_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R, p.walkers, p.nbr_shift, p.wilson_level, p.mpref_shift,
                   p.spill + (size_t)blockIdx.x * p.spill_stride, p.cold + (size_t)blockIdx.x * p.cold_stride);
   else
     smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R,

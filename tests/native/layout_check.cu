@@ -71,7 +71,8 @@ static bool check_wilson(int N, int CN, int CE, int R, int W, int sh) {
     static unsigned char sm[1], gl[1], co[1];
     Smem s;
     size_t glob = 0, cold = 0;
-    const size_t smem = wilson_layout(&s, sm, N, CN, CE, R, W, sh, level, gl, co, &glob, &cold);
+    const int msh = N >= 65536 ? 2 : 0;
+    const size_t smem = wilson_layout(&s, sm, N, CN, CE, R, W, sh, level, msh, gl, co, &glob, &cold);
     std::vector<Span> in_sm, in_gl, in_co;
     auto put = [&](const char* name, const void* p, size_t bytes, int tier) {
       const unsigned char* q = (const unsigned char*)p;
@@ -82,7 +83,7 @@ static bool check_wilson(int N, int CN, int CE, int R, int W, int sh) {
       else in_gl.push_back(Span{name, (size_t)(q - gl), (size_t)(q - gl) + bytes});
     };
     put("misc", s.misc, 512, 0); put("wmeta", s.wmeta, 512, 0); put("wring", s.wring, (size_t)W * 512, 0);
-    put("mbits", s.mbits, 4 * (size_t)NW, 0); put("mpref", s.mpref, 2 * (size_t)NW, 0);
+    put("mbits", s.mbits, 4 * (size_t)NW, 0); put("mpref", s.mpref, 2 * (size_t)((NW >> msh) + 1), 0);
     put("oldb", s.oldb, 4 * (size_t)CW, 1); put("newb", s.newb, 4 * (size_t)CW, 1); put("whas", s.whas, 4 * (size_t)CW, 1);
     put("wsum", s.wsum, 4 * (size_t)CN, 1); put("wst", s.wst, 2 * (size_t)W * CN, 1);
     put("nbr", s.nbr, 4 * ((size_t)(CN + CN / 8) << sh), 2); put("wdeg", s.wdeg, 2 * (size_t)CN, 2);
