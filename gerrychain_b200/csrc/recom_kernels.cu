@@ -349,7 +349,16 @@ __device__ int tree_edge_list(Chain& c, const Step& st) {
   }
   __syncthreads();
   // endpoints of the tree edges, fetched once (L2, independent loads) for the whole tour
-  for (int q = threadIdx.x; q < nt; q += blockDim.x) s.tuv[q] = s.euv[s.te[q]];
+  {
+    const uint32_t* __restrict__ euv = s.euv;
+    const int T = blockDim.x;
+    int q = threadIdx.x;
+    for (; q + T < nt; q += 2 * T) {
+      const uint32_t e0 = __ldcg(euv + s.te[q]), e1 = __ldcg(euv + s.te[q + T]);
+      s.tuv[q] = e0; s.tuv[q + T] = e1;
+    }
+    if (q < nt) s.tuv[q] = __ldcg(euv + s.te[q]);
+  }
   __syncthreads();
   return RC_OK;
 }
@@ -383,7 +392,16 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
       }
     }
   }
-  for (int j = tid; j < m; j += T) { s.lab[j] = s.euv[j]; s.lj[j] = (lid_t)j; }
+  {  // the pair's edge list streams in from the cold tier (L2): four loads in flight per thread
+    const uint32_t* __restrict__ euv = s.euv;
+    int j = tid;
+    for (; j + 3 * T < m; j += 4 * T) {
+      const uint32_t e0 = __ldcg(euv + j), e1 = __ldcg(euv + j + T), e2 = __ldcg(euv + j + 2 * T), e3 = __ldcg(euv + j + 3 * T);
+      s.lab[j] = e0; s.lab[j + T] = e1; s.lab[j + 2 * T] = e2; s.lab[j + 3 * T] = e3;
+      s.lj[j] = (lid_t)j; s.lj[j + T] = (lid_t)(j + T); s.lj[j + 2 * T] = (lid_t)(j + 2 * T); s.lj[j + 3 * T] = (lid_t)(j + 3 * T);
+    }
+    for (; j < m; j += T) { s.lab[j] = __ldcg(euv + j); s.lj[j] = (lid_t)j; }
+  }
   for (int i = tid; i < n; i += T) { s.best[i] = 0xffffffffu; s.bpos[i] = 0xffffffffu; s.hook[i] = (lid_t)i; }
   for (int i = tid; i < (m + 31) >> 5; i += T) s.tflag[i] = 0;
   if (tid == 0) { s.misc[M_NLIVE] = 0; s.misc[M_NV] = 0; }
