@@ -82,8 +82,9 @@ struct Params {
 };
 
 // ---- shared-memory carve-up -------------------------------------------------------
+constexpr int kMiscInts = 160;
 struct Smem {
-  int32_t* misc;     // [128]
+  int32_t* misc;     // [kMiscInts]
   // whole step
   uint32_t* mbits;   // [NW] membership bitmap of the merged pair over global node ids
   lid_t* mpref;      // [NW >> msh] exclusive prefix popcount of every (1 << msh)-th word: local id = prefix + popc(below)
@@ -148,7 +149,7 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return r; };
   const int NW = (N + 31) / 32;
-  size_t o_misc = take(128 * 4);
+  size_t o_misc = take(kMiscInts * 4);
   size_t o_mbits = take(size_t(NW) * 4);
   size_t o_mpref = take(size_t(NW) * 2);
   const size_t split = o;
@@ -236,7 +237,7 @@ __host__ __device__ inline size_t wilson_layout(Smem* s, unsigned char* base, in
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return r; };
   const int NW = (N + 31) / 32;
-  size_t o_misc = take(128 * 4);
+  size_t o_misc = take(kMiscInts * 4);
   size_t o_meta = take(4 * 32 * 4);
   size_t o_ring = take(size_t(W) * 128 * 4);
   size_t o_mbits = take(size_t(NW) * 4);
@@ -288,7 +289,10 @@ __host__ __device__ inline size_t wilson_layout(Smem* s, unsigned char* base, in
 enum { M_WSUM = 0 /* 0..63: two alternating banks of 32 warp sums */,
        M_ERR = 65, M_PICK, M_CNT, M_TOT, M_NINT, M_SUBSET, M_DELTA, M_NLIVE, M_NBAL, M_TAILLEN, M_NV, M_WALKER /* Wilson: the warp whose lanes walk */, M_SPARE0, M_SPARE1 /* 78..79 */,
        M_BEST64 = 80 /* 80..81, 8-byte aligned */, M_TICKET = 82 /* 82..83 */,
-       M_ROOTKIDS = 86 /* Wilson: children of the tree root */, M_CTR = 88 /* 88..95 counters */ };
+       M_ROOTKIDS = 86 /* Wilson: children of the tree root */, M_CTR = 88 /* 88..95 counters */,
+       /* 96..127: phase timers of RC_TIMERS builds */
+       M_HC = 128 /* 128..134: the pair a helper gathered last (chain, session, a, b, n, m, tot) */,
+       M_TICKET64 = 136 /* 136..137: the ticket this CTA holds (8-byte aligned) */ };
 // wmeta[] rows (Wilson, per walker)
 enum { WM_ROOT = 0, WM_DRAWS = 32, WM_ERR = 64 };
 

@@ -1186,6 +1186,32 @@ __device__ bool commit_proposal(Chain& c, const Step& st, int cut_count, long lo
   return true;
 }
 
+// This CTA's descriptor, a pure function of the launch parameters: the out-of-line functions
+// below build their own instead of taking the caller's (a Chain whose address escapes would
+// pin its ~40 pointers in local memory for the whole step path, which otherwise rematerialises
+// them from the shared-memory base).
+template <bool kWilson, bool kSpill>
+__device__ __forceinline__ void chain_layout(Chain& c, const Params& p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  c.p = &p;
+  if constexpr (kWilson)
+    wilson_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R, p.walkers, p.nbr_shift, p.wilson_level, p.mpref_shift,
+                  p.spill + (size_t)blockIdx.x * p.spill_stride, p.cold + (size_t)blockIdx.x * p.cold_stride);
+  else
+    smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R,
+                kSpill ? p.spill + (size_t)blockIdx.x * p.spill_stride : nullptr,
+                p.cold + (size_t)blockIdx.x * p.cold_stride);
+  c.nodes = p.nodes + (size_t)blockIdx.x * p.cap_nodes;
+  c.eids = p.eids + (size_t)blockIdx.x * p.cap_edges;
+}
+__device__ __forceinline__ void chain_bind(Chain& c, const Params& p, int chain) {
+  c.chain = chain;
+  c.gchain = (uint32_t)(chain + p.cfg.chain_offset);
+  c.assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
+  c.mask = p.st.d_cut_mask + (size_t)chain * p.st.mask_stride;
+  c.tally = p.st.d_tally + (size_t)chain * p.cfg.n_districts;
+}
+
 // =========================================================================================
 // Shared retries.  bipartition_tree (tree.py:679-718) draws trees t = 0, 1, 2, ... until one
 // has a balanced cut; the trees are independent of each other (tree t is a pure function of
@@ -1282,7 +1308,7 @@ __device__ long long help_value_sum(const Smem& s, const unsigned long long* ST,
 // only units below `limit` exist (max_attempts), the last of them may hold fewer trees
 // (trees_cap trees in all).
 template <bool kWilson>
-__device__ __noinline__ SharedOut shared_retry(Chain& c, const Step& st, uint32_t t_first, int unit, long long limit_ll,
+__device__ SharedOut shared_retry(Chain& c, const Step& st, uint32_t t_first, int unit, long long limit_ll,
                                   long long trees_cap, uint32_t prop_no, double ideal, double thr) {
   const Params& p = *c.p;
   const Smem& s = c.s;
@@ -1410,8 +1436,51 @@ __device__ __noinline__ SharedOut shared_retry(Chain& c, const Step& st, uint32_
   return out;
 }
 
+// Everything a step does beyond its first kHelpAfter trees, out of line (the step path of the
+// common case keeps its registers): unit after unit here while every CTA has a chain of its
+// own, handed to shared_retry as soon as one has not.
+template <bool kWilson, bool kSpill>
+__device__ __noinline__ SharedOut long_retry(const Params* pp, int chain, int* par, const Step st, uint32_t t_first, int unit,
+                                             long long limit, long long trees_cap, uint32_t prop_no, double ideal, double thr) {
+  const Params& p = *pp;
+  Chain c;
+  chain_layout<kWilson, kSpill>(c, p);
+  chain_bind(c, p, chain);
+  c.par = *par;
+  struct ParOut { int* out; Chain* c; __device__ ~ParOut() { *out = c->par; } } par_out{par, &c};  // hand the scan parity back
+  const Smem& s = c.s;
+  const int tid = threadIdx.x;
+  SharedOut out = {-1, 0u, 0, 0, 0, 0, 0};
+  for (long long u = 0; u < limit; ++u) {
+    if (tid == 0) s.misc[M_SPARE0] = *(volatile int32_t*)p.idle > 0;
+    __syncthreads();
+    const bool idle = s.misc[M_SPARE0] != 0;
+    __syncthreads();
+    if (idle) {
+      SharedOut so = shared_retry<kWilson>(c, st, t_first + (uint32_t)(u * unit), unit, limit - u, trees_cap - u * unit,
+                                           prop_no, ideal, thr);
+      so.trees += out.trees; so.value += out.value; so.units += out.units;
+      return so;
+    }
+    const int nw = (int)min((long long)unit, trees_cap - u * unit);
+    const UnitResult r = eval_unit<kWilson>(c, st, t_first + (uint32_t)(u * unit), nw, prop_no, ideal, thr);
+    out.units += 1;
+    out.value += r.value;
+    out.trees += r.first_ok >= 0 ? r.first_ok + 1 : nw;
+    if (r.status) { out.status = r.status; return out; }
+    if (r.first_ok >= 0) {
+      out.status = RC_OK;
+      out.tree_no = t_first + (uint32_t)(u * unit) + (uint32_t)r.first_ok;
+      out.wsel = r.first_ok;
+      out.nbal = r.nbal;
+      return out;
+    }
+  }
+  return out;  // status -1: no tree below max_attempts has a balanced cut
+}
+
 // One recom proposal + validity + commit (tree_proposals.py:36-146, chain.py:186-195).
-template <bool kWilson, bool kShare>
+template <bool kWilson, bool kShare, bool kSpill>
 __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep* rs,
                                   int32_t* ctr /* smem counters */) {
   const Params& p = *c.p;
@@ -1465,10 +1534,7 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
   if (res.status) return res;
   const int n = st.n, nt = n - 1;
   bool reselect = false;
-  if constexpr (kShare) {  // are there CTAs without a chain?  (read again while every tree is drawn)
-    if (tid == 0) s.misc[M_SPARE0] = *(volatile int32_t*)p.idle > 0;
-    __syncthreads();
-  }
+
   uint32_t batch_lo = t0, batch_hi = t0;  // Wilson: trees [batch_lo, batch_hi) have been walked
   for (uint32_t tree_no = t0;; ++tree_no) {
     // tree.py:679-700 attempt accounting (see oracle/recom_oracle.c rco_bipartition)
@@ -1488,24 +1554,17 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
     // (shared_retry above); checked once per tree / batch, at a point where nothing is in flight
     bool go_shared = false;
     if constexpr (kShare) {
-      // only a step that has already failed kHelpAfter trees asks for help: the common step
-      // (a handful of trees) is not worth a helper's gather, and helpers share SMs with owners
-      if (!rs && !resel && tree_no >= t0 + (uint32_t)kHelpAfter && (!kWilson || tree_no >= batch_hi)) {
-        // thread 0 looked at the idle counter while the previous tree was drawn (no barrier of
-        // its own: the ones of the tree lie in between); it looks again for the next one
-        go_shared = s.misc[M_SPARE0] != 0;
-        __syncthreads();
-        if (tid == 0) s.misc[M_SPARE0] = *(volatile int32_t*)p.idle > 0;
-      }
+      // a step that has already failed kHelpAfter trees leaves the common path for good (long_retry):
+      // the common step (a handful of trees) is not worth a helper's gather
+      go_shared = !rs && !resel && tree_no >= t0 + (uint32_t)kHelpAfter && (!kWilson || tree_no >= batch_hi);
     }
     if (kShare && go_shared) {
       const int unit = kWilson ? (p.walkers > 0 ? p.walkers : 1) : 1;
       const long long trees_cap = (max_attempts - attempts + nr - 1) / nr;  // trees from tree_no on that may still be examined
-      // (a copy of the chain descriptor goes to the out-of-line function: the original stays in registers)
-      Chain cc = c;
-      const Step stc = st;
-      const SharedOut so = shared_retry<kWilson>(cc, stc, tree_no, unit, (trees_cap + unit - 1) / unit, trees_cap, prop_no, ideal, thr);
-      c.par = cc.par;
+      int par = c.par;
+      const SharedOut so = long_retry<kWilson, kSpill>(c.p, c.chain, &par, st, tree_no, unit, (trees_cap + unit - 1) / unit, trees_cap,
+                                                       prop_no, ideal, thr);
+      c.par = par;
       if (tid == 0) {
         ctr[RC_CTR_TREES] += (int)so.trees;
         ctr[kWilson ? RC_CTR_WALK : RC_CTR_ROUNDS] += (int)so.value;
@@ -1869,12 +1928,27 @@ __device__ __forceinline__ void st_release(int32_t* p, int v) {
 
 // The helper's side of a shared retry (see shared_retry): one unit of somebody else's step.
 // `hc` remembers the pair gathered last, so that staying with a chain costs one gather.
-struct HelpCache { int chain, session; Step st; };
+// (kept in shared memory, misc[M_HC..]: registers held across the step loop cost the step path)
+struct HelpCache {
+  int32_t* m;
+  __device__ __forceinline__ int chain() const { return m[0]; }
+  __device__ __forceinline__ int session() const { return m[1]; }
+  __device__ __forceinline__ Step st() const { Step s; s.a = m[2]; s.b = m[3]; s.n = m[4]; s.m = m[5]; s.tot = m[6]; return s; }
+  __device__ __forceinline__ void set(int chain, int session, const Step& s) {  // thread 0, between barriers
+    m[0] = chain; m[1] = session; m[2] = s.a; m[3] = s.b; m[4] = s.n; m[5] = s.m; m[6] = s.tot;
+  }
+};
 
-template <bool kWilson>
-__device__ __noinline__ void help_once(Chain& c, HelpCache& hc) {
-  const Params& p = *c.p;
+template <bool kWilson, bool kSpill>
+__device__ __noinline__ void help_once(const Params* pp, int* par) {
+  const Params& p = *pp;
+  Chain c;
+  chain_layout<kWilson, kSpill>(c, p);
+  c.par = *par;
+  struct ParOut { int* out; Chain* c; __device__ ~ParOut() { *out = c->par; } } par_out{par, &c};  // hand the scan parity back
   const Smem& s = c.s;
+  HelpCache hc;
+  hc.m = s.misc + M_HC;
   const int tid = threadIdx.x, T = blockDim.x;
   const int n_chains = p.cfg.n_chains;
   constexpr int kInf = 0x7fffffff;
@@ -1918,14 +1992,11 @@ __device__ __noinline__ void help_once(Chain& c, HelpCache& hc) {
   const uint32_t prop_no = (uint32_t)s.misc[M_SUBSET], t_first = (uint32_t)s.misc[M_DELTA];
   __syncthreads();
   if (epoch == 0) return;
-  c.chain = ch;
-  c.gchain = (uint32_t)(ch + p.cfg.chain_offset);
-  c.assign = p.st.d_assignment + (size_t)ch * p.st.assign_stride;
-  c.mask = p.st.d_cut_mask + (size_t)ch * p.st.mask_stride;
-  c.tally = p.st.d_tally + (size_t)ch * p.cfg.n_districts;
-  if (hc.chain != ch || hc.session != session) {
+  chain_bind(c, p, ch);
+  if (hc.chain() != ch || hc.session() != session) {
     // the chain's plan is stable while its record is live (the owner retires it before the commit)
-    hc.chain = -1;
+    __syncthreads();
+    if (tid == 0) hc.m[0] = -1;
     Step st;
     st.a = pair & 0xffff; st.b = pair >> 16;
     int d_sub = 0;
@@ -1936,8 +2007,10 @@ __device__ __noinline__ void help_once(Chain& c, HelpCache& hc) {
     const int still = bc[0];
     __syncthreads();
     if (rc != RC_OK || still != epoch) return;  // retired (or slid) meanwhile: the plan may have moved under the gather
-    hc.chain = ch; hc.session = session; hc.st = st;
+    if (tid == 0) hc.set(ch, session, st);
+    __syncthreads();
   }
+  const Step hst = hc.st();
   // take a unit
   if (tid == 0) {
     int u = -1;
@@ -1954,7 +2027,7 @@ __device__ __noinline__ void help_once(Chain& c, HelpCache& hc) {
   if (u < 0) { __nanosleep(1000); return; }
   const double ideal = p.cfg.pop_target;
   const double thr = __dmul_rn(ideal, p.cfg.epsilon);
-  const UnitResult r = eval_unit<kWilson>(c, hc.st, t_first + (uint32_t)u * (uint32_t)unit, unit, prop_no, ideal, thr);
+  const UnitResult r = eval_unit<kWilson>(c, hst, t_first + (uint32_t)u * (uint32_t)unit, unit, prop_no, ideal, thr);
   if (tid == 0 && ld_acquire(&R->epoch) == epoch) {
     const int kind = r.status ? HK_ERR : (r.first_ok >= 0 ? HK_OK : HK_FAIL);
     st_release64(p.help_status + (size_t)ch * kHelpWin + (u - base), help_pack(epoch, kind, r.first_ok >= 0 ? r.first_ok : 0, r.value));
@@ -1968,20 +2041,10 @@ __device__ __noinline__ void help_once(Chain& c, HelpCache& hc) {
 // and a slow step delays only its own chain.  Replay mode (TEST HOOK) is one CTA walking one
 // chain through the record.
 template <bool kWilson, bool kSpill, bool kShare>
-__global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_step_kernel(const Params p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_step_kernel(const __grid_constant__ Params p) {
   Chain c;
-  c.p = &p;
-  if constexpr (kWilson)
-    wilson_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R, p.walkers, p.nbr_shift, p.wilson_level, p.mpref_shift,
-                  p.spill + (size_t)blockIdx.x * p.spill_stride, p.cold + (size_t)blockIdx.x * p.cold_stride);
-  else
-    smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R,
-                kSpill ? p.spill + (size_t)blockIdx.x * p.spill_stride : nullptr,
-                p.cold + (size_t)blockIdx.x * p.cold_stride);
+  chain_layout<kWilson, kSpill>(c, p);
   const int tid = threadIdx.x;
-  c.nodes = p.nodes + (size_t)blockIdx.x * p.cap_nodes;
-  c.eids = p.eids + (size_t)blockIdx.x * p.cap_edges;
   c.par = 0;
 #ifdef RC_TIMERS
   if (tid < 30) c.s.misc[96 + tid] = 0;  // misc[96..127]: per-CTA phase cycles (+ last stamp), flushed at exit
@@ -2017,8 +2080,10 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
   // CTA into a helper for the rest of the launch, i.e. until every chain-step is done.
   const bool share = kShare && p.share != 0 && !replay;
   HelpCache hc;
-  hc.chain = -1; hc.session = 0;
-  unsigned long long ticket = ~0ull;  // ~0: none
+  hc.m = c.s.misc + M_HC;
+  unsigned long long* const ticket_p = reinterpret_cast<unsigned long long*>(c.s.misc + M_TICKET64);  // thread 0's
+  if (tid == 0) { hc.m[0] = -1; hc.m[1] = 0; *ticket_p = ~0ull; }  // ~0: no ticket
+  __syncthreads();
   bool idle = false;
   for (;;) {
     unsigned long long t;
@@ -2028,6 +2093,7 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
       chain = p.rp.chain;
     } else {
       if (tid == 0) {
+        unsigned long long ticket = *ticket_p;
         if (ticket == ~0ull) ticket = atomicAdd(p.work_counter, 1ull);
         int ch = -1;  // -1: nothing to step right now, -2: the launch is over
         if (ticket < total) {
@@ -2045,7 +2111,7 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
         } else if (!share || *(volatile unsigned long long*)p.steps_done >= total) {
           ch = -2;
         }
-        if (ch >= 0) ticket = ~0ull;
+        *ticket_p = ch >= 0 ? ~0ull : ticket;
         if (share && (ch == -1) != idle) atomicAdd(p.idle, ch == -1 ? 1 : -1);
         tslot[flip] = ch;
       }
@@ -2056,14 +2122,14 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
       if (chain == -1) {
         idle = true;
         if constexpr (kShare) {
-          Chain cc = c;  // out-of-line: keeps the step path's registers out of it
-          help_once<kWilson>(cc, hc);
-          c.par = cc.par;
+          int par = c.par;
+          help_once<kWilson, kSpill>(&p, &par);  // out of line, with a descriptor of its own
+          c.par = par;
         }
         continue;
       }
       idle = false;
-      hc.chain = -1;  // this CTA's shared memory is about to hold another pair
+      if (kShare && tid == 0) hc.m[0] = -1;  // this CTA's shared memory is about to hold another pair
       t = chain < 0 ? total : 0;
     }
     if (t >= total) break;
@@ -2082,9 +2148,9 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
       for (int streak = 0; streak < streak_cap; ++streak) {
         if constexpr (kWilson) {
           if (p.cfg.proposal_kind == RC_PROPOSAL_REVERSIBLE && !replay) r = propose_reversible(c, prop_no, ctr);
-          else r = propose<kWilson, kShare>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
+          else r = propose<kWilson, kShare, kSpill>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
         } else {
-          r = propose<kWilson, kShare>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
+          r = propose<kWilson, kShare, kSpill>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
         }
         ++prop_no;
         __syncthreads();
