@@ -61,7 +61,11 @@ struct RcEngine {
   bool spill = false;
   const void* kernel = nullptr;
   const void* kernel_share = nullptr;  // the build with shared retries
-  int share_mode = 2;                  // RECOM_B200_SHARE: 0 never, 1 always, 2 (default) short launches / spare CTAs
+  int share_mode = 2;                  // RECOM_B200_SHARE: 0 never, 1 always, 2 (default) whichever build measures faster
+  double ms_avg[2] = {0, 0};           // launch time of the plain / shared-retry build at stat_steps steps per launch
+  int n_obs[2] = {0, 0}, n_tried[2] = {0, 0}, since_explore = 0;
+  int64_t stat_steps = -1;
+  struct Obs { cudaEvent_t a = nullptr, b = nullptr; bool share = false, pending = false; int64_t steps = 0; } obs[8];
   int64_t launches = 0;
   // owned device memory
   int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_slot_edge = nullptr, *d_edge_uv = nullptr,
@@ -94,6 +98,7 @@ int rc_engine_destroy(RcEngine* e) {
   cudaFree(e->d_pop); cudaFree(e->d_region); cudaFree(e->d_scratch); cudaFree(e->d_cc_scratch);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  for (auto& o : e->obs) { if (o.a) cudaEventDestroy(o.a); if (o.b) cudaEventDestroy(o.b); }
   delete e;
   return RC_OK;
 }
@@ -389,16 +394,56 @@ int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream) {
   void* args[] = {(void*)&p};
   // shared retries where the tail of the launch matters: few steps per chain, or spare CTAs
   const int n_chains = e->p.cfg.n_chains;
-  // Measured on B200 (config 3, 1024 chains): 32 steps per launch 0.26 M -> 1.11 M steps/s with shared
-  // retries, 512 steps per launch 2.48 M -> 2.30 M (the build costs the step path registers and a
-  // bigger loop), and with fewer chains than CTAs the polling helpers cost more than the rare
-  // stuck step returns.  Hence: short launches of a full grid only (RECOM_B200_SHARE=0/1 forces it).
-  const bool share = p.share && e->share_mode != 0 && (e->share_mode == 1 || (n_steps < 128 && n_chains >= e->grid));
+  // Which build?  Shared retries cut the tail of a launch (config 3, 1024 chains x 32 steps: 0.26 M ->
+  // 1.1 M steps/s; the slowest of 5 launches of 512 steps: -30 %) and cost the step path 12-17 %
+  // (a bigger kernel, out-of-line retries); with fewer chains than CTAs the polling helpers cost
+  // more than the rare stuck step returns.  How heavy the tail is depends on the workload (how
+  // rare balanced cuts are), so the engine measures: launches of the same length are timed with
+  // CUDA events, each build is tried twice, then the faster one is used and the other one tried
+  // again every 16th launch.  The chains are bit-identical either way.  RECOM_B200_SHARE=0/1 forces it.
+  for (auto& o : e->obs) {  // harvest the launches that have finished since
+    if (!o.pending || cudaEventQuery(o.b) != cudaSuccess) continue;
+    float ms = 0.f;
+    if (o.steps == e->stat_steps && cudaEventElapsedTime(&ms, o.a, o.b) == cudaSuccess) {
+      const int v = o.share ? 1 : 0;
+      e->ms_avg[v] = e->n_obs[v] == 0 ? ms : 0.7 * e->ms_avg[v] + 0.3 * ms;
+      e->n_obs[v]++;
+    }
+    o.pending = false;
+  }
+  if (e->stat_steps != n_steps) {
+    e->stat_steps = n_steps;
+    e->n_obs[0] = e->n_obs[1] = e->n_tried[0] = e->n_tried[1] = e->since_explore = 0;
+  }
+  bool share = false;
+  if (p.share && e->share_mode != 0 && n_chains >= e->grid) {
+    if (e->share_mode == 1) share = true;
+    else if (e->n_tried[0] < 2) share = false;
+    else if (e->n_tried[1] < 2) share = true;
+    else if (e->n_obs[0] > 0 && e->n_obs[1] > 0) {
+      share = e->ms_avg[1] < e->ms_avg[0];
+      if (++e->since_explore >= 16) { e->since_explore = 0; share = !share; }
+    }
+  } else if (p.share && e->share_mode == 1) {
+    share = true;
+  }
+  e->n_tried[share ? 1 : 0]++;
+  RcEngine::Obs* slot = nullptr;
+  for (auto& o : e->obs)
+    if (!o.pending) { slot = &o; break; }
+  if (slot) {
+    if (!slot->a) { CUDA_OK(cudaEventCreate(&slot->a)); CUDA_OK(cudaEventCreate(&slot->b)); }
+    CUDA_OK(cudaEventRecord(slot->a, s));
+  }
   const int grid = share ? e->grid : (n_chains < e->grid ? n_chains : e->grid);
   CUDA_OK(cudaLaunchKernel(share ? e->kernel_share : e->kernel, dim3(grid), dim3(e->threads), args, e->smem, s));
   e->launches++;
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(e->ev1, s));
+  if (slot) {
+    CUDA_OK(cudaEventRecord(slot->b, s));
+    slot->share = share; slot->steps = n_steps; slot->pending = true;
+  }
   e->timed = true;
   return RC_OK;
 }
