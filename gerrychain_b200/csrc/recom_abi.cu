@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -11,6 +12,8 @@
 #include "recom_stats.cu"
 
 namespace {
+std::mutex g_const_mutex;            // guards g_const_event and the order of writes to rc::g_params
+cudaEvent_t g_const_event[64] = {};  // per device: the last launch that reads rc::g_params
 
 thread_local char g_err[512] = "";
 
@@ -276,12 +279,20 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   e->kernel_share = wilson ? (const void*)rc::recom_step_kernel<true, false, true>
                            : (e->spill ? (const void*)rc::recom_step_kernel<false, true, true> : (const void*)rc::recom_step_kernel<false, false, true>);
   CUDA_OK_E(cudaFuncSetAttribute(e->kernel_share, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  if (const char* sm = getenv("RECOM_B200_SHARE")) e->share_mode = sm[0] == '0' ? 0 : sm[0] == '1' ? 1 : 2;
+  if (const char* sm = getenv("RECOM_B200_SHARE")) e->share_mode = sm[0] == '0' ? 0 : sm[0] == '1' ? 1 : sm[0] == '3' ? 3 : 2;
   p.help_win = rc::kHelpWin;
   if (const char* hw = getenv("RECOM_B200_HELP_WIN")) {  // test knob: a tiny window makes every shared step slide it
     const int v = atoi(hw);
     if (v >= 1 && v <= rc::kHelpWin) p.help_win = v;
   }
+  p.recruit_after = 128;     // tuning knobs of the shared retries (recom_kernels.cu long_retry / shared_retry)
+  p.units_per_recruit = 1;
+  p.help_after = rc::kHelpAfter;
+  p.recruit_mult = 1;
+  if (const char* v = getenv("RECOM_B200_HELP_AFTER")) p.help_after = std::max(1, atoi(v));
+  if (const char* v = getenv("RECOM_B200_RECRUIT_MULT")) p.recruit_mult = std::max(1, atoi(v));
+  if (const char* v = getenv("RECOM_B200_RECRUIT_AFTER")) p.recruit_after = std::max(1, atoi(v));
+  if (const char* v = getenv("RECOM_B200_UNITS_PER_RECRUIT")) p.units_per_recruit = std::max(1, atoi(v));
   CUDA_OK_E(cudaFuncSetAttribute(e->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   CUDA_OK_E(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->ctas_per_sm, e->kernel, e->threads, e->smem));
   if (e->ctas_per_sm < 1) { rc_engine_destroy(e); return fail(RC_ERR_CAPACITY, "kernel does not fit an SM"); }
@@ -317,7 +328,8 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   // + shared-retry board: one record and one window of status words per chain
   const size_t o_help = (b_prog + 63) & ~size_t(63);
   const size_t o_hstat = o_help + (size_t)cfg->n_chains * sizeof(rc::HelpRec);
-  b_prog = o_hstat + (size_t)cfg->n_chains * rc::kHelpWin * sizeof(unsigned long long);
+  const size_t o_hbits = o_hstat + (size_t)cfg->n_chains * rc::kHelpWin * sizeof(unsigned long long);
+  b_prog = o_hbits + ((size_t)cfg->n_chains / 32 + 1) * sizeof(uint32_t);
   size_t b_spill = (size_t)e->grid * e->spill_bytes;
   size_t b_cold = (size_t)e->grid * e->cold_bytes;
   e->scratch_bytes = al(b_nodes) + al(b_eids) + al(b_bad) + al(b_prog) + al(b_spill) + al(b_cold);
@@ -336,6 +348,8 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   p.steps_done = (unsigned long long*)(base + 128);
   p.help = (rc::HelpRec*)(base + o_help);
   p.help_status = (unsigned long long*)(base + o_hstat);
+  p.help_bits = (uint32_t*)(base + o_hbits);
+  p.help_count = (int32_t*)(base + 192);
   p.share = (cfg->allow_pair_reselection || cfg->proposal_kind == RC_PROPOSAL_REVERSIBLE || cfg->node_repeats < 1) ? 0 : 1;
   base += al(b_prog);
   p.spill = b_spill ? (unsigned char*)base : nullptr;
@@ -427,6 +441,7 @@ int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream) {
   } else if (p.share && e->share_mode == 1) {
     share = true;
   }
+  if (e->share_mode == 3) { share = true; p.share = 0; }  // dev: the shared-retry build with the protocol switched off
   e->n_tried[share ? 1 : 0]++;
   RcEngine::Obs* slot = nullptr;
   for (auto& o : e->obs)
@@ -436,7 +451,19 @@ int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream) {
     CUDA_OK(cudaEventRecord(slot->a, s));
   }
   const int grid = share ? e->grid : (n_chains < e->grid ? n_chains : e->grid);
-  CUDA_OK(cudaLaunchKernel(share ? e->kernel_share : e->kernel, dim3(grid), dim3(e->threads), args, e->smem, s));
+  if (share) {
+    // the shared-retry build reads Params from constant memory in its out-of-line parts
+    // (rc::g_params); launches that write it are ordered by an event per device
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    cudaEvent_t& ev = g_const_event[e->device & 63];
+    if (!ev) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    else CUDA_OK(cudaStreamWaitEvent(s, ev, 0));
+    CUDA_OK(cudaMemcpyToSymbolAsync(rc::g_params, &p, sizeof(p), 0, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaLaunchKernel(e->kernel_share, dim3(grid), dim3(e->threads), args, e->smem, s));
+    CUDA_OK(cudaEventRecord(ev, s));
+  } else {
+    CUDA_OK(cudaLaunchKernel(e->kernel, dim3(grid), dim3(e->threads), args, e->smem, s));
+  }
   e->launches++;
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(e->ev1, s));

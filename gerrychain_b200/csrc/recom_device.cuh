@@ -41,7 +41,8 @@ struct HelpRec {
   int32_t base;      // first unit of the status window
   int32_t next;      // next unit to hand out (atomic)
   int32_t won;       // lowest unit with a balanced cut so far (atomicMin)
-  int32_t pad[6];
+  int32_t want;      // CTAs that should leave their own chains for this step (grows with the units that have failed)
+  int32_t pad[5];
 };
 constexpr int kHelpWin = 256;  // status words per chain: units [base, base + kHelpWin)
 
@@ -75,10 +76,16 @@ struct Params {
   int32_t mpref_shift;    // Wilson: Smem.msh
   HelpRec* help;                       // [n_chains]
   unsigned long long* help_status;     // [n_chains][kHelpWin]
+  uint32_t* help_bits;                 // [n_chains / 32 + 1] bit c: chain c has a live help record
+  int32_t* help_count;                 // live help records
   int32_t* idle;                       // CTAs of this launch that have no chain to step
   unsigned long long* steps_done;      // chain-steps completed in this launch
   int32_t share;                       // 0: no shared retries
   int32_t help_win;                    // units per status window (<= kHelpWin)
+  int32_t help_after;                  // failed trees after which a step leaves the common path (long_retry)
+  int32_t recruit_mult;                // CTAs recruited per units_per_recruit failed units
+  int32_t recruit_after;               // failed trees from which a step is shared although every CTA has a chain of its own
+  int32_t units_per_recruit;           // ... and takes one more CTA off its own chains per this many failed units
 };
 
 // ---- shared-memory carve-up -------------------------------------------------------
@@ -291,8 +298,10 @@ enum { M_WSUM = 0 /* 0..63: two alternating banks of 32 warp sums */,
        M_BEST64 = 80 /* 80..81, 8-byte aligned */, M_TICKET = 82 /* 82..83 */,
        M_ROOTKIDS = 86 /* Wilson: children of the tree root */, M_CTR = 88 /* 88..95 counters */,
        /* 96..127: phase timers of RC_TIMERS builds */
-       M_HC = 128 /* 128..134: the pair a helper gathered last (chain, session, a, b, n, m, tot) */,
-       M_TICKET64 = 136 /* 136..137: the ticket this CTA holds (8-byte aligned) */ };
+       M_HC = 128 /* 128..134: the pair a helper gathered last (chain, session, a, b, n, m, tot); 128..136: arguments of long_finish */,
+       M_TICKET64 = 140 /* 140..141: the ticket this CTA holds (8-byte aligned) */,
+       M_KEEP = 138 /* the chain this CTA goes on with (thread 0's), -1: none */,
+       M_HELPMODE = 139 /* thread 0's: this CTA, though chains are ready, draws trees for a long step */ };
 // wmeta[] rows (Wilson, per walker)
 enum { WM_ROOT = 0, WM_DRAWS = 32, WM_ERR = 64 };
 

@@ -506,18 +506,19 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
     // D: relabel the live edges to the new roots and drop the ones inside a component;
     // in place: a sweep's reads all precede its writes, and it writes below what it read
     for (int base = 0; base < nlive; base += T * kCompactK) {
-      uint32_t nab[kCompactK], nj[kCompactK];
+      uint32_t nab[kCompactK], nj[kCompactK / 2];  // staged in registers (edge indices two to a word)
       int cnt = 0;
+#pragma unroll
+      for (int k = 0; k < kCompactK / 2; ++k) nj[k] = 0;
 #pragma unroll
       for (int k = 0; k < kCompactK; ++k) {
         const int q = base + k * T + tid;
         nab[k] = 0xffffffffu;
-        nj[k] = 0;
         if (base + k * T >= nlive) break;  // block uniform
         if (q < nlive) {
           const uint32_t ab = s.lab[q];
           const int a = s.hook[ab & 0xffffu], b = s.hook[ab >> 16];
-          if (a != b) { nab[k] = (uint32_t)a | ((uint32_t)b << 16); nj[k] = s.lj[q]; ++cnt; }
+          if (a != b) { nab[k] = (uint32_t)a | ((uint32_t)b << 16); nj[k >> 1] |= (uint32_t)s.lj[q] << (16 * (k & 1)); ++cnt; }
         }
       }
       // warp-aggregated allocation of output slots (their order is immaterial)
@@ -530,7 +531,7 @@ __device__ int boruvka_mst(Chain& c, const Step& st, uint32_t tree_no, uint32_t 
 #pragma unroll
       for (int k = 0; k < kCompactK; ++k) {
         if (base + k * T >= nlive) break;
-        if (nab[k] != 0xffffffffu) { s.lab[o] = nab[k]; s.lj[o] = (lid_t)nj[k]; ++o; }
+        if (nab[k] != 0xffffffffu) { s.lab[o] = nab[k]; s.lj[o] = (lid_t)(nj[k >> 1] >> (16 * (k & 1))); ++o; }
       }
     }
     __syncthreads();
@@ -1190,6 +1191,13 @@ __device__ bool commit_proposal(Chain& c, const Step& st, int cut_count, long lo
 // below build their own instead of taking the caller's (a Chain whose address escapes would
 // pin its ~40 pointers in local memory for the whole step path, which otherwise rematerialises
 // them from the shared-memory base).
+// The launch's Params once more, in constant memory: out-of-line device functions (long_retry,
+// help_once) cannot reach the kernel's parameter bank, and through a generic pointer to it every
+// field is a load (plus the descriptor set-up) that has to be repeated after each barrier.
+// Written by rc_engine_run on the launch's stream before a shared-retry launch; launches that
+// use it are ordered by an event (recom_abi.cu).
+__constant__ Params g_params;
+
 template <bool kWilson, bool kSpill>
 __device__ __forceinline__ void chain_layout(Chain& c, const Params& p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1229,7 +1237,9 @@ __device__ __forceinline__ void chain_bind(Chain& c, const Params& p, int chain)
 // final it retires the record, draws the winning tree again if it is not the one in its
 // shared memory, and goes on to the cut as if it had found the tree itself.
 struct UnitResult { int status, first_ok, nbal; uint32_t value; };  // value: Boruvka rounds / walk draws
-constexpr int kHelpAfter = 8;  // failed trees before a step is shared
+constexpr int kHelpAfter = 32;  // failed trees before a step leaves the common path (and is shared when CTAs are idle)
+constexpr int kGoLong = -100;  // ProposalResult.status of propose: the proposal is to be finished by long_finish
+constexpr int kLagMargin = 2;  // steps behind the average progress of the launch from which a chain keeps its CTA
 
 // status word: epoch (24) | kind (2) | first_ok (6) | value (32)
 enum { HK_FAIL = 1, HK_OK = 2, HK_ERR = 3 };
@@ -1327,9 +1337,11 @@ __device__ SharedOut shared_retry(Chain& c, const Step& st, uint32_t t_first, in
     const int e = R->epoch + 1;  // odd from here on
     __threadfence();  // (the retirement of the last session is out before its fields change)
     R->session += 1; R->pair = st.a | (st.b << 16); R->prop_no = prop_no; R->t_first = t_first; R->unit = unit;
-    R->limit = limit; R->base = 0; R->next = 0; R->won = kInf;
+    R->limit = limit; R->base = 0; R->next = 0; R->won = kInf; R->want = 0;
     __threadfence();
     st_release(&R->epoch, e);
+    atomicOr(p.help_bits + (c.chain >> 5), 1u << (c.chain & 31));  // what the idle CTAs poll
+    atomicAdd(p.help_count, 1);
     bc[0] = e;
   }
   __syncthreads();
@@ -1350,6 +1362,7 @@ __device__ SharedOut shared_retry(Chain& c, const Step& st, uint32_t t_first, in
         if (!(u >= base && u < base + win && u < limit && u <= known_dec)) u = -1;
       }
       R->won = known_dec;
+      R->want = min(nx * p.recruit_mult / p.units_per_recruit, 4096);  // one more CTA off its own chains per kUnitsPerRecruit units that have failed
       bc[0] = u;
       bc[1] = min(min(*(volatile int32_t*)&R->next, base + win), limit) - base;  // units of the window handed out
       *lo_ok = kInf; *lo_pend = kInf; *lo_err = kInf;
@@ -1408,7 +1421,12 @@ __device__ SharedOut shared_retry(Chain& c, const Step& st, uint32_t t_first, in
     __syncthreads();
   }
   // retire the record: helpers drop what they are doing for it
-  if (tid == 0) { __threadfence(); st_release(&R->epoch, epoch + 1); }
+  if (tid == 0) {
+    atomicAdd(p.help_count, -1);
+    atomicAnd(p.help_bits + (c.chain >> 5), ~(1u << (c.chain & 31)));
+    __threadfence();
+    st_release(&R->epoch, epoch + 1);
+  }
   __syncthreads();
   out.value = acc_value;
   out.trees = min((long long)out.units * unit, trees_cap);
@@ -1439,20 +1457,21 @@ __device__ SharedOut shared_retry(Chain& c, const Step& st, uint32_t t_first, in
 // Everything a step does beyond its first kHelpAfter trees, out of line (the step path of the
 // common case keeps its registers): unit after unit here while every CTA has a chain of its
 // own, handed to shared_retry as soon as one has not.
-template <bool kWilson, bool kSpill>
-__device__ __noinline__ SharedOut long_retry(const Params* pp, int chain, int* par, const Step st, uint32_t t_first, int unit,
-                                             long long limit, long long trees_cap, uint32_t prop_no, double ideal, double thr) {
-  const Params& p = *pp;
-  Chain c;
-  chain_layout<kWilson, kSpill>(c, p);
-  chain_bind(c, p, chain);
-  c.par = *par;
-  struct ParOut { int* out; Chain* c; __device__ ~ParOut() { *out = c->par; } } par_out{par, &c};  // hand the scan parity back
+// (The descriptor's address must not escape - body and wrapper are separate so that the body's
+// `Chain&` dissolves into registers after inlining; with the descriptor in local memory every
+// array pointer is re-loaded from the stack and every shared-memory access turns generic.)
+template <bool kWilson>
+__device__ __forceinline__ SharedOut long_retry_body(const Params& p, Chain& c, const Step st, uint32_t t_first, int unit,
+                                                     long long limit, long long trees_cap, uint32_t prop_no, double ideal, double thr) {
   const Smem& s = c.s;
   const int tid = threadIdx.x;
   SharedOut out = {-1, 0u, 0, 0, 0, 0, 0};
   for (long long u = 0; u < limit; ++u) {
-    if (tid == 0) s.misc[M_SPARE0] = *(volatile int32_t*)p.idle > 0;
+    // shared from here on when CTAs are idle (the tail of a launch), or when the step is deep in the
+    // heavy tail of the retry distribution (config 3: 4 steps in 10 000 need more than 64 trees, a
+    // few per launch more than 1000 = tens of milliseconds): the chain would hold up the launch,
+    // so CTAs leave their own chains for it, the more the longer it lasts (HelpRec.want)
+    if (tid == 0) s.misc[M_SPARE0] = *(volatile int32_t*)p.idle > 0 || (u + 1) * unit + p.help_after > p.recruit_after;
     __syncthreads();
     const bool idle = s.misc[M_SPARE0] != 0;
     __syncthreads();
@@ -1479,234 +1498,87 @@ __device__ __noinline__ SharedOut long_retry(const Params* pp, int chain, int* p
   return out;  // status -1: no tree below max_attempts has a balanced cut
 }
 
-// One recom proposal + validity + commit (tree_proposals.py:36-146, chain.py:186-195).
-template <bool kWilson, bool kShare, bool kSpill>
-__device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep* rs,
-                                  int32_t* ctr /* smem counters */) {
+
+// Root, cut choice, sides, validity and commit for the tree in shared memory: tree number tree_no
+// of proposal prop_no, with nbal balanced cuts (tree.py:377-424, 446-578, 888-966; chain.py:186-195).
+template <bool kWilson>
+__device__ __forceinline__ ProposalResult finish_proposal(Chain& c, const Step& st, const RcReplayStep* rs, const int n_rec,
+                                                          const uint32_t tree_no, const int nbal, const int wsel, const long long attempts,
+                                                          const uint32_t prop_no, const int cut_count, int32_t* ctr, ProposalResult res) {
   const Params& p = *c.p;
   const Smem& s = c.s;
   const int tid = threadIdx.x, T = blockDim.x;
-  ProposalResult res = {RC_OK, 0, 0, 0};
-  const int cut_count = __ldcg(p.st.d_cut_count + c.chain);
-  if (cut_count <= 0) { res.status = RC_ERR_NO_CUT_EDGES; return res; }
-  Step st;
-  const int k = p.cfg.n_districts;
-  const bool resel = p.cfg.allow_pair_reselection != 0 && !rs;
-  uint32_t* bad = p.badpairs ? p.badpairs + (size_t)blockIdx.x * 2048 : nullptr;
-  int n_bad = 0;
-  if (resel) {
-    for (int i = tid; i < 2048; i += T) bad[i] = 0;
-    __syncthreads();
-  }
+  const int n = st.n, nt = n - 1;
   const double ideal = p.cfg.pop_target;
   const double thr = __dmul_rn(ideal, p.cfg.epsilon);
-  const long long max_attempts = p.cfg.max_attempts > 0 ? p.cfg.max_attempts : 0x7fffffffffffffffLL;
-  const long long nr = p.cfg.node_repeats;
   const bool warn_on = !p.cfg.allow_pair_reselection && p.cfg.warn_attempts > 0;
-  const int n_rec = rs ? rs->n_trees : 0;
-  const uint32_t t0 = (rs && nr == 0 && n_rec > 0) ? (uint32_t)(n_rec - 1) : 0u;
-  const int r0 = 0;  // tour root: local node 0 (any node will do)
-  int tstar = -1, root = -1;
-  int wsel = 0, cut_child = -1;  // Wilson: winning walker, child endpoint of the chosen cut
-  for (uint32_t retry = 0;; ++retry) {  // tree_proposals.py:103-138
-  if (resel && (n_bad >= k * (k - 1) / 2 || retry >= 64u * (uint32_t)(k * k))) { res.status = RC_ERR_ALL_PAIRS_BAD; return res; }
-  // ---- P0
-  int e;
-  if (rs) {
-    e = rs->pair_edge;
-    if (e < 0 || e >= p.g.E || !((__ldcg(c.mask + (e >> 5)) >> (e & 31)) & 1)) { res.status = RC_ERR_REPLAY; return res; }
-  } else {
-    RC_PH(PH_OTHER);
-    e = pick_cut_edge(c, cut_count, prop_no, retry);
-    RC_PH(PH_PICK);
-    if (e < 0) { res.status = RC_ERR_NO_CUT_EDGES; return res; }
-  }
+  int tstar = -1, root = -1, cut_child = -1;
   {
-    const int la = __ldcg(c.assign + p.g.edge_uv[2 * e]), lb = __ldcg(c.assign + p.g.edge_uv[2 * e + 1]);
-    st.a = min(la, lb); st.b = max(la, lb);  // tree_proposals.py:113
-  }
-  if (resel && ((bad[(st.a * 256 + st.b) >> 5] >> ((st.a * 256 + st.b) & 31)) & 1)) continue;
-  // ---- P1
-  int d_sub = 0;
-  res.status = gather_pair<kWilson>(c, st, &d_sub);
-  RC_PH(PH_GATHER);
-  if (tid == 0) { ctr[RC_CTR_NODES] += st.n; ctr[RC_CTR_SLOTS] += d_sub; }
-  if (res.status) return res;
-  const int n = st.n, nt = n - 1;
-  bool reselect = false;
-
-  uint32_t batch_lo = t0, batch_hi = t0;  // Wilson: trees [batch_lo, batch_hi) have been walked
-  for (uint32_t tree_no = t0;; ++tree_no) {
-    // tree.py:679-700 attempt accounting (see oracle/recom_oracle.c rco_bipartition)
-    long long attempts = nr > 0 ? (long long)tree_no * nr : (tree_no == t0 ? 0 : max_attempts);
-    if (attempts >= max_attempts) {
-      if (tid == 0) {
-        ctr[RC_CTR_ATTEMPTS] += (int)min(max_attempts, 0x7fffffffLL);
-        if (warn_on && max_attempts >= p.cfg.warn_attempts) atomicOr(p.st.d_flags + c.chain, RC_FLAG_WARNED);
-      }
-      if (resel) { reselect = true; break; }  // ReselectException, tree.py:712-716
-      res.status = RC_ERR_MAX_ATTEMPTS;
-      return res;
-    }
-    if (rs && (int)tree_no >= n_rec) { res.status = RC_ERR_REPLAY; return res; }
-    int nbal;
-    // CTAs without a chain to step?  Then the rest of this search is shared with them
-    // (shared_retry above); checked once per tree / batch, at a point where nothing is in flight
-    bool go_shared = false;
-    if constexpr (kShare) {
-      // a step that has already failed kHelpAfter trees leaves the common path for good (long_retry):
-      // the common step (a handful of trees) is not worth a helper's gather
-      go_shared = !rs && !resel && tree_no >= t0 + (uint32_t)kHelpAfter && (!kWilson || tree_no >= batch_hi);
-    }
-    if (kShare && go_shared) {
-      const int unit = kWilson ? (p.walkers > 0 ? p.walkers : 1) : 1;
-      const long long trees_cap = (max_attempts - attempts + nr - 1) / nr;  // trees from tree_no on that may still be examined
-      int par = c.par;
-      const SharedOut so = long_retry<kWilson, kSpill>(c.p, c.chain, &par, st, tree_no, unit, (trees_cap + unit - 1) / unit, trees_cap,
-                                                       prop_no, ideal, thr);
-      c.par = par;
-      if (tid == 0) {
-        ctr[RC_CTR_TREES] += (int)so.trees;
-        ctr[kWilson ? RC_CTR_WALK : RC_CTR_ROUNDS] += (int)so.value;
-        if (kWilson) ctr[RC_CTR_ROUNDS] += (int)so.units;
-      }
-      res.trees = (int)(tree_no + (uint32_t)so.trees);
-      if (so.status > 0) { res.status = so.status; return res; }
-      if (so.status < 0) {  // no tree below max_attempts has a balanced cut: the check at the top of the loop reports it
-        tree_no += (uint32_t)trees_cap - 1u;
-        continue;
-      }
-      tree_no = so.tree_no;
-      res.trees = (int)tree_no + 1;
-      attempts = (long long)tree_no * nr;
-      nbal = so.nbal;
-      wsel = so.wsel;
-      batch_lo = tree_no - (uint32_t)so.wsel;
-      batch_hi = batch_lo + (uint32_t)unit;
-    } else if constexpr (kWilson) {
-      // ---- P2b: the next batch of trees, one per lane of warp 0; examined in order
-      if (tree_no >= batch_hi) {
-        long long nw = p.walkers > 0 ? p.walkers : 1;
-        if (rs) nw = 1;  // a recorded tree is walked by one thread (wilson_walk_recorded)
-        if (nr > 0) nw = min(nw, (max_attempts - attempts + nr - 1) / nr);  // trees beyond max_attempts are never examined
-        else nw = 1;
-        wilson_walk(c, st, tree_no, (int)nw, prop_no, rs ? rs->first_tree + tree_no : 0);
-        batch_lo = tree_no;
-        batch_hi = tree_no + (uint32_t)nw;
-        if (tid == 0) ctr[RC_CTR_ROUNDS] += 1;  // Wilson: batches of concurrent walks
-        RC_PH(PH_TREE);
-      }
-      wsel = (int)(tree_no - batch_lo);
-      res.status = s.wmeta[WM_ERR + wsel];
-      if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_WALK] += s.wmeta[WM_DRAWS + wsel]; }
-      res.trees = (int)tree_no + 1;
-      if (res.status) return res;
-      if (n < 3) { res.status = RC_ERR_NO_ROOT; return res; }  // tree.py:377: no node of degree > 1
-      nbal = wilson_eval(c, st, wsel, ideal, thr);
-      RC_PH(PH_EULER);
+    const bool last_rec = rs && (int)tree_no == n_rec - 1;
+    if (rs && !last_rec) { res.status = RC_ERR_REPLAY; return res; }
+    const uint16_t* __restrict__ S = kWilson ? s.wst + (size_t)wsel * p.cap_nodes : nullptr;
+    const int wroot = kWilson ? s.wmeta[WM_ROOT + wsel] : 0;
+    const int rootkids = kWilson ? s.misc[M_ROOTKIDS] : 0;
+    auto internal = [&](int i) {  // tree degree > 1
+      if constexpr (kWilson) return i == wroot ? rootkids >= 2 : (bool)((s.whas[i >> 5] >> (i & 31)) & 1u);
+      else return s.nxt[s.head[i]] != kNone;
+    };
+    // ---- root (tree.py:377): uniform over tree nodes of degree > 1, ascending node index
+    if (last_rec) {
+      const int gr = rs->root;
+      root = (gr >= 0 && gr < p.g.N && is_member(s, gr)) ? local_id(s, gr) : -1;
+      if (root < 0 || !internal(root)) { res.status = RC_ERR_REPLAY; return res; }
     } else {
-      const uint32_t* rrank = rs ? p.rp.weight_rank + (rs->first_tree + tree_no) * (long long)p.g.E : nullptr;
-      // ---- P2a
-      int rounds = 0;
-      res.status = boruvka_mst(c, st, tree_no, prop_no, rrank, &rounds);
-      RC_PH(PH_TREE);
-      if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_ROUNDS] += rounds; }
-      res.trees = (int)tree_no + 1;
-      if (res.status) return res;
-      // tree.py:377: the root is drawn among tree nodes of degree > 1 (none: IndexError);
-      // only the two-node tree has none
-      if (n < 3) { res.status = RC_ERR_NO_ROOT; return res; }
-      // ---- P3
-      euler_subtree_pops(c, st, r0);
-      RC_PH(PH_EULER);
-      // ---- P4: balanced tree edges (cur[t] = population below edge t)
-      if (tid == 0) s.misc[M_NBAL] = 0;
+      if (tid == 0) s.misc[M_NINT] = 0;
       __syncthreads();
       int cnt = 0;
-      for (int t = tid; t < nt; t += T) cnt += balanced(s.cur[t], st.tot, ideal, thr) ? 1 : 0;
+      for (int i = tid; i < n; i += T) cnt += internal(i) ? 1 : 0;
       cnt = warp_sum(cnt);
-      if ((tid & 31) == 0 && cnt) atomicAdd(&s.misc[M_NBAL], cnt);
+      if ((tid & 31) == 0 && cnt) atomicAdd(&s.misc[M_NINT], cnt);
       __syncthreads();
-      nbal = s.misc[M_NBAL];
+      const int n_int = s.misc[M_NINT];
+      RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_ROOT, 0, tree_no, prop_no, 0);
+      root = select_kth(c, n, (int)rc_below(r.v[0], r.v[1], (uint32_t)n_int), internal);
     }
-    RC_PH(PH_BALANCE);
-    res.nbal = nbal;
-    if (nbal > 0) {
-      const bool last_rec = rs && (int)tree_no == n_rec - 1;
-      if (rs && !last_rec) { res.status = RC_ERR_REPLAY; return res; }
-      const uint16_t* __restrict__ S = kWilson ? s.wst + (size_t)wsel * p.cap_nodes : nullptr;
-      const int wroot = kWilson ? s.wmeta[WM_ROOT + wsel] : 0;
-      const int rootkids = kWilson ? s.misc[M_ROOTKIDS] : 0;
-      auto internal = [&](int i) {  // tree degree > 1
-        if constexpr (kWilson) return i == wroot ? rootkids >= 2 : (bool)((s.whas[i >> 5] >> (i & 31)) & 1u);
-        else return s.nxt[s.head[i]] != kNone;
+    // ---- P5
+    if constexpr (kWilson) {
+      // no random_weight and no node attributes on the Wilson tree: every branch of the
+      // reference's cut choice degenerates to a uniform pick (tree.py:540-545), taken in
+      // ascending edge id like the oracle's canonical order
+      auto bal_edge = [&](int j) {
+        const int ch = wilson_tree_child(s, S, j);
+        return ch >= 0 && balanced(s.wsum[ch], st.tot, ideal, thr);
       };
-      // ---- root (tree.py:377): uniform over tree nodes of degree > 1, ascending node index
-      if (last_rec) {
-        const int gr = rs->root;
-        root = (gr >= 0 && gr < p.g.N && is_member(s, gr)) ? local_id(s, gr) : -1;
-        if (root < 0 || !internal(root)) { res.status = RC_ERR_REPLAY; return res; }
+      int jstar;
+      if (rs && rs->cut_edge >= 0) {
+        const int want = rs->cut_edge;
+        jstar = select_kth(c, st.m, 0, [&](int j) { return c.eids[j] == want && bal_edge(j); });
       } else {
-        if (tid == 0) s.misc[M_NINT] = 0;
-        __syncthreads();
-        int cnt = 0;
-        for (int i = tid; i < n; i += T) cnt += internal(i) ? 1 : 0;
-        cnt = warp_sum(cnt);
-        if ((tid & 31) == 0 && cnt) atomicAdd(&s.misc[M_NINT], cnt);
-        __syncthreads();
-        const int n_int = s.misc[M_NINT];
-        RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_ROOT, 0, tree_no, prop_no, 0);
-        root = select_kth(c, n, (int)rc_below(r.v[0], r.v[1], (uint32_t)n_int), internal);
+        RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_CUT, 0, tree_no, prop_no, 0);
+        jstar = select_kth(c, st.m, (int)rc_below(r.v[0], r.v[1], (uint32_t)nbal), bal_edge);
       }
-      // ---- P5
-      if constexpr (kWilson) {
-        // no random_weight and no node attributes on the Wilson tree: every branch of the
-        // reference's cut choice degenerates to a uniform pick (tree.py:540-545), taken in
-        // ascending edge id like the oracle's canonical order
-        auto bal_edge = [&](int j) {
-          const int ch = wilson_tree_child(s, S, j);
-          return ch >= 0 && balanced(s.wsum[ch], st.tot, ideal, thr);
-        };
-        int jstar;
-        if (rs && rs->cut_edge >= 0) {
-          const int want = rs->cut_edge;
-          jstar = select_kth(c, st.m, 0, [&](int j) { return c.eids[j] == want && bal_edge(j); });
-        } else {
-          RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_CUT, 0, tree_no, prop_no, 0);
-          jstar = select_kth(c, st.m, (int)rc_below(r.v[0], r.v[1], (uint32_t)nbal), bal_edge);
-        }
-        if (jstar < 0) { res.status = RC_ERR_REPLAY; return res; }
-        cut_child = wilson_tree_child(s, S, jstar);
+      if (jstar < 0) { res.status = RC_ERR_REPLAY; return res; }
+      cut_child = wilson_tree_child(s, S, jstar);
+    } else {
+      const uint32_t* rrank = rs ? p.rp.weight_rank + (rs->first_tree + tree_no) * (long long)p.g.E : nullptr;
+      auto is_bal = [&](int t) { return balanced(s.cur[t], st.tot, ideal, thr); };
+      const int policy = p.cfg.cut_policy;
+      if (rs && rs->cut_edge >= 0) {
+        const int want = rs->cut_edge;
+        tstar = select_kth(c, nt, 0, [&](int t) { return c.eids[s.te[t]] == want && is_bal(t); });
+        if (tstar < 0) { res.status = RC_ERR_REPLAY; return res; }
+      } else if (policy == RC_CUT_UNIFORM) {
+        RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_CUT, 0, tree_no, prop_no, 0);
+        tstar = select_kth(c, nt, (int)rc_below(r.v[0], r.v[1], (uint32_t)nbal), is_bal);
       } else {
-        const uint32_t* rrank = rs ? p.rp.weight_rank + (rs->first_tree + tree_no) * (long long)p.g.E : nullptr;
-        auto is_bal = [&](int t) { return balanced(s.cur[t], st.tot, ideal, thr); };
-        const int policy = p.cfg.cut_policy;
-        if (rs && rs->cut_edge >= 0) {
-          const int want = rs->cut_edge;
-          tstar = select_kth(c, nt, 0, [&](int t) { return c.eids[s.te[t]] == want && is_bal(t); });
-          if (tstar < 0) { res.status = RC_ERR_REPLAY; return res; }
-        } else if (policy == RC_CUT_UNIFORM) {
-          RcPhilox r = rc_draw(p.cfg.seed, c.gchain, RC_DRAW_CUT, 0, tree_no, prop_no, 0);
-          tstar = select_kth(c, nt, (int)rc_below(r.v[0], r.v[1], (uint32_t)nbal), is_bal);
-        } else {
-          tstar = choose_cut_by_weight(c, st, policy, tree_no, prop_no, rrank, ideal, thr);
-        }
+        tstar = choose_cut_by_weight(c, st, policy, tree_no, prop_no, rrank, ideal, thr);
       }
-      if (tid == 0) {
-        ctr[RC_CTR_ATTEMPTS] += (int)min(attempts + 1, 0x7fffffffLL);
-        if (warn_on && attempts >= p.cfg.warn_attempts) atomicOr(p.st.d_flags + c.chain, RC_FLAG_WARNED);
-      }
-      break;
+    }
+    if (tid == 0) {
+      ctr[RC_CTR_ATTEMPTS] += (int)min(attempts + 1, 0x7fffffffLL);
+      if (warn_on && attempts >= p.cfg.warn_attempts) atomicOr(p.st.d_flags + c.chain, RC_FLAG_WARNED);
     }
   }
-  if (reselect) {  // tree_proposals.py:133-136
-    if (tid == 0) { bad[(st.a * 256 + st.b) >> 5] |= 1u << ((st.a * 256 + st.b) & 31); ctr[RC_CTR_RESELECT] += 1; }
-    ++n_bad;
-    __syncthreads();
-    continue;
-  }
-  break;
-  }  // pair loop
   RC_PH(PH_CHOOSE);
   // ---- P6: the side holding the reference's root keeps the lower id (tree.py:421, :947-950)
   bool root_below;
@@ -1755,6 +1627,226 @@ __device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep
   RC_PH(PH_COMMIT);
   res.accepted = 1;
   return res;
+}
+
+// The long path of a proposal: the search from tree_no on (long_retry_body: alone, or shared with
+// other CTAs) and, when it has found a tree, the rest of the proposal.  Free-running only.
+template <bool kWilson, bool kSpill>
+__device__ __noinline__ ProposalResult long_finish(int* par) {
+  const Params& p = g_params;
+  Chain c;
+  chain_layout<kWilson, kSpill>(c, p);
+  // the arguments come through shared memory (misc[M_HC..], free while this CTA steps a chain of its
+  // own): a call with a handful of register arguments costs the caller's loops registers
+  const int32_t* arg = c.s.misc + M_HC;
+  Step st;
+  const int chain = arg[0];
+  st.a = arg[1]; st.b = arg[2]; st.n = arg[3]; st.m = arg[4]; st.tot = arg[5];
+  uint32_t tree_no = (uint32_t)arg[6];
+  const uint32_t prop_no = (uint32_t)arg[7];
+  const int cut_count = arg[8];
+  __syncthreads();  // (read before thread 0 marks the helper cache empty again)
+  if (threadIdx.x == 0) c.s.misc[M_HC] = -1;
+  chain_bind(c, p, chain);
+  c.par = *par;
+  const int tid = threadIdx.x;
+  int32_t* ctr = c.s.misc + M_CTR;
+  ProposalResult res = {RC_OK, 0, 0, 0};
+  const double ideal = p.cfg.pop_target;
+  const double thr = __dmul_rn(ideal, p.cfg.epsilon);
+  const long long max_attempts = p.cfg.max_attempts > 0 ? p.cfg.max_attempts : 0x7fffffffffffffffLL;
+  const long long nr = p.cfg.node_repeats;  // >= 1 (Params.share is 0 otherwise)
+  const bool warn_on = !p.cfg.allow_pair_reselection && p.cfg.warn_attempts > 0;
+  const int unit = kWilson ? (p.walkers > 0 ? p.walkers : 1) : 1;
+  const long long trees_cap = (max_attempts - (long long)tree_no * nr + nr - 1) / nr;  // trees from tree_no on that may still be examined
+  const SharedOut so = long_retry_body<kWilson>(p, c, st, tree_no, unit, (trees_cap + unit - 1) / unit, trees_cap, prop_no, ideal, thr);
+  if (tid == 0) {
+    ctr[RC_CTR_TREES] += (int)so.trees;
+    ctr[kWilson ? RC_CTR_WALK : RC_CTR_ROUNDS] += (int)so.value;
+    if (kWilson) ctr[RC_CTR_ROUNDS] += (int)so.units;
+  }
+  res.trees = (int)(tree_no + (uint32_t)so.trees);
+  if (so.status > 0) {
+    res.status = so.status;
+  } else if (so.status < 0) {  // no tree below max_attempts has a balanced cut (tree.py:718; the long path excludes pair reselection)
+    if (tid == 0) {
+      ctr[RC_CTR_ATTEMPTS] += (int)min(max_attempts, 0x7fffffffLL);
+      if (warn_on && max_attempts >= p.cfg.warn_attempts) atomicOr(p.st.d_flags + c.chain, RC_FLAG_WARNED);
+    }
+    res.status = RC_ERR_MAX_ATTEMPTS;
+  } else {
+    tree_no = so.tree_no;
+    res.trees = (int)tree_no + 1;
+    res.nbal = so.nbal;
+    res = finish_proposal<kWilson>(c, st, nullptr, 0, tree_no, so.nbal, so.wsel, (long long)tree_no * nr, prop_no, cut_count, ctr, res);
+  }
+  *par = c.par;  // hand the scan parity back
+  return res;
+}
+
+// One recom proposal + validity + commit (tree_proposals.py:36-146, chain.py:186-195).
+template <bool kWilson, bool kShare, bool kSpill>
+__device__ ProposalResult propose(Chain& c, uint32_t prop_no, const RcReplayStep* rs,
+                                  int32_t* ctr /* smem counters */) {
+  const Params& p = *c.p;
+  const Smem& s = c.s;
+  const int tid = threadIdx.x, T = blockDim.x;
+  ProposalResult res = {RC_OK, 0, 0, 0};
+  const int cut_count = __ldcg(p.st.d_cut_count + c.chain);
+  if (cut_count <= 0) { res.status = RC_ERR_NO_CUT_EDGES; return res; }
+  Step st;
+  const int k = p.cfg.n_districts;
+  const bool resel = p.cfg.allow_pair_reselection != 0 && !rs;
+  uint32_t* bad = p.badpairs ? p.badpairs + (size_t)blockIdx.x * 2048 : nullptr;
+  int n_bad = 0;
+  if (resel) {
+    for (int i = tid; i < 2048; i += T) bad[i] = 0;
+    __syncthreads();
+  }
+  const double ideal = p.cfg.pop_target;
+  const double thr = __dmul_rn(ideal, p.cfg.epsilon);
+  const long long max_attempts = p.cfg.max_attempts > 0 ? p.cfg.max_attempts : 0x7fffffffffffffffLL;
+  const long long nr = p.cfg.node_repeats;
+  const bool warn_on = !p.cfg.allow_pair_reselection && p.cfg.warn_attempts > 0;
+  const int n_rec = rs ? rs->n_trees : 0;
+  const uint32_t t0 = (rs && nr == 0 && n_rec > 0) ? (uint32_t)(n_rec - 1) : 0u;
+  const int r0 = 0;  // tour root: local node 0 (any node will do)
+  int tstar = -1, root = -1;
+  int wsel = 0, cut_child = -1;  // Wilson: winning walker, child endpoint of the chosen cut
+  uint32_t tree_no = t0;
+  long long attempts = 0;
+  int nbal = 0;
+  for (uint32_t retry = 0;; ++retry) {  // tree_proposals.py:103-138
+  if (resel && (n_bad >= k * (k - 1) / 2 || retry >= 64u * (uint32_t)(k * k))) { res.status = RC_ERR_ALL_PAIRS_BAD; return res; }
+  // ---- P0
+  int e;
+  if (rs) {
+    e = rs->pair_edge;
+    if (e < 0 || e >= p.g.E || !((__ldcg(c.mask + (e >> 5)) >> (e & 31)) & 1)) { res.status = RC_ERR_REPLAY; return res; }
+  } else {
+    RC_PH(PH_OTHER);
+    e = pick_cut_edge(c, cut_count, prop_no, retry);
+    RC_PH(PH_PICK);
+    if (e < 0) { res.status = RC_ERR_NO_CUT_EDGES; return res; }
+  }
+  {
+    const int la = __ldcg(c.assign + p.g.edge_uv[2 * e]), lb = __ldcg(c.assign + p.g.edge_uv[2 * e + 1]);
+    st.a = min(la, lb); st.b = max(la, lb);  // tree_proposals.py:113
+  }
+  if (resel && ((bad[(st.a * 256 + st.b) >> 5] >> ((st.a * 256 + st.b) & 31)) & 1)) continue;
+  // ---- P1
+  int d_sub = 0;
+  res.status = gather_pair<kWilson>(c, st, &d_sub);
+  RC_PH(PH_GATHER);
+  if (tid == 0) { ctr[RC_CTR_NODES] += st.n; ctr[RC_CTR_SLOTS] += d_sub; }
+  if (res.status) return res;
+  const int n = st.n, nt = n - 1;
+  bool reselect = false;
+
+  uint32_t batch_lo = t0, batch_hi = t0;  // Wilson: trees [batch_lo, batch_hi) have been walked
+  bool go_long = false;  // shared-retry build: the search leaves the common path (below the loop)
+  tree_no = t0;
+  attempts = 0;
+  nbal = 0;
+  for (;; ++tree_no) {
+    // tree.py:679-700 attempt accounting (see oracle/recom_oracle.c rco_bipartition)
+    attempts = nr > 0 ? (long long)tree_no * nr : (tree_no == t0 ? 0 : max_attempts);
+    if (attempts >= max_attempts) {
+      if (tid == 0) {
+        ctr[RC_CTR_ATTEMPTS] += (int)min(max_attempts, 0x7fffffffLL);
+        if (warn_on && max_attempts >= p.cfg.warn_attempts) atomicOr(p.st.d_flags + c.chain, RC_FLAG_WARNED);
+      }
+      if (resel) { reselect = true; break; }  // ReselectException, tree.py:712-716
+      res.status = RC_ERR_MAX_ATTEMPTS;
+      return res;
+    }
+    if (rs && (int)tree_no >= n_rec) { res.status = RC_ERR_REPLAY; return res; }
+    // CTAs without a chain to step?  Then the rest of this search is shared with them
+    // (shared_retry above); checked once per tree / batch, at a point where nothing is in flight
+    bool go_shared = false;
+    if constexpr (kShare) {
+      // a step that has already failed kHelpAfter trees leaves the common path for good (long_retry):
+      // the common step (a handful of trees) is not worth a helper's gather
+      go_shared = !rs && !resel && tree_no >= t0 + (uint32_t)p.help_after && (!kWilson || tree_no >= batch_hi);
+    }
+    if (kShare && go_shared) { go_long = true; break; }
+    if constexpr (kWilson) {
+      // ---- P2b: the next batch of trees, one per lane of warp 0; examined in order
+      if (tree_no >= batch_hi) {
+        long long nw = p.walkers > 0 ? p.walkers : 1;
+        if (rs) nw = 1;  // a recorded tree is walked by one thread (wilson_walk_recorded)
+        if (nr > 0) nw = min(nw, (max_attempts - attempts + nr - 1) / nr);  // trees beyond max_attempts are never examined
+        else nw = 1;
+        wilson_walk(c, st, tree_no, (int)nw, prop_no, rs ? rs->first_tree + tree_no : 0);
+        batch_lo = tree_no;
+        batch_hi = tree_no + (uint32_t)nw;
+        if (tid == 0) ctr[RC_CTR_ROUNDS] += 1;  // Wilson: batches of concurrent walks
+        RC_PH(PH_TREE);
+      }
+      wsel = (int)(tree_no - batch_lo);
+      res.status = s.wmeta[WM_ERR + wsel];
+      if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_WALK] += s.wmeta[WM_DRAWS + wsel]; }
+      res.trees = (int)tree_no + 1;
+      if (res.status) return res;
+      if (n < 3) { res.status = RC_ERR_NO_ROOT; return res; }  // tree.py:377: no node of degree > 1
+      nbal = wilson_eval(c, st, wsel, ideal, thr);
+      RC_PH(PH_EULER);
+    } else {
+      const uint32_t* rrank = rs ? p.rp.weight_rank + (rs->first_tree + tree_no) * (long long)p.g.E : nullptr;
+      // ---- P2a
+      int rounds = 0;
+      res.status = boruvka_mst(c, st, tree_no, prop_no, rrank, &rounds);
+      RC_PH(PH_TREE);
+      if (tid == 0) { ctr[RC_CTR_TREES] += 1; ctr[RC_CTR_ROUNDS] += rounds; }
+      res.trees = (int)tree_no + 1;
+      if (res.status) return res;
+      // tree.py:377: the root is drawn among tree nodes of degree > 1 (none: IndexError);
+      // only the two-node tree has none
+      if (n < 3) { res.status = RC_ERR_NO_ROOT; return res; }
+      // ---- P3
+      euler_subtree_pops(c, st, r0);
+      RC_PH(PH_EULER);
+      // ---- P4: balanced tree edges (cur[t] = population below edge t)
+      if (tid == 0) s.misc[M_NBAL] = 0;
+      __syncthreads();
+      int cnt = 0;
+      for (int t = tid; t < nt; t += T) cnt += balanced(s.cur[t], st.tot, ideal, thr) ? 1 : 0;
+      cnt = warp_sum(cnt);
+      if ((tid & 31) == 0 && cnt) atomicAdd(&s.misc[M_NBAL], cnt);
+      __syncthreads();
+      nbal = s.misc[M_NBAL];
+    }
+    RC_PH(PH_BALANCE);
+    res.nbal = nbal;
+    if (nbal > 0) break;
+  }
+  if constexpr (kShare) {
+    // Everything beyond the first help_after trees - the rest of the search AND what follows it, down
+    // to the commit - happens out of line, in tail position: nothing of this function is live
+    // across the call.  (With the search alone out of line and the step finished here, the values
+    // kept for afterwards cost the Boruvka compaction of the common case its staging registers:
+    // spills, -8 % at config 2 with nothing shared at all.)
+    if (go_long) {
+      __syncthreads();
+      if (tid == 0) {
+        int32_t* arg = s.misc + M_HC;
+        arg[0] = c.chain; arg[1] = st.a; arg[2] = st.b; arg[3] = st.n; arg[4] = st.m; arg[5] = st.tot;
+        arg[6] = (int)tree_no; arg[7] = (int)prop_no; arg[8] = cut_count;
+      }
+      __syncthreads();
+      res.status = kGoLong;  // step_body makes the call
+      return res;
+    }
+  }
+  if (reselect) {  // tree_proposals.py:133-136
+    if (tid == 0) { bad[(st.a * 256 + st.b) >> 5] |= 1u << ((st.a * 256 + st.b) & 31); ctr[RC_CTR_RESELECT] += 1; }
+    ++n_bad;
+    __syncthreads();
+    continue;
+  }
+  break;
+  }  // pair loop
+  return finish_proposal<kWilson>(c, st, rs, n_rec, tree_no, nbal, wsel, attempts, prop_no, cut_count, ctr, res);
 }
 
 // ---- reversible ReCom (proposals/tree_proposals.py:149-267) ------------------------------
@@ -1939,35 +2031,42 @@ struct HelpCache {
   }
 };
 
-template <bool kWilson, bool kSpill>
-__device__ __noinline__ void help_once(const Params* pp, int* par) {
-  const Params& p = *pp;
-  Chain c;
-  chain_layout<kWilson, kSpill>(c, p);
-  c.par = *par;
-  struct ParOut { int* out; Chain* c; __device__ ~ParOut() { *out = c->par; } } par_out{par, &c};  // hand the scan parity back
-  const Smem& s = c.s;
-  HelpCache hc;
-  hc.m = s.misc + M_HC;
+// a chain that wants help: the first bit of the help bitmap at or after a CTA-specific start
+// (spreads the helpers), or -1
+__device__ __forceinline__ int help_pick(const Params& p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* const misc = reinterpret_cast<int32_t*>(smem_raw);  // Smem.misc is the first array of every layout
   const int tid = threadIdx.x, T = blockDim.x;
   const int n_chains = p.cfg.n_chains;
   constexpr int kInf = 0x7fffffff;
-  int32_t* bc = s.misc + M_SPARE0;
-  // a chain that wants help: the first one at or after a CTA-specific start (spreads the helpers)
-  if (tid == 0) s.misc[M_PICK] = kInf;
+  if (tid == 0) misc[M_PICK] = kInf;
   __syncthreads();
-  const int start = (int)(blockIdx.x % (unsigned)n_chains);
-  for (int i = tid; i < n_chains; i += T) {
-    int ch = start + i;
-    if (ch >= n_chains) ch -= n_chains;
-    if (__ldcg(&p.help[ch].epoch) & 1) { atomicMin(&s.misc[M_PICK], i); break; }
+  const int nw = (n_chains + 31) >> 5;
+  const int start = (int)(blockIdx.x % (unsigned)n_chains), sw = start >> 5, sb = start & 31;
+  for (int i = tid; i <= nw; i += T) {  // the start word twice: its high bits first, its low bits last
+    int w = sw + i;
+    if (w >= nw) w -= nw;
+    uint32_t bits = __ldcg(p.help_bits + w);
+    if (i == 0) bits &= ~0u << sb;
+    if (i == nw) bits &= (1u << sb) - 1u;
+    if (bits) { atomicMin(&misc[M_PICK], (i << 5) | (__ffs((int)bits) - 1)); break; }  // (words after the start word) << 5 | bit
   }
   __syncthreads();
-  const int pick = s.misc[M_PICK];
+  const int pick = misc[M_PICK];
   __syncthreads();
-  if (pick == kInf) { __nanosleep(8000); return; }
-  int ch = start + pick;
-  if (ch >= n_chains) ch -= n_chains;
+  if (pick == kInf) return -1;
+  int wsel = sw + (pick >> 5);
+  if (wsel >= nw) wsel -= nw;
+  return (wsel << 5) | (pick & 31);
+}
+
+template <bool kWilson>
+__device__ __forceinline__ int help_body(const Params& p, Chain& c, const int ch, const bool busy) {
+  const Smem& s = c.s;
+  HelpCache hc;
+  hc.m = s.misc + M_HC;
+  const int tid = threadIdx.x;
+  int32_t* bc = s.misc + M_SPARE0;
   HelpRec* R = p.help + ch;
   // The record is read under ONE epoch value: every change of it (publish, window slide,
   // retirement) bumps the epoch, the owner fences between the bump and the next change of a
@@ -1983,15 +2082,18 @@ __device__ __noinline__ void help_once(const Params* pp, int* par) {
     s.misc[M_NLIVE] = __ldcg(&R->limit);
     s.misc[M_NBAL] = __ldcg(&R->base);
     bc[1] = __ldcg(&R->session);
+    // a CTA that has chains to step joins only when the step has failed often enough to want it
+    // (stateless admission: the first `want` CTAs counted from a record-specific offset)
+    const bool admitted = !busy || (int)((blockIdx.x + (unsigned)ch * 7919u) % gridDim.x) < __ldcg(&R->want);
     __threadfence();
-    bc[0] = (ld_acquire(&R->epoch) == e && (e & 1)) ? e : 0;
+    bc[0] = (ld_acquire(&R->epoch) == e && (e & 1) && admitted) ? e : 0;
   }
   __syncthreads();
   const int epoch = bc[0], session = bc[1], pair = s.misc[M_CNT], unit = s.misc[M_NINT];
   const int limit = s.misc[M_NLIVE], base = s.misc[M_NBAL];
   const uint32_t prop_no = (uint32_t)s.misc[M_SUBSET], t_first = (uint32_t)s.misc[M_DELTA];
   __syncthreads();
-  if (epoch == 0) return;
+  if (epoch == 0) return 0;
   chain_bind(c, p, ch);
   if (hc.chain() != ch || hc.session() != session) {
     // the chain's plan is stable while its record is live (the owner retires it before the commit)
@@ -2006,7 +2108,7 @@ __device__ __noinline__ void help_once(const Params* pp, int* par) {
     __syncthreads();
     const int still = bc[0];
     __syncthreads();
-    if (rc != RC_OK || still != epoch) return;  // retired (or slid) meanwhile: the plan may have moved under the gather
+    if (rc != RC_OK || still != epoch) return 0;  // retired (or slid) meanwhile: the plan may have moved under the gather
     if (tid == 0) hc.set(ch, session, st);
     __syncthreads();
   }
@@ -2024,7 +2126,10 @@ __device__ __noinline__ void help_once(const Params* pp, int* par) {
   __syncthreads();
   const int u = bc[0];
   __syncthreads();
-  if (u < 0) { __nanosleep(1000); return; }
+  if (u < 0) {
+    if (!busy) __nanosleep(1000);
+    return 0;
+  }
   const double ideal = p.cfg.pop_target;
   const double thr = __dmul_rn(ideal, p.cfg.epsilon);
   const UnitResult r = eval_unit<kWilson>(c, hst, t_first + (uint32_t)u * (uint32_t)unit, unit, prop_no, ideal, thr);
@@ -2034,6 +2139,82 @@ __device__ __noinline__ void help_once(const Params* pp, int* par) {
     if (kind != HK_FAIL) atomicMin(&R->won, u);
   }
   __syncthreads();
+  return 1;
+}
+
+// returns 1 when a unit was drawn; busy: the CTA has chains to step (see help_body)
+template <bool kWilson, bool kSpill>
+__device__ __noinline__ int help_once(int* par, const int busy) {
+  const Params& p = g_params;
+  const int ch = help_pick(p);
+  if (ch < 0) {
+    if (!busy) __nanosleep(2000);
+    return 0;
+  }
+  Chain c;
+  chain_layout<kWilson, kSpill>(c, p);
+  c.par = *par;
+  const int did = help_body<kWilson>(p, c, ch, busy != 0);
+  *par = c.par;  // hand the scan parity back
+  return did;
+}
+
+// One accepted step of `chain` (chain.py:185-195) and its bookkeeping; returns the chain's status.
+template <bool kWilson, bool kSpill, bool kShare>
+__device__ __forceinline__ int step_body(const Params& p, Chain& c, const int chain, const unsigned long long t,
+                                         const bool replay, const int streak_cap, int32_t* ctr) {
+  const int tid = threadIdx.x;
+  c.chain = chain;
+  c.gchain = (uint32_t)(chain + p.cfg.chain_offset);
+  c.assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
+  c.mask = p.st.d_cut_mask + (size_t)chain * p.st.mask_stride;
+  c.tally = p.st.d_tally + (size_t)chain * p.cfg.n_districts;
+  int status = __ldcg(p.st.d_status + chain);
+  if (status == RC_OK) {
+    // one accepted step (chain.py:185-195): propose until valid, accept always
+    uint32_t prop_no = __ldcg(p.st.d_proposal_no + chain);
+    RC_PH(PH_STATE);
+    const RcReplayStep* rs = replay ? p.rp.steps + t : nullptr;
+    ProposalResult r = {RC_OK, 0, 0, 0};
+    for (int streak = 0; streak < streak_cap; ++streak) {
+      if constexpr (kWilson) {
+        if (p.cfg.proposal_kind == RC_PROPOSAL_REVERSIBLE && !replay) r = propose_reversible(c, prop_no, ctr);
+        else r = propose<kWilson, kShare, kSpill>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
+      } else {
+        r = propose<kWilson, kShare, kSpill>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
+      }
+      if constexpr (kShare) {
+        if (r.status == kGoLong) {  // the proposal goes on out of line (its arguments are in shared memory)
+          int par = c.par;
+          r = long_finish<kWilson, kSpill>(&par);
+          c.par = par;
+        }
+      }
+      ++prop_no;
+      __syncthreads();
+      if (r.status || r.accepted || replay) break;
+    }
+    status = r.status ? r.status : (r.accepted ? RC_OK : RC_ERR_INVALID_STREAK);
+    if (tid == 0) {
+      p.st.d_proposal_no[chain] = prop_no;
+      if (status == RC_OK) p.st.d_step_no[chain] = __ldcg(p.st.d_step_no + chain) + 1;
+      else p.st.d_status[chain] = status;
+    }
+    if (tid < RC_N_COUNTERS) {
+      int64_t* g = p.st.d_counters + (size_t)chain * RC_N_COUNTERS + tid;
+      *g = __ldcg(g) + ctr[tid];
+      ctr[tid] = 0;
+    }
+    if (replay) {
+      if (p.rp.info_trace && tid == 0) {
+        int32_t* inf = p.rp.info_trace + 4 * t;
+        inf[0] = r.trees; inf[1] = r.nbal; inf[2] = p.st.d_cut_count[chain]; inf[3] = status;
+      }
+      if (p.rp.assign_trace)
+        for (int i = tid; i < p.g.N; i += blockDim.x) p.rp.assign_trace[(size_t)t * p.g.N + i] = c.assign[i];
+    }
+  }
+  return status;
 }
 
 // Free-running mode is a persistent grid over a ring of READY chains (see the loop below):
@@ -2082,7 +2263,7 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
   HelpCache hc;
   hc.m = c.s.misc + M_HC;
   unsigned long long* const ticket_p = reinterpret_cast<unsigned long long*>(c.s.misc + M_TICKET64);  // thread 0's
-  if (tid == 0) { hc.m[0] = -1; hc.m[1] = 0; *ticket_p = ~0ull; }  // ~0: no ticket
+  if (tid == 0) { hc.m[0] = -1; hc.m[1] = 0; *ticket_p = ~0ull; c.s.misc[M_KEEP] = -1; c.s.misc[M_HELPMODE] = 0; }  // ~0: no ticket
   __syncthreads();
   bool idle = false;
   for (;;) {
@@ -2093,38 +2274,66 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
       chain = p.rp.chain;
     } else {
       if (tid == 0) {
-        unsigned long long ticket = *ticket_p;
-        if (ticket == ~0ull) ticket = atomicAdd(p.work_counter, 1ull);
-        int ch = -1;  // -1: nothing to step right now, -2: the launch is over
-        if (ticket < total) {
-          if (ticket < (unsigned long long)n_chains) {
-            ch = (int)ticket;
-          } else {
-            int32_t* slot = p.ring + (ticket - (unsigned long long)n_chains) % cap;
-            int v = ld_acquire(slot);
-            if (!share) while (v == 0) { __nanosleep(32); v = ld_acquire(slot); }
-            if (v != 0) {
-              st_release(slot, 0);  // the slot may be refilled cap pushes later
-              ch = v - 1;
+        int ch = c.s.misc[M_KEEP];  // a chain behind the field goes on without queueing (below)
+        if (ch >= 0) {
+          c.s.misc[M_KEEP] = -1;
+        } else if (kShare && c.s.misc[M_HELPMODE]) {
+          ch = -4;  // a long step somewhere wants CTAs (below)
+        } else {
+          unsigned long long ticket = *ticket_p;
+          if (ticket == ~0ull) ticket = atomicAdd(p.work_counter, 1ull);
+          ch = -1;  // -1: nothing to step right now, -2: the launch is over
+          if (ticket < total) {
+            if (ticket < (unsigned long long)n_chains) {
+              ch = (int)ticket;
+            } else {
+              // (kept chains are not pushed: the last tickets wait for pushes that never come,
+              // until the count of finished steps says that the launch is over)
+              int32_t* slot = p.ring + (ticket - (unsigned long long)n_chains) % cap;
+              int v = ld_acquire(slot);
+              if (!share) {
+                for (int spin = 1; v == 0; ++spin) {
+                  __nanosleep(32);
+                  v = ld_acquire(slot);
+                  if (v == 0 && (spin & 15) == 0 && *(volatile unsigned long long*)p.steps_done >= total) { ch = -2; break; }
+                }
+              } else if (v == 0 && *(volatile unsigned long long*)p.steps_done >= total) {
+                ch = -2;
+              }
+              if (v != 0) {
+                st_release(slot, 0);  // the slot may be refilled cap pushes later
+                ch = v - 1;
+              }
             }
+          } else if (!share || *(volatile unsigned long long*)p.steps_done >= total) {
+            ch = -2;
           }
-        } else if (!share || *(volatile unsigned long long*)p.steps_done >= total) {
-          ch = -2;
+          *ticket_p = ch >= 0 ? ~0ull : ticket;
+          if (share && (ch == -1) != idle) atomicAdd(p.idle, ch == -1 ? 1 : -1);
+          if (share && ch == -1 && *(volatile int32_t*)p.help_count <= 0) ch = -3;  // nobody to help right now
         }
-        *ticket_p = ch >= 0 ? ~0ull : ticket;
-        if (share && (ch == -1) != idle) atomicAdd(p.idle, ch == -1 ? 1 : -1);
         tslot[flip] = ch;
       }
       __syncthreads();
       chain = tslot[flip];
       flip ^= 1;
       RC_PH(PH_TICKET);
-      if (chain == -1) {
+      if (chain == -3) {  // (one word polled by one thread: the CTAs at work keep the L2 to themselves)
         idle = true;
+        __nanosleep(2000);
+        continue;
+      }
+      if (chain == -1 || chain == -4) {
+        if (chain == -1) idle = true;
         if constexpr (kShare) {
           int par = c.par;
-          help_once<kWilson, kSpill>(&p, &par);  // out of line, with a descriptor of its own
+#ifndef RC_X_NOHELP
+          const int did = help_once<kWilson, kSpill>(&par, chain == -4);  // out of line, with a descriptor of its own
+#else
+          const int did = 0;
+#endif
           c.par = par;
+          if (chain == -4 && !did && tid == 0) c.s.misc[M_HELPMODE] = 0;  // back to the ring of ready chains
         }
         continue;
       }
@@ -2133,57 +2342,22 @@ __global__ void __launch_bounds__(kWilson ? 256 : 512, kWilson ? 4 : 2) recom_st
       t = chain < 0 ? total : 0;
     }
     if (t >= total) break;
-    c.chain = chain;
-    c.gchain = (uint32_t)(chain + p.cfg.chain_offset);
-    c.assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
-    c.mask = p.st.d_cut_mask + (size_t)chain * p.st.mask_stride;
-    c.tally = p.st.d_tally + (size_t)chain * p.cfg.n_districts;
-    int status = __ldcg(p.st.d_status + chain);
-    if (status == RC_OK) {
-      // one accepted step (chain.py:185-195): propose until valid, accept always
-      uint32_t prop_no = __ldcg(p.st.d_proposal_no + chain);
-      RC_PH(PH_STATE);
-      const RcReplayStep* rs = replay ? p.rp.steps + t : nullptr;
-      ProposalResult r = {RC_OK, 0, 0, 0};
-      for (int streak = 0; streak < streak_cap; ++streak) {
-        if constexpr (kWilson) {
-          if (p.cfg.proposal_kind == RC_PROPOSAL_REVERSIBLE && !replay) r = propose_reversible(c, prop_no, ctr);
-          else r = propose<kWilson, kShare, kSpill>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
-        } else {
-          r = propose<kWilson, kShare, kSpill>(c, replay ? (uint32_t)t : prop_no, rs, ctr);
-        }
-        ++prop_no;
-        __syncthreads();
-        if (r.status || r.accepted || replay) break;
-      }
-      status = r.status ? r.status : (r.accepted ? RC_OK : RC_ERR_INVALID_STREAK);
-      if (tid == 0) {
-        p.st.d_proposal_no[chain] = prop_no;
-        if (status == RC_OK) p.st.d_step_no[chain] = __ldcg(p.st.d_step_no + chain) + 1;
-        else p.st.d_status[chain] = status;
-      }
-      if (tid < RC_N_COUNTERS) {
-        int64_t* g = p.st.d_counters + (size_t)chain * RC_N_COUNTERS + tid;
-        *g = __ldcg(g) + ctr[tid];
-        ctr[tid] = 0;
-      }
-      if (replay) {
-        if (p.rp.info_trace && tid == 0) {
-          int32_t* inf = p.rp.info_trace + 4 * t;
-          inf[0] = r.trees; inf[1] = r.nbal; inf[2] = p.st.d_cut_count[chain]; inf[3] = status;
-        }
-        if (p.rp.assign_trace)
-          for (int i = tid; i < p.g.N; i += blockDim.x) p.rp.assign_trace[(size_t)t * p.g.N + i] = c.assign[i];
-      }
-    }
+    const int status = step_body<kWilson, kSpill, kShare>(p, c, chain, t, replay, streak_cap, ctr);
     __threadfence();
     __syncthreads();
     RC_PH(PH_FLUSH);
     if (!replay && tid == 0) {
       const int done = __ldcg(p.progress + chain) + 1;  // this CTA owns the chain until it is pushed back
       p.progress[chain] = done;
-      atomicAdd(p.steps_done, 1ull);
-      if (done < p.n_steps) {
+      const unsigned long long all_done = atomicAdd(p.steps_done, 1ull) + 1ull;
+      if (kShare && share && *(volatile int32_t*)p.help_count > 0) c.s.misc[M_HELPMODE] = 1;  // look at it before the next ticket
+      // The launch ends with its slowest chain, and a chain that has fallen behind (a step with
+      // hundreds of retries) loses more time yet queueing between its steps.  So a chain more than
+      // kLagMargin steps behind the average keeps its CTA until it has caught up: with more chains
+      // than CTAs the field queues ~ n_chains / grid step times per step, the laggard none.
+      if (done < p.n_steps && (unsigned long long)(done + kLagMargin) * (unsigned long long)n_chains <= all_done) {
+        c.s.misc[M_KEEP] = chain;
+      } else if (done < p.n_steps) {
         const unsigned long long q = atomicAdd(p.work_counter + 1, 1ull);
         int32_t* slot = p.ring + q % cap;
         while (ld_acquire(slot) != 0) __nanosleep(32);  // its previous content has been taken

@@ -30,14 +30,18 @@ eng = Engine(csr, cfg, plan)
 info = eng.info()
 eng.run(4).synchronize(); eng.check_status()
 best = 0
+tot_ms = 0.0
+all_ms = []
 c0 = eng.counters.sum(0).cpu().numpy()
 for _ in range(a.reps):
     eng.run(a.S); ms = eng.last_run_ms()
     best = max(best, a.chains * a.S / ms * 1e3)
+    tot_ms += ms
+    all_ms.append(round(ms, 1))
 eng.check_status()
 c = eng.counters.sum(0).cpu().numpy() - c0
 steps = a.chains * a.S * a.reps
 print(f"{a.workload}{' wilson' if a.wilson else ''} W={info.wilson_walkers} thr={info.threads_per_cta} ctas/sm={info.ctas_per_sm} "
-      f"smem={info.smem_bytes} spill={info.spill} chains={a.chains} S={a.S}: best {best:,.0f} steps/s  "
+      f"smem={info.smem_bytes} spill={info.spill} chains={a.chains} S={a.S}: best {best:,.0f} mean {a.chains * a.S * a.reps / tot_ms * 1e3:,.0f} steps/s  "
       f"trees/step {c[_abi.RC_CTR_TREES]/steps:.2f} draws/tree {c[_abi.RC_CTR_WALK]/max(c[_abi.RC_CTR_TREES],1):.0f} "
-      f"n_sub {c[_abi.RC_CTR_NODES]/steps:.0f}", flush=True)
+      f"n_sub {c[_abi.RC_CTR_NODES]/steps:.0f} ms {all_ms}", flush=True)
