@@ -12,6 +12,11 @@ prof() {  # tag, quick.py args
 prof mst_c2 config2 --chains 1024 --S 64 --reps 2
 prof mst_c3 config3 --chains 1024 --S 64 --reps 2
 prof wilson_c3 config3 --wilson --chains 1024 --S 16 --reps 2
+# the shared-retry build on the same config-3 launch
+CMD="python scripts/dev/quick.py config3 --chains 1024 --S 64 --reps 2"
+RECOM_B200_SHARE=1 timeout 120 $CMD > gpurun_out/r2_plain_mst_c3_share.log 2>&1 && \
+RECOM_B200_SHARE=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:recom_step -s 2 -c 1 -f -o gpurun_out/r2_prof_mst_c3_share $CMD > gpurun_out/r2_ncu_mst_c3_share.log 2>&1
+tail -1 gpurun_out/r2_plain_mst_c3_share.log
 BENCH="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --extras config3,config3_wilson"
 timeout 200 $BENCH > gpurun_out/r2_bench_plain.json 2> gpurun_out/r2_bench_plain.err && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv $BENCH > gpurun_out/r2_bench_ncu.log 2>&1

@@ -195,7 +195,7 @@ def test_shared_retries_bit_exact_with_oracle(monkeypatch):
     monkeypatch.setenv("RECOM_B200_HELP_WIN", "3")
     csr, plan, cfg = workloads.config3(n_chains=24, seed=9)
     eng = _free_run_vs_oracle(csr, plan, cfg, 30)
-    assert eng.counters.cpu().numpy()[:, _abi.RC_CTR_TREES].max() > 150  # steps of more than 8 + 3 trees happened
+    assert eng.counters.cpu().numpy()[:, _abi.RC_CTR_TREES].max() > 150  # (many steps went beyond the common path)
     monkeypatch.delenv("RECOM_B200_HELP_WIN")
     csr, plan, cfg = workloads.config3(n_chains=3, seed=78)
     _free_run_vs_oracle(csr, plan, cfg, 40)
@@ -205,6 +205,37 @@ def test_shared_retries_bit_exact_with_oracle(monkeypatch):
 
     ora = oracle.OracleChains(csr, cfg, plan).run(12, n_threads=8)
     assert np.array_equal(eng.counters.cpu().numpy()[:, _abi.RC_CTR_WALK], ora.counters[:, _abi.RC_CTR_WALK])
+
+
+def test_shared_retries_recruiting_and_limits(monkeypatch):
+    """The rest of the shared-retry protocol.  (1) Recruiting: with the thresholds turned down
+    (steps leave the common path after 4 failed trees and publish after 12 although every CTA has
+    a chain of its own) busy CTAs leave their chains for other chains' steps all the time, and
+    lagging chains keep their CTAs - the chains must not change.  (2) max_attempts in the long
+    path: a step whose trees run out ends in RC_ERR_MAX_ATTEMPTS exactly where the oracle's does
+    (tree.py:718), with the same attempt counts."""
+    from oracle import oracle
+
+    monkeypatch.setenv("RECOM_B200_SHARE", "1")
+    monkeypatch.setenv("RECOM_B200_HELP_AFTER", "4")
+    monkeypatch.setenv("RECOM_B200_RECRUIT_AFTER", "12")
+    csr, plan, cfg = workloads.config3(n_chains=1024, seed=80)
+    _free_run_vs_oracle(csr, plan, cfg, 8)
+    monkeypatch.setenv("RECOM_B200_UNITS_PER_RECRUIT", "4")
+    csr, plan, cfg = workloads.config3(n_chains=700, seed=82, tree_kind=_abi.RC_TREE_WILSON)
+    _free_run_vs_oracle(csr, plan, cfg, 3)
+    csr, plan, cfg = workloads.config3(n_chains=64, seed=81, max_attempts=20)
+    eng = _engine(csr, cfg, plan)
+    eng.run(40).synchronize()
+    ora = oracle.OracleChains(csr, cfg, plan).run(40, n_threads=8)
+    st = eng.status.cpu().numpy()
+    assert np.array_equal(st, ora.status)
+    assert (st == _abi.RC_ERR_MAX_ATTEMPTS).any() and (st == 0).any()
+    assert np.array_equal(eng.step_no.cpu().numpy(), ora.step_no)
+    assert np.array_equal(eng.assignments(), ora.assignments())
+    ce, co = eng.counters.cpu().numpy(), ora.counters
+    for i in (_abi.RC_CTR_TREES, _abi.RC_CTR_ATTEMPTS):
+        assert np.array_equal(ce[:, i], co[:, i]), i
 
 
 def test_max_attempts_status():
