@@ -11,7 +11,7 @@ d = dict(zip(rows[0], zip(rows[2], rows[1])))
 def g(k):
     return float(d[k][0].replace(",", "")) if k in d and d[k][0] not in ("", "n/a") else float("nan")
 head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
-print(f"{title}\nncu --set full --clock-control none --import-source on, one launch; built from commit {head} (+ working tree)\n")
+print(f"{title}\nncu --set full --clock-control none --import-source on, one launch" + (f"; built from commit {head} (+ working tree)" if head else "") + "\n")
 inst = g("smsp__inst_executed.sum")
 print(f"launch: grid {int(g('launch__grid_size'))} x {int(g('launch__block_size'))} threads, {int(g('launch__registers_per_thread'))} registers/thread, "
       f"{g('launch__shared_mem_per_block_dynamic'):.1f} KB dynamic shared memory per CTA; CTAs/SM limited by registers {int(g('launch__occupancy_limit_registers'))}, "
