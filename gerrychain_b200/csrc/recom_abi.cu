@@ -212,18 +212,26 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
     // the walkers' state in shared memory and the adjacency in L2; else both in L2
     size_t glob = 0;
     int level = 0;
+    if (const char* v = getenv("RECOM_B200_WILSON_LEVEL")) level = std::min(2, std::max(0, atoi(v)));  // dev: lowest placement level tried
     const int msh = N >= 65536 ? 2 : 0;  // large graphs: a popcount prefix per four bitmap words
     p.mpref_shift = msh;
+    const int W0 = W;
     for (;;) {
       total = rc::wilson_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R, W, sh, level, msh, nullptr, nullptr, &glob, &cold);
-      if (total <= smem_max) break;
-      if (cfg->wilson_walkers == 0 && W > 2 && level < 2) { W >>= 1; continue; }
+      // Level 0 takes what fits (with fewer walkers if need be).  Level 1 (walker state in shared
+      // memory, adjacency in L2) only where it still leaves room for 3 CTAs per SM: once a walk
+      // step is a round trip to L2 / HBM anyway, what counts is walks in flight, and level 2
+      // (shared memory holds the membership bitmap alone) runs 4 CTAs of 256 threads per SM.
+      // Measured at config 4 (200 k nodes, 8 k-node pairs, steps/s): level 1, 1 CTA x 4 walkers
+      // 5.6 k; level 1, 2 x 2: 7.7 k; level 2, 4 x 4: 8.0-8.2 k; 5 x 192 threads 7.8 k;
+      // 6 x 160: 5.8 k; 7 x 128: 5.0 k (the blocks of that many CTAs thrash L2); 8 walkers 6.6 k.
+      if (level == 0 && total <= smem_max) break;
+      if (level == 1 && total <= smem_max && 3 * (total + 1024) <= (size_t)prop.sharedMemPerMultiprocessor) break;
       if (level == 2) break;
+      if (level == 0 && cfg->wilson_walkers == 0 && W > 2) { W >>= 1; continue; }
       ++level;
-      W = cfg->wilson_walkers > 0 ? cfg->wilson_walkers : (cfg->proposal_kind == RC_PROPOSAL_REVERSIBLE ? 1 : 4);
+      W = W0;
     }
-    // (level 1, config 4: two CTAs per SM with two walkers each were measured against one CTA with
-    // four - 5.1 k vs 5.7 k steps/s: the second CTA's adjacency pushes the first one's out of L2)
     p.walkers = W;
     p.wilson_level = level;
     split = total;
@@ -298,11 +306,14 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   if (e->ctas_per_sm < 1) { rc_engine_destroy(e); return fail(RC_ERR_CAPACITY, "kernel does not fit an SM"); }
   // persistent grid: every CTA resident; they pop ready chains from a ring (recom_step_kernel)
   e->grid = e->ctas_per_sm * e->n_sms;
-  if (e->spill) {
-    // spill mode: every step of a walk is a round trip to the CTA's scratch block; keep the
-    // blocks of the resident CTAs inside L2 (126 MB) rather than have more CTAs wait on DRAM
+  if (e->spill && !wilson) {
+    // MST spill mode: the Boruvka rounds stream the CTA's scratch block again and again; keep the
+    // blocks of the resident CTAs inside L2 (126 MB) rather than have more CTAs wait on DRAM.
+    // (Not for Wilson: its walks are latency bound, more of them in flight win - see above.)
     const size_t per_cta = e->spill_bytes + (e->cold_bytes + (size_t)(cap_nodes + cap_edges) * 4) / 4;  // the streamed arrays are touched once
-    long long fit = (long long)((size_t)96 << 20) / (long long)(per_cta ? per_cta : 1);
+    size_t l2_budget = (size_t)96 << 20;
+    if (const char* v = getenv("RECOM_B200_L2_FIT_MB")) l2_budget = (size_t)std::max(1, atoi(v)) << 20;  // dev
+    long long fit = (long long)l2_budget / (long long)(per_cta ? per_cta : 1);
     fit = fit / e->n_sms * e->n_sms;
     if (fit < e->n_sms) fit = e->n_sms;
     if (e->grid > fit) e->grid = (int)fit;

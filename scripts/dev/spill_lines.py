@@ -27,5 +27,5 @@ w = "1" if "--wilson" in sys.argv else "0"
 reg = next((x.split("=")[1] for x in sys.argv if x.startswith("--region=")), "main")
 a, b = analyze(f"recom_step_kernelILb{w}ELb0ELb0"), analyze(f"recom_step_kernelILb{w}ELb0ELb1", reg)
 for k in sorted(set(a) | set(b), key=lambda k: (k[1], k[0])):
-    if abs(a[k] - b[k]) >= 3: print(k, "plain", a[k], "share", b[k])
+    if abs(a[k] - b[k]) >= (1 if "--all" in sys.argv else 3): print(k, "plain", a[k], "share", b[k])
 print("total", sum(a.values()), sum(b.values()))

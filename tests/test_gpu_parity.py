@@ -322,14 +322,16 @@ def test_full_size_properties_config2():
 def test_spill_mode_bit_exact_with_oracle():
     """Caps too large for shared memory push the working arrays into the per-CTA global
     scratch (the path 200k-node graphs take); results must not change."""
-    for tree_kind in (_abi.RC_TREE_MST, _abi.RC_TREE_WILSON):
+    for tree_kind, cap_nodes in ((_abi.RC_TREE_MST, 9000), (_abi.RC_TREE_WILSON, 5400), (_abi.RC_TREE_WILSON, 9000)):
         csr, plan, cfg = workloads.config3(n_chains=24, seed=31, tree_kind=tree_kind,
-                                           cap_nodes=9000, cap_edges=26976)
+                                           cap_nodes=cap_nodes, cap_edges=26976)
         eng = _free_run_vs_oracle(csr, plan, cfg, 12)
         if tree_kind == _abi.RC_TREE_MST:
             assert eng.info().smem_bytes < 16 * 1024  # only the membership bitmap stays on chip
+        elif cap_nodes == 5400:
+            assert eng.info().spill == 1  # walker state on chip (3 CTAs per SM), the adjacency in the CTA's L2 block
         else:
-            assert eng.info().spill == 1  # walker state on chip, the adjacency in the CTA's L2 block
+            assert eng.info().spill == 2  # level 1 would leave one CTA per SM: everything in the global block, 4 CTAs
 
 
 def test_wilson_all_in_l2_bit_exact_with_oracle():
