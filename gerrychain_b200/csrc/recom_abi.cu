@@ -216,8 +216,12 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
     const int msh = N >= 65536 ? 2 : 0;  // large graphs: a popcount prefix per four bitmap words
     p.mpref_shift = msh;
     const int W0 = W;
+    // small pairs (row index in 11 bits, degree in 5): 16-bit adjacency entries, level 0 only
+    const bool can16 = cap_nodes + cap_nodes / 8 <= 2048 && maxdeg <= 31 && !getenv("RECOM_B200_NBR32");
     for (;;) {
-      total = rc::wilson_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R, W, sh, level, msh, nullptr, nullptr, &glob, &cold);
+      p.nbr16 = (can16 && level == 0) ? 1 : 0;
+      total = rc::wilson_layout(nullptr, nullptr, N, cap_nodes, cap_edges, R, W, sh, level, msh, nullptr, nullptr, &glob, &cold,
+                                p.nbr16 ? 2 : 4);
       // Level 0 takes what fits (with fewer walkers if need be).  Level 1 (walker state in shared
       // memory, adjacency in L2) only where it still leaves room for 3 CTAs per SM: once a walk
       // step is a round trip to L2 / HBM anyway, what counts is walks in flight, and level 2

@@ -72,6 +72,7 @@ struct Params {
   int64_t cold_stride;
   int32_t walkers;        // Wilson: spanning trees drawn concurrently per chain-step (lanes of one warp)
   int32_t nbr_shift;      // Wilson: log2 of the adjacency slots per node kept in the hot tier
+  int32_t nbr16;          // Wilson: 16-bit adjacency entries (neighbour 11 bits | its degree << 11): small pairs, level 0
   int32_t wilson_level;   // Wilson: 0 = state and adjacency in shared memory, 1 = adjacency in L2, 2 = both in L2
   int32_t mpref_shift;    // Wilson: Smem.msh
   HelpRec* help;                       // [n_chains]
@@ -103,7 +104,8 @@ struct Smem {
   uint32_t* newb;    // [CN/32] the same after the proposed cut
   uint8_t* ecls;     // [CE] bitmask of region columns the edge crosses (R > 0 only)
   // Wilson only: adjacency of the merged pair, rows in ascending neighbour id
-  uint32_t* nbr;     // [(CN + CN/8) << nbr_shift] rows of D = 1 << nbr_shift slots: row u < n belongs to
+  uint32_t* nbr;     // (uint16_t entries, neighbour | degree << 11, when Params.nbr16)
+                     // [(CN + CN/8) << nbr_shift] rows of D = 1 << nbr_shift slots: row u < n belongs to
                      // node u; an entry is a neighbour (bits 0-15) | degree OF THAT NEIGHBOUR << 16,
                      // ascending; a node of degree > D keeps D - 1 entries and a link (slot D - 1) to
                      // a spare row (index >= n) that holds the next ones, and so on
@@ -240,7 +242,7 @@ __host__ __device__ inline size_t smem_layout(Smem* s, unsigned char* base, int 
 // (S and/or A), *cold_out the cold bytes.
 __host__ __device__ inline size_t wilson_layout(Smem* s, unsigned char* base, int N, int CN, int CE, int R, int W,
                                                 int nbr_shift, int level, int msh, unsigned char* glob, unsigned char* cold,
-                                                size_t* glob_out = nullptr, size_t* cold_out = nullptr) {
+                                                size_t* glob_out = nullptr, size_t* cold_out = nullptr, int nbr_bytes = 4) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return r; };
   const int NW = (N + 31) / 32;
@@ -256,7 +258,7 @@ __host__ __device__ inline size_t wilson_layout(Smem* s, unsigned char* base, in
   size_t o_wsum = take(size_t(CN) * 4);
   size_t o_wst = take(size_t(W) * size_t(CN) * 2);
   const size_t s_end = o;
-  size_t o_nbr = take((size_t(CN + CN / 8) << nbr_shift) * 4);
+  size_t o_nbr = take((size_t(CN + CN / 8) << nbr_shift) * (size_t)nbr_bytes);
   size_t o_wdeg = take(size_t(CN) * 2);
   const size_t a_end = o;
   const size_t smem = level == 0 ? a_end : level == 1 ? s_end : core;

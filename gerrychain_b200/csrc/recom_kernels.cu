@@ -114,14 +114,23 @@ __device__ int pick_cut_edge(Chain& c, int cut_count, uint32_t prop_no, uint32_t
 // of degree > D keep D - 1 entries there and a link in slot D - 1 to a spare row (index >= n)
 // with the next ones - linked again if those are more than D.
 // entry number idx of node u (degree du): slot idx of a short row, else down the links
-__device__ __forceinline__ uint32_t* nbr_slot(const Smem& s, int u, int du, int idx, int sh) {
+// (E: uint32_t entries, neighbour | degree << 16, or - small pairs - uint16_t, neighbour | degree << 11)
+template <typename E>
+__device__ __forceinline__ E* nbr_slot(const Smem& s, int u, int du, int idx, int sh) {
   const int D = 1 << sh;
-  uint32_t* row = s.nbr + ((size_t)u << sh);
-  while (du > D) { if (idx < D - 1) return row + idx; row = s.nbr + ((size_t)row[D - 1] << sh); idx -= D - 1; du -= D - 1; }
+  E* const base = reinterpret_cast<E*>(s.nbr);
+  E* row = base + ((size_t)u << sh);
+  while (du > D) { if (idx < D - 1) return row + idx; row = base + ((size_t)row[D - 1] << sh); idx -= D - 1; du -= D - 1; }
   return row + idx;
 }
+// neighbour number q of node u (degree d)
+__device__ __forceinline__ int nbr_id(const Smem& s, const Params& p, int u, int d, int q) {
+  return p.nbr16 ? (int)(*nbr_slot<uint16_t>(s, u, d, q, p.nbr_shift) & 0x7ffu) : (int)(*nbr_slot<uint32_t>(s, u, d, q, p.nbr_shift) & 0xffffu);
+}
 
-__device__ int build_local_adjacency(Chain& c, const Step& st) {
+template <typename E>
+__device__ int build_local_adjacency_t(Chain& c, const Step& st) {
+  constexpr int kDegShift = sizeof(E) == 2 ? 11 : 16;
   const Params& p = *c.p;
   const Smem& s = c.s;
   const int tid = threadIdx.x, T = blockDim.x;
@@ -141,10 +150,10 @@ __device__ int build_local_adjacency(Chain& c, const Step& st) {
       for (int left = d - (D - 1); left > 0; left -= (left > D ? D - 1 : left)) ++need;
       int r = atomicAdd(&s.misc[M_CNT], need);
       if (r + need <= rows_cap) {
-        uint32_t* row = s.nbr + ((size_t)i << sh);
+        E* row = reinterpret_cast<E*>(s.nbr) + ((size_t)i << sh);
         for (int left = d - (D - 1); left > 0; left -= (left > D ? D - 1 : left)) {
-          row[D - 1] = (uint32_t)r;
-          row = s.nbr + ((size_t)r << sh);
+          row[D - 1] = (E)r;
+          row = reinterpret_cast<E*>(s.nbr) + ((size_t)r << sh);
           ++r;
         }
       }
@@ -156,22 +165,25 @@ __device__ int build_local_adjacency(Chain& c, const Step& st) {
   for (int j = tid; j < m; j += T) {
     const uint32_t uv = s.euv[j];
     const int u = (int)(uv & 0xffffu), v = (int)(uv >> 16);
-    *nbr_slot(s, u, s.wdeg[u], (int)atomicAdd(&s.wtmp[u], 1u), sh) = (uint32_t)v;
-    *nbr_slot(s, v, s.wdeg[v], (int)atomicAdd(&s.wtmp[v], 1u), sh) = (uint32_t)u;
+    *nbr_slot<E>(s, u, s.wdeg[u], (int)atomicAdd(&s.wtmp[u], 1u), sh) = (E)v;
+    *nbr_slot<E>(s, v, s.wdeg[v], (int)atomicAdd(&s.wtmp[v], 1u), sh) = (E)u;
   }
   __syncthreads();
   for (int i = tid; i < n; i += T) {  // insertion sort of a short row, then the neighbours' degrees
     const int d = s.wdeg[i];
     for (int a = 1; a < d; ++a) {
-      const uint32_t kv = *nbr_slot(s, i, d, a, sh);
+      const E kv = *nbr_slot<E>(s, i, d, a, sh);
       int b = a - 1;
-      while (b >= 0 && *nbr_slot(s, i, d, b, sh) > kv) { *nbr_slot(s, i, d, b + 1, sh) = *nbr_slot(s, i, d, b, sh); --b; }
-      *nbr_slot(s, i, d, b + 1, sh) = kv;
+      while (b >= 0 && *nbr_slot<E>(s, i, d, b, sh) > kv) { *nbr_slot<E>(s, i, d, b + 1, sh) = *nbr_slot<E>(s, i, d, b, sh); --b; }
+      *nbr_slot<E>(s, i, d, b + 1, sh) = kv;
     }
-    for (int a = 0; a < d; ++a) { uint32_t* q = nbr_slot(s, i, d, a, sh); const uint32_t v = *q; *q = v | ((uint32_t)s.wdeg[v] << 16); }
+    for (int a = 0; a < d; ++a) { E* q = nbr_slot<E>(s, i, d, a, sh); const uint32_t v = *q; *q = (E)(v | ((uint32_t)s.wdeg[v] << kDegShift)); }
   }
   __syncthreads();
   return RC_OK;
+}
+__device__ int build_local_adjacency(Chain& c, const Step& st) {
+  return c.p->nbr16 ? build_local_adjacency_t<uint16_t>(c, st) : build_local_adjacency_t<uint32_t>(c, st);
 }
 
 // ---- P1: gather the merged pair into shared memory ---------------------------------------
@@ -598,8 +610,22 @@ struct WalkArgs {
 
 struct MemShared {  // level 0: 32-bit shared-window addresses
   static constexpr int kFirst = 2, kRest = 8;  // burst lengths (steps of straight-line code)
+  static constexpr uint32_t kIdMask = 0xffffu, kDegShift = 16;  // adjacency entry: neighbour | its degree << kDegShift
   uint32_t nbr, S, ring, deg;
   __device__ __forceinline__ uint32_t ld_nbr(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(nbr + 4u * i) : "memory"); return v; }
+  __device__ __forceinline__ uint32_t ld_ring(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + 4u * i) : "memory"); return v; }
+  __device__ __forceinline__ uint32_t ld_S(uint32_t i) const { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(S + 2u * i) : "memory"); return v; }
+  __device__ __forceinline__ void st_S(uint32_t i, uint32_t v) const { asm volatile("st.shared.u16 [%0], %1;" :: "r"(S + 2u * i), "h"((uint16_t)v) : "memory"); }
+  __device__ __forceinline__ uint32_t ld_deg(uint32_t i) const { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(deg + 2u * i) : "memory"); return v; }
+};
+
+// level 0 with 16-bit adjacency entries (pairs of at most 2048 rows, degrees below 32): half the
+// shared memory of the adjacency, one more CTA - four more walks - per SM at config 3
+struct MemShared16 {
+  static constexpr int kFirst = 2, kRest = 8;
+  static constexpr uint32_t kIdMask = 0x7ffu, kDegShift = 11;
+  uint32_t nbr, S, ring, deg;
+  __device__ __forceinline__ uint32_t ld_nbr(uint32_t i) const { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(nbr + 2u * i) : "memory"); return v; }
   __device__ __forceinline__ uint32_t ld_ring(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + 4u * i) : "memory"); return v; }
   __device__ __forceinline__ uint32_t ld_S(uint32_t i) const { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(S + 2u * i) : "memory"); return v; }
   __device__ __forceinline__ void st_S(uint32_t i, uint32_t v) const { asm volatile("st.shared.u16 [%0], %1;" :: "r"(S + 2u * i), "h"((uint16_t)v) : "memory"); }
@@ -610,6 +636,7 @@ struct MemShared {  // level 0: 32-bit shared-window addresses
 // cached loads, kept in program order by asm volatile), the walker state stays in shared memory
 struct MemMixed {
   static constexpr int kFirst = 1, kRest = 2;  // a step is an L2 round trip: a wasted one costs more than a branch
+  static constexpr uint32_t kIdMask = 0xffffu, kDegShift = 16;
   const uint32_t* nbr; const uint16_t* deg;
   uint32_t S, ring;
   __device__ __forceinline__ uint32_t ld_nbr(uint32_t i) const { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(nbr + i) : "memory"); return v; }
@@ -621,6 +648,7 @@ struct MemMixed {
 
 struct MemGlobal {  // level 2: state and adjacency in the CTA's global block
   static constexpr int kFirst = 1, kRest = 2;
+  static constexpr uint32_t kIdMask = 0xffffu, kDegShift = 16;
   const uint32_t* nbr; uint16_t* S; const uint16_t* deg;
   uint32_t ring;
   __device__ __forceinline__ uint32_t ld_nbr(uint32_t i) const { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(nbr + i) : "memory"); return v; }
@@ -710,9 +738,9 @@ __device__ __noinline__ void wilson_walk_loop(const WalkArgs a, Mem M) {
           bool alive = true;
 #pragma unroll
           for (int k = 0; k < K; ++k) {
-            const uint32_t v = e & 0xffffu;
+            const uint32_t v = e & Mem::kIdMask;
             if (alive) M.st_S(u, v);
-            const uint32_t en = pick(v, e >> 16, rr[k]);  // the entry the NEXT step takes (draw t + 1 + k)
+            const uint32_t en = pick(v, e >> Mem::kDegShift, rr[k]);  // the entry the NEXT step takes (draw t + 1 + k)
             const uint32_t wv = M.ld_S(v);
             t += alive ? 1u : 0u;
             const bool go = alive && !(wv & kInTree);
@@ -763,7 +791,14 @@ __device__ __forceinline__ void wilson_walk_warp(const Chain& c, const Step& st,
   a.nbr = s.nbr; a.wst = s.wst; a.wring = s.wring; a.wdeg = s.wdeg; a.wmeta = s.wmeta;
   a.timers = reinterpret_cast<unsigned long long*>(s.misc + 96);
   const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s.wring + w * kRing);
-  if (p.wilson_level == 0) {
+  if (p.wilson_level == 0 && p.nbr16) {
+    MemShared16 M;
+    M.nbr = (uint32_t)__cvta_generic_to_shared(s.nbr);
+    M.S = (uint32_t)__cvta_generic_to_shared(s.wst + (size_t)w * p.cap_nodes);
+    M.ring = ring;
+    M.deg = (uint32_t)__cvta_generic_to_shared(s.wdeg);
+    if (a.sh == 2) wilson_walk_loop<MemShared16, 2>(a, M); else wilson_walk_loop<MemShared16, 3>(a, M);
+  } else if (p.wilson_level == 0) {
     MemShared M;
     M.nbr = (uint32_t)__cvta_generic_to_shared(s.nbr);
     M.S = (uint32_t)__cvta_generic_to_shared(s.wst + (size_t)w * p.cap_nodes);
@@ -802,7 +837,7 @@ __device__ void wilson_walk_recorded(const Chain& c, const Step& st, long long t
         const int gv = p.rp.stack_val[sp[gu] + cu];
         if (gv >= 0 && gv < p.g.N && is_member(s, gv)) {
           const int lv = local_id(s, gv);
-          for (int q = 0; q < d; ++q) if ((int)(*nbr_slot(s, u, d, q, sh) & 0xffffu) == lv) v = lv;
+          for (int q = 0; q < d; ++q) if (nbr_id(s, p, u, d, q) == lv) v = lv;
         }
       }
       if (v < 0) { err = RC_ERR_REPLAY; break; }
@@ -1204,7 +1239,8 @@ __device__ __forceinline__ void chain_layout(Chain& c, const Params& p) {
   c.p = &p;
   if constexpr (kWilson)
     wilson_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R, p.walkers, p.nbr_shift, p.wilson_level, p.mpref_shift,
-                  p.spill + (size_t)blockIdx.x * p.spill_stride, p.cold + (size_t)blockIdx.x * p.cold_stride);
+                  p.spill + (size_t)blockIdx.x * p.spill_stride, p.cold + (size_t)blockIdx.x * p.cold_stride, nullptr, nullptr,
+                  p.nbr16 ? 2 : 4);
   else
     smem_layout(&c.s, smem_raw, p.g.N, p.cap_nodes, p.cap_edges, p.g.R,
                 kSpill ? p.spill + (size_t)blockIdx.x * p.spill_stride : nullptr,

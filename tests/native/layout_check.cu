@@ -64,15 +64,15 @@ static bool check(int N, int CN, int CE, int R) {
 
 // rc::wilson_layout: for every placement level the arrays of each tier are disjoint and inside
 // the tier's block (shared memory / the CTA's global block / the cold block); wtmp aliases wsum.
-static bool check_wilson(int N, int CN, int CE, int R, int W, int sh) {
+static bool check_wilson(int N, int CN, int CE, int R, int W, int sh, int nbr_bytes = 4) {
   using namespace rc;
   const int NW = (N + 31) / 32, CW = (CN + 31) / 32;
-  for (int level = 0; level < 3; ++level) {
+  for (int level = 0; level < (nbr_bytes == 2 ? 1 : 3); ++level) {
     static unsigned char sm[1], gl[1], co[1];
     Smem s;
     size_t glob = 0, cold = 0;
     const int msh = N >= 65536 ? 2 : 0;
-    const size_t smem = wilson_layout(&s, sm, N, CN, CE, R, W, sh, level, msh, gl, co, &glob, &cold);
+    const size_t smem = wilson_layout(&s, sm, N, CN, CE, R, W, sh, level, msh, gl, co, &glob, &cold, nbr_bytes);
     std::vector<Span> in_sm, in_gl, in_co;
     auto put = [&](const char* name, const void* p, size_t bytes, int tier) {
       const unsigned char* q = (const unsigned char*)p;
@@ -86,7 +86,7 @@ static bool check_wilson(int N, int CN, int CE, int R, int W, int sh) {
     put("mbits", s.mbits, 4 * (size_t)NW, 0); put("mpref", s.mpref, 2 * (size_t)((NW >> msh) + 1), 0);
     put("oldb", s.oldb, 4 * (size_t)CW, 1); put("newb", s.newb, 4 * (size_t)CW, 1); put("whas", s.whas, 4 * (size_t)CW, 1);
     put("wsum", s.wsum, 4 * (size_t)CN, 1); put("wst", s.wst, 2 * (size_t)W * CN, 1);
-    put("nbr", s.nbr, 4 * ((size_t)(CN + CN / 8) << sh), 2); put("wdeg", s.wdeg, 2 * (size_t)CN, 2);
+    put("nbr", s.nbr, (size_t)nbr_bytes * ((size_t)(CN + CN / 8) << sh), 2); put("wdeg", s.wdeg, 2 * (size_t)CN, 2);
     put("pop", s.pop, 4 * (size_t)CN, 3); put("euv", s.euv, 4 * (size_t)CE, 3);
     put("ecls", s.ecls, R > 0 ? (size_t)CE : 0, 3);
     if (!disjoint(in_sm, "wilson shared") || !disjoint(in_gl, "wilson global") || !disjoint(in_co, "wilson cold")) return false;
@@ -110,6 +110,10 @@ int main() {
       for (int sh : {2, 3}) {
         if (!check_wilson(c[0], c[1], c[2], c[3], W, sh)) { printf("wilson case N=%d CN=%d CE=%d R=%d W=%d sh=%d\n", c[0], c[1], c[2], c[3], W, sh); return 1; }
         ++n;
+        if (c[1] + c[1] / 8 <= 2048) {  // 16-bit adjacency entries (level 0)
+          if (!check_wilson(c[0], c[1], c[2], c[3], W, sh, 2)) { printf("wilson16 case N=%d CN=%d W=%d sh=%d\n", c[0], c[1], W, sh); return 1; }
+          ++n;
+        }
       }
   }
   printf("ok %d\n", n);
