@@ -25,7 +25,8 @@ RC_ERR_BALANCE = 11
 RC_ERR_REVERSIBILITY = 12
 RC_PROPOSAL_RECOM = 0
 RC_PROPOSAL_REVERSIBLE = 1
-RC_SEED_REMAINING = 255
+RC_SEED_REMAINING = 255  # in the 8-bit-label build; 65535 in librecom_b200_l16.so
+RC_MAX_DISTRICTS = {8: 255, 16: 32767}  # include/recom_b200.h: RC_MAX_DISTRICTS per label width
 
 STATUS_NAMES = {
     0: "RC_OK",
@@ -169,6 +170,7 @@ class RcEngineInfo(C.Structure):
 EXPORTS = (
     "rc_last_error",
     "rc_abi_version",
+    "rc_label_bits",
     "rc_state_strides",
     "rc_engine_create",
     "rc_engine_destroy",
@@ -187,24 +189,43 @@ EXPORTS = (
     "rc_engine_last_run_ms",
 )
 
-LIB_NAME = "librecom_b200.so"
-_lib: Optional[C.CDLL] = None
+LIB_NAME = "librecom_b200.so"          # district labels in one byte (k <= 255)
+LIB_NAME_L16 = "librecom_b200_l16.so"  # the same sources built with 16-bit labels (k <= 32767)
+_libs: dict = {}
 
 
-def lib_path() -> str:
-    """The in-tree library; RECOM_B200_LIB selects another build of the same ABI (A/B runs)."""
-    override = os.environ.get("RECOM_B200_LIB")
+def label_bits_for(n_districts: int) -> int:
+    """Width of the district labels a plan with ``n_districts`` districts needs."""
+    if n_districts <= RC_MAX_DISTRICTS[8]:
+        return 8
+    if n_districts <= RC_MAX_DISTRICTS[16]:
+        return 16
+    raise ValueError(f"at most {RC_MAX_DISTRICTS[16]} districts (16-bit labels)")
+
+
+def label_dtype(label_bits: int):
+    import numpy as np
+
+    return np.uint8 if label_bits == 8 else np.uint16
+
+
+def lib_path(label_bits: int = 8) -> str:
+    """The in-tree library; RECOM_B200_LIB (RECOM_B200_LIB_L16 for the 16-bit-label build)
+    selects another build of the same ABI (A/B runs)."""
+    override = os.environ.get("RECOM_B200_LIB" if label_bits == 8 else "RECOM_B200_LIB_L16")
     if override:
         return override
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME if label_bits == 8 else LIB_NAME_L16)
 
 
-def load() -> C.CDLL:
-    """Load the in-tree CUDA library; raise loudly if it is missing."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    path = lib_path()
+def load(label_bits: int = 8) -> C.CDLL:
+    """Load the in-tree CUDA library (the build with ``label_bits``-wide district labels);
+    raise loudly if it is missing."""
+    if label_bits not in (8, 16):
+        raise ValueError("label_bits must be 8 or 16")
+    if label_bits in _libs:
+        return _libs[label_bits]
+    path = lib_path(label_bits)
     if not os.path.exists(path):
         raise ImportError(
             f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; "
@@ -213,7 +234,8 @@ def load() -> C.CDLL:
     lib = C.CDLL(path)
     lib.rc_last_error.restype = C.c_char_p
     lib.rc_abi_version.restype = C.c_int
-    for name in EXPORTS[2:]:
+    lib.rc_label_bits.restype = C.c_int
+    for name in EXPORTS[3:]:
         getattr(lib, name).restype = C.c_int
     lib.rc_state_strides.argtypes = [C.POINTER(RcGraph), C.POINTER(RcConfig), _i64p, _i64p]
     lib.rc_engine_create.argtypes = [
@@ -236,8 +258,10 @@ def load() -> C.CDLL:
     lib.rc_engine_info.argtypes = [C.c_void_p, C.POINTER(RcEngineInfo)]
     lib.rc_engine_last_run_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     if lib.rc_abi_version() != 1:
-        raise ImportError("librecom_b200.so ABI version mismatch")
-    _lib = lib
+        raise ImportError(f"{path}: ABI version mismatch")
+    if lib.rc_label_bits() != label_bits:
+        raise ImportError(f"{path} was built with {lib.rc_label_bits()}-bit labels, not {label_bits}")
+    _libs[label_bits] = lib
     return lib
 
 

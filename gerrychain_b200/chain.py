@@ -151,7 +151,8 @@ class ChainBatch:
 
     @property
     def assignment(self):
-        """torch.uint8 [n_chains, N] district index per node, on the device."""
+        """[n_chains, N] district index per node, on the device (torch.uint8; torch.int16 for
+        plans with more than 255 districts)."""
         return self._r.engine.assignment[:, : self._r.engine.csr.n_nodes]
 
     def cut_edge_counts(self) -> np.ndarray:
@@ -195,7 +196,7 @@ class ChainBatch:
         """Host ``Partition`` snapshot of chain ``i``."""
         e, init = self._r.engine, self._r.initial_state
         return init.__class__._from_device(
-            init, e.assignment[i, : e.csr.n_nodes].cpu().numpy(), (self._r.pop_col,),
+            init, e._labels_to_numpy(e.assignment[i, : e.csr.n_nodes]), (self._r.pop_col,),
             e.tally[i].cpu().numpy(), int(e.cut_count[i].item()),
             e.cut_mask[i].cpu().numpy().view(np.uint32).copy(), e.last_pair[i].cpu().numpy())
 
@@ -263,7 +264,7 @@ class BatchedMarkovChain:
         init = self.initial_state
         csr = init._ctx.csr(self.pop_col, self.region_surcharge)
         cfg = EngineConfig(n_districts=len(init), n_chains=self.n_chains, **self._ekw)
-        plans = init._vec if self._plans is None else np.asarray(self._plans, dtype=np.uint8)
+        plans = init._vec if self._plans is None else np.asarray(self._plans, dtype=init._vec.dtype)
         self.engine = Engine(csr, cfg, plans, device=self._device)
         self._warned = False
 

@@ -75,5 +75,5 @@ def cut_policy_for(region_surcharge, tree_kind: int) -> int:
 
 
 def strides(n_nodes: int, n_edges: int):
-    """(assign_stride bytes, mask_stride words): 16-byte aligned rows (128-bit loads of the assignment row)."""
+    """(assign_stride labels, mask_stride words): 16-byte aligned rows (128-bit loads of the assignment row)."""
     return (n_nodes + 15) // 16 * 16, ((n_edges + 31) // 32 + 3) // 4 * 4

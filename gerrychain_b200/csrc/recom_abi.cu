@@ -85,6 +85,7 @@ extern "C" {
 
 const char* rc_last_error(void) { return g_err; }
 int rc_abi_version(void) { return RC_ABI_VERSION; }
+int rc_label_bits(void) { return RC_LABEL_BITS; }
 
 int rc_state_strides(const RcGraph* g, const RcConfig* c, int64_t* assign_stride, int64_t* mask_stride) {
   (void)c;
@@ -110,8 +111,11 @@ int rc_engine_create(const RcGraph* g, const RcConfig* cfg, int device, RcEngine
   if (!g || !cfg || !out) return fail(RC_ERR_INVALID_ARG, "null argument");
   *out = nullptr;
   if (g->n_nodes < 2 || g->n_edges < 1) return fail(RC_ERR_INVALID_ARG, "empty graph");
-  if (cfg->n_districts < 2 || cfg->n_districts > 255)
-    return fail(RC_ERR_INVALID_ARG, "n_districts must be in [2, 255] (uint8 assignment)");
+  if (cfg->n_districts < 2 || cfg->n_districts > RC_MAX_DISTRICTS)
+    return fail(RC_ERR_INVALID_ARG, "n_districts must be in [2, %d] (%d-bit labels; librecom_b200_l16.so carries 16-bit labels)",
+                RC_MAX_DISTRICTS, RC_LABEL_BITS);
+  if (cfg->allow_pair_reselection && cfg->n_districts > 256)
+    return fail(RC_ERR_INVALID_ARG, "allow_pair_reselection keeps a 256 x 256 bitset of failed pairs: n_districts <= 256");
   if (cfg->n_chains < 1) return fail(RC_ERR_INVALID_ARG, "n_chains must be >= 1");
   if (g->n_region_cols < 0 || g->n_region_cols > 8)
     return fail(RC_ERR_INVALID_ARG, "at most 8 region columns");
@@ -490,8 +494,8 @@ int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream) {
   return RC_OK;
 }
 
-int rc_engine_step_host(RcEngine* e, const uint8_t* h_assignment, int64_t h_stride, int64_t n_steps,
-                        uint8_t* h_assignment_out, int64_t* h_tally_out, int32_t* h_cut_count_out,
+int rc_engine_step_host(RcEngine* e, const rc_label_t* h_assignment, int64_t h_stride, int64_t n_steps,
+                        rc_label_t* h_assignment_out, int64_t* h_tally_out, int32_t* h_cut_count_out,
                         int32_t* h_status_out, void* stream) {
   if (!e || !e->bound) return fail(RC_ERR_INVALID_ARG, "engine has no bound state");
   if (!h_assignment) return fail(RC_ERR_INVALID_ARG, "null h_assignment");
@@ -500,20 +504,21 @@ int rc_engine_step_host(RcEngine* e, const uint8_t* h_assignment, int64_t h_stri
   CUDA_OK(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
   const RcState& st = e->p.st;
+  constexpr size_t LB = sizeof(rc_label_t);
   if (h_stride == st.assign_stride)  // same pitch on both sides: one contiguous copy
-    CUDA_OK(cudaMemcpyAsync(st.d_assignment, h_assignment, (size_t)h_stride * n, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(st.d_assignment, h_assignment, LB * (size_t)h_stride * n, cudaMemcpyHostToDevice, s));
   else
-    CUDA_OK(cudaMemcpy2DAsync(st.d_assignment, (size_t)st.assign_stride, h_assignment, (size_t)h_stride,
-                              (size_t)N, (size_t)n, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpy2DAsync(st.d_assignment, LB * (size_t)st.assign_stride, h_assignment, LB * (size_t)h_stride,
+                              LB * (size_t)N, (size_t)n, cudaMemcpyHostToDevice, s));
   int rc = init_state_impl(e, stream, 1);
   if (rc) return rc;
   rc = rc_engine_run(e, n_steps, stream);
   if (rc) return rc;
   if (h_assignment_out && h_stride == st.assign_stride)
-    CUDA_OK(cudaMemcpyAsync(h_assignment_out, st.d_assignment, (size_t)h_stride * n, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(h_assignment_out, st.d_assignment, LB * (size_t)h_stride * n, cudaMemcpyDeviceToHost, s));
   else if (h_assignment_out)
-    CUDA_OK(cudaMemcpy2DAsync(h_assignment_out, (size_t)h_stride, st.d_assignment, (size_t)st.assign_stride,
-                              (size_t)N, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpy2DAsync(h_assignment_out, LB * (size_t)h_stride, st.d_assignment, LB * (size_t)st.assign_stride,
+                              LB * (size_t)N, (size_t)n, cudaMemcpyDeviceToHost, s));
   if (h_tally_out)
     CUDA_OK(cudaMemcpyAsync(h_tally_out, st.d_tally, sizeof(int64_t) * (size_t)n * k, cudaMemcpyDeviceToHost, s));
   if (h_cut_count_out)
@@ -529,7 +534,8 @@ static int seed_impl(RcEngine* e, int32_t max_attempts, const RcReplay* rp, void
   if (e->p.cap_nodes < e->p.g.N || e->p.cap_edges < e->p.g.E)
     return fail(RC_ERR_CAPACITY, "seed plans split the whole graph: create the engine with cap_nodes = %d, cap_edges = %d",
                 e->p.g.N, e->p.g.E);
-  if (e->p.cfg.n_districts > 254) return fail(RC_ERR_INVALID_ARG, "seed plans need n_districts <= 254");
+  if (e->p.cfg.n_districts >= RC_SEED_REMAINING)
+    return fail(RC_ERR_INVALID_ARG, "seed plans need n_districts <= %d", RC_SEED_REMAINING - 1);
   if (e->p.g.R > 0) return fail(RC_ERR_INVALID_ARG, "seed plans are drawn without region surcharges");
   if (rp && (rp->n_steps != e->p.cfg.n_districts - 1 || !rp->steps || !rp->weight_rank ||
              rp->chain < 0 || rp->chain >= e->p.cfg.n_chains))

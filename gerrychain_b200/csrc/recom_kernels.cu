@@ -28,7 +28,7 @@ struct Chain {
   Smem s;
   int chain;            // local chain index
   uint32_t gchain;      // global chain id (RNG subsequence)
-  uint8_t* assign;
+  rc_label_t* assign;
   uint32_t* mask;
   int64_t* tally;
   int32_t* nodes;
@@ -53,6 +53,36 @@ __device__ __forceinline__ uint32_t match4(uint32_t x, uint32_t a4, uint32_t b4)
 
 __device__ __forceinline__ uint32_t match16(const uint4 q, uint32_t a4, uint32_t b4) {
   return match4(q.x, a4, b4) | match4(q.y, a4, b4) << 4 | match4(q.z, a4, b4) << 8 | match4(q.w, a4, b4) << 12;
+}
+
+// the 16-bit-label build: 2 labels per word -> 2 bits, 8 labels per 128-bit load -> 8 bits
+__device__ __forceinline__ uint32_t match2(uint32_t x, uint32_t a2, uint32_t b2) {
+  const uint32_t r = __vcmpeq2(x, a2) | __vcmpeq2(x, b2);
+  return (r & 1u) | ((r >> 15) & 2u);
+}
+
+__device__ __forceinline__ uint32_t match8(const uint4 q, uint32_t a2, uint32_t b2) {
+  return match2(q.x, a2, b2) | match2(q.y, a2, b2) << 2 | match2(q.z, a2, b2) << 4 | match2(q.w, a2, b2) << 6;
+}
+
+// membership bits of nodes 32 w .. 32 w + 31 of an assignment row (label == a or == b); bits past
+// N are garbage (the caller masks them).  128-bit loads; rows are padded to 16 bytes.
+__device__ __forceinline__ uint32_t row_match32(const rc_label_t* row, int w, int N, uint32_t apat, uint32_t bpat) {
+#if RC_LABEL_BITS == 8
+  const uint4* src = reinterpret_cast<const uint4*>(row + (size_t)w * 32);
+  uint32_t bits = match16(__ldcg(src), apat, bpat);
+  if (w * 32 + 16 < N) bits |= match16(__ldcg(src + 1), apat, bpat) << 16;
+  return bits;
+#else
+  const uint4* src = reinterpret_cast<const uint4*>(row + (size_t)w * 32);
+  uint4 q[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) q[j] = (w * 32 + 8 * j < N) ? __ldcg(src + j) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bits |= match8(q[j], apat, bpat) << (8 * j);
+  return bits;
+#endif
 }
 
 // ---- weight key of local edge j for tree `tree_no` (tree.py:78-89) ------------------------
@@ -194,7 +224,11 @@ __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
   const Smem& s = c.s;
   const int tid = threadIdx.x, T = blockDim.x;
   const int N = p.g.N, NW = (N + 31) >> 5;
+#if RC_LABEL_BITS == 8
   const uint32_t a4 = 0x01010101u * (uint32_t)st.a, b4 = 0x01010101u * (uint32_t)st.b;
+#else
+  const uint32_t a4 = 0x00010001u * (uint32_t)st.a, b4 = 0x00010001u * (uint32_t)st.b;
+#endif
   if (tid == 0) { s.misc[M_TOT] = 0; s.misc[M_CNT] = 0; }
   // local id -> global node table, built with the bitmap (a spanning-tree array that is
   // initialised after the gather serves as its home); in spill mode that array lives in
@@ -211,9 +245,7 @@ __device__ int gather_pair(Chain& c, Step& st, int* d_sub_out) {
       // memory - cp.async.bulk + mbarrier - was measured against these loads, scripts/dev/tma_bench.cu:
       // 1142 vs 740 cycles for a 10 KB row alone on the SM, 1576 vs 1697 with 3 CTAs per SM, i.e.
       // +-0.1 % of a step - not worth the staging buffer)
-      const uint4* src = reinterpret_cast<const uint4*>(c.assign + (size_t)w * 32);
-      bits = match16(__ldcg(src), a4, b4);
-      if (w * 32 + 16 < N) bits |= match16(__ldcg(src + 1), a4, b4) << 16;
+      bits = row_match32(c.assign, w, N, a4, b4);
       const int rem = N - w * 32;
       if (rem < 32) bits &= (1u << rem) - 1u;
       s.mbits[w] = bits;
@@ -1194,7 +1226,7 @@ __device__ bool commit_proposal(Chain& c, const Step& st, int cut_count, long lo
   if (tid == 0) s.misc[M_DELTA] = 0;
   for (int i = tid; i < st.n; i += T) {  // partition/assignment.py:76-86
     const bool nb = (s.newb[i >> 5] >> (i & 31)) & 1u, ob = (s.oldb[i >> 5] >> (i & 31)) & 1u;
-    if (nb != ob) c.assign[c.nodes[i]] = (uint8_t)(nb ? st.b : st.a);
+    if (nb != ob) c.assign[c.nodes[i]] = (rc_label_t)(nb ? st.b : st.a);
   }
   __syncthreads();
   int delta = 0;
@@ -2025,7 +2057,7 @@ __device__ ProposalResult propose_reversible(Chain& c, uint32_t prop_no, int32_t
   }
   for (int i = tid; i < n; i += T) {
     const bool nb = (s.newb[i >> 5] >> (i & 31)) & 1u, ob = (s.oldb[i >> 5] >> (i & 31)) & 1u;
-    if (nb != ob) c.assign[c.nodes[i]] = (uint8_t)(nb ? st.b : st.a);
+    if (nb != ob) c.assign[c.nodes[i]] = (rc_label_t)(nb ? st.b : st.a);
   }
   for (int j = tid; j < st.m; j += T) {
     const uint32_t uv = s.euv[j];
@@ -2543,14 +2575,14 @@ __global__ void __launch_bounds__(512, 2) seed_kernel(const Params p) {
           part_pop = take_below ? pop_below : st.tot - pop_below;
           for (int i = tid; i < n; i += T) {
             const bool below = child_side(i) != root_cs;
-            if (below == take_below) c.assign[c.nodes[i]] = (uint8_t)part;
+            if (below == take_below) c.assign[c.nodes[i]] = (rc_label_t)part;
           }
           if (tid == 0) c.tally[part] = part_pop;
           if (!(lb_pop <= (double)part_pop && (double)part_pop <= ub_pop)) status = RC_ERR_BALANCE;
           debt = __dadd_rn(debt, __dsub_rn((double)part_pop, pt));
         } else {  // root side -> parts[-2], the rest -> parts[-1] (tree.py:1054-1075)
           for (int i = tid; i < n; i += T)
-            c.assign[c.nodes[i]] = (uint8_t)((child_side(i) != root_cs) ? k - 1 : k - 2);
+            c.assign[c.nodes[i]] = (rc_label_t)((child_side(i) != root_cs) ? k - 1 : k - 2);
           const long long p_hi = pop_below, p_lo = (long long)st.tot - pop_below;
           if (tid == 0) { c.tally[k - 1] = p_hi; c.tally[k - 2] = p_lo; }
           if (!(lb_pop <= (double)p_hi && (double)p_hi <= ub_pop && lb_pop <= (double)p_lo && (double)p_lo <= ub_pop))
@@ -2576,7 +2608,7 @@ __global__ void __launch_bounds__(512, 2) seed_kernel(const Params p) {
 __global__ void init_state_kernel(const Params p) {
   __shared__ int cnt;
   const int chain = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
-  const uint8_t* assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
+  const rc_label_t* assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
   uint32_t* mask = p.st.d_cut_mask + (size_t)chain * p.st.mask_stride;
   int64_t* tally = p.st.d_tally + (size_t)chain * p.cfg.n_districts;
   const int k = p.cfg.n_districts;
@@ -2625,10 +2657,11 @@ __global__ void init_state_kernel(const Params p) {
 // Election updater): out[chain][d] = sum of column[v] over nodes v of district d.  One CTA
 // per chain, shared-memory bins, 128-bit loads of the assignment row.
 __global__ void tally_column_kernel(const Params p, const int32_t* __restrict__ column, long long* __restrict__ out) {
-  __shared__ unsigned long long bins[256];
   const int chain = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
   const int k = p.cfg.n_districts, N = p.g.N;
-  const uint8_t* assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
+  const rc_label_t* assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
+#if RC_LABEL_BITS == 8
+  __shared__ unsigned long long bins[256];
   for (int d = tid; d < 256; d += T) bins[d] = 0;
   __syncthreads();
   for (int v0 = tid * 16; v0 < N; v0 += T * 16) {
@@ -2645,6 +2678,24 @@ __global__ void tally_column_kernel(const Params p, const int32_t* __restrict__ 
   }
   __syncthreads();
   for (int d = tid; d < k; d += T) out[(size_t)chain * k + d] = (long long)bins[d];
+#else
+  // up to 32 767 districts: the bins are the chain's output row itself (L2 atomics)
+  unsigned long long* bins = reinterpret_cast<unsigned long long*>(out + (size_t)chain * k);
+  for (int d = tid; d < k; d += T) bins[d] = 0;
+  __syncthreads();
+  for (int v0 = tid * 8; v0 < N; v0 += T * 8) {
+    const uint4 q = __ldcg(reinterpret_cast<const uint4*>(assign + v0));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int v = v0 + i;
+      if (v < N) {
+        const uint32_t d = (w[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+        if (d < (uint32_t)k) atomicAdd(&bins[d], (unsigned long long)(long long)__ldg(column + v));
+      }
+    }
+  }
+#endif
 }
 
 // Ensemble histograms (one thread per chain).

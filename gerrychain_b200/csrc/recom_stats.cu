@@ -29,7 +29,7 @@ __global__ void region_splits_kernel(const Params p, const int32_t* __restrict__
   uint32_t* seen = sm + R;        // [R][kw] districts present in the region
   __shared__ int acc[3];
   for (int chain = blockIdx.x; chain < p.cfg.n_chains; chain += gridDim.x) {
-    const uint8_t* assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
+    const rc_label_t* assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
     const uint32_t* mask = p.st.d_cut_mask + (size_t)chain * p.st.mask_stride;
     for (int i = tid; i < R * (1 + kw); i += T) sm[i] = 0;
     if (tid < 3) acc[tid] = 0;
@@ -78,7 +78,9 @@ __global__ void contiguity_kernel(const Params p, int* __restrict__ gscratch, in
   const int tid = threadIdx.x, T = blockDim.x;
   const int N = p.g.N, E = p.g.E, k = p.cfg.n_districts;
   int* parent = use_smem ? reinterpret_cast<int*>(sm) : gscratch + (size_t)blockIdx.x * N;
+#if RC_LABEL_BITS == 8
   __shared__ int pieces[256];
+#endif
   auto find = [&](int x) {
     volatile int* par = parent;
     int px = par[x];
@@ -91,9 +93,14 @@ __global__ void contiguity_kernel(const Params p, int* __restrict__ gscratch, in
     return x;
   };
   for (int chain = blockIdx.x; chain < p.cfg.n_chains; chain += gridDim.x) {
-    const uint8_t* assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
+    const rc_label_t* assign = p.st.d_assignment + (size_t)chain * p.st.assign_stride;
     for (int v = tid; v < N; v += T) parent[v] = v;
+#if RC_LABEL_BITS == 8
     for (int d = tid; d < 256; d += T) pieces[d] = 0;
+#else
+    int* pieces = out + (size_t)chain * k;  // up to 32 767 districts: count in the output row
+    for (int d = tid; d < k; d += T) pieces[d] = 0;
+#endif
     __syncthreads();
     for (int e = tid; e < E; e += T) {
       const int2 uv = __ldg(reinterpret_cast<const int2*>(p.g.edge_uv) + e);
@@ -109,9 +116,11 @@ __global__ void contiguity_kernel(const Params p, int* __restrict__ gscratch, in
     }
     __syncthreads();
     for (int v = tid; v < N; v += T)
-      if (((volatile int*)parent)[v] == v) atomicAdd(&pieces[assign[v]], 1);
+      if (((volatile int*)parent)[v] == v && (RC_LABEL_BITS == 8 || (int)assign[v] < k)) atomicAdd(&pieces[assign[v]], 1);
     __syncthreads();
+#if RC_LABEL_BITS == 8
     for (int d = tid; d < k; d += T) out[(size_t)chain * k + d] = pieces[d];
+#endif
     __syncthreads();
   }
 }

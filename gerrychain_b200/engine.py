@@ -32,13 +32,20 @@ def _check(lib, rc: int):
 class Engine:
     """n_chains independent ReCom chains resident on one GPU."""
 
-    def __init__(self, csr: GraphCSR, cfg: EngineConfig, assignment, device=None):
+    def __init__(self, csr: GraphCSR, cfg: EngineConfig, assignment, device=None, label_bits: Optional[int] = None):
+        """``label_bits``: 8 or 16, which build of the library holds the plans (default: 8 up
+        to 255 districts, 16 beyond; 16 may be forced for a small plan - the results are the same)."""
         import torch
 
         if not torch.cuda.is_available():
             raise RuntimeError("gerrychain_b200.Engine needs a CUDA device (no CPU fallback)")
-        self.lib = _abi.load()
+        # plans with more than 255 districts run on the 16-bit-label build of the library
+        self.label_bits = max(_abi.label_bits_for(cfg.n_districts), int(label_bits or 8))
+        self.label_dtype = _abi.label_dtype(self.label_bits)
+        self.lib = _abi.load(self.label_bits)
         self.torch = torch
+        # (labels <= 32767, so the signed torch type holds them; numpy views are unsigned)
+        self.torch_label = torch.uint8 if self.label_bits == 8 else torch.int16
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.csr = csr
         self.cfg = cfg
@@ -52,9 +59,7 @@ class Engine:
             raise ValueError("assignment must be [N] or [n_chains, N]")
         if a.min() < 0 or a.max() >= k:
             raise ValueError("assignment entries must be district indices in [0, k)")
-        host = np.zeros((n, self.assign_stride), dtype=np.uint8)
-        host[:, : csr.n_nodes] = a
-        self.assignment = torch.from_numpy(host).to(dev)
+        self.assignment = self._labels_to_torch(a).to(dev)
         self.tally = torch.zeros((n, k), dtype=torch.int64, device=dev)
         self.cut_mask = torch.zeros((n, self.mask_stride), dtype=torch.int32, device=dev)
         self.cut_count = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -85,6 +90,16 @@ class Engine:
         _check(self.lib, self.lib.rc_engine_bind_state(self._handle, C.byref(st)))
         self.init_state()
 
+    def _labels_to_torch(self, a):
+        """[n_chains, N] district indices -> CPU tensor [n_chains, assign_stride] of the label type."""
+        host = np.zeros((self.cfg.n_chains, self.assign_stride), dtype=self.label_dtype)
+        host[:, : self.csr.n_nodes] = a
+        return self.torch.from_numpy(host if self.label_bits == 8 else host.view(np.int16))
+
+    def _labels_to_numpy(self, t):
+        a = t.cpu().numpy()
+        return a if self.label_bits == 8 else a.view(np.uint16)
+
     # -- lifecycle ---------------------------------------------------------------------
     def close(self):
         if getattr(self, "_handle", None) and self._handle.value:
@@ -107,12 +122,10 @@ class Engine:
 
     def set_assignment(self, assignment):
         """Host -> device copy of new plans (one per chain or one for all) + re-init."""
-        a = np.asarray(assignment, dtype=np.uint8)
+        a = np.asarray(assignment, dtype=self.label_dtype)
         if a.ndim == 1:
             a = np.broadcast_to(a, (self.cfg.n_chains, self.csr.n_nodes))
-        host = np.zeros((self.cfg.n_chains, self.assign_stride), dtype=np.uint8)
-        host[:, : self.csr.n_nodes] = a
-        self.assignment.copy_(self.torch.from_numpy(host), non_blocking=False)
+        self.assignment.copy_(self._labels_to_torch(a), non_blocking=False)
         self.init_state()
 
     def run(self, n_steps: int):
@@ -125,7 +138,7 @@ class Engine:
         t = self.torch
         n, k = self.cfg.n_chains, self.cfg.n_districts
         # rows padded to the device pitch: each direction is then one contiguous copy
-        return (t.zeros((n, self.assign_stride), dtype=t.uint8).pin_memory()[:, : self.csr.n_nodes],
+        return (t.zeros((n, self.assign_stride), dtype=self.torch_label).pin_memory()[:, : self.csr.n_nodes],
                 t.empty((n, k), dtype=t.int64).pin_memory(),
                 t.empty(n, dtype=t.int32).pin_memory(),
                 t.empty(n, dtype=t.int32).pin_memory())
@@ -141,11 +154,15 @@ class Engine:
             return x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data
 
         def pitch(x):
-            return int(x.stride(0)) if hasattr(x, "data_ptr") else int(x.strides[0])
+            # row pitch in labels (include/recom_b200.h: h_stride)
+            return int(x.stride(0)) if hasattr(x, "data_ptr") else int(x.strides[0]) // x.itemsize
 
         n, N = self.cfg.n_chains, self.csr.n_nodes
         if tuple(h_assignment.shape) != (n, N):
-            raise ValueError("h_assignment must be [n_chains, N] uint8")
+            raise ValueError("h_assignment must be [n_chains, N] district labels")
+        isz = h_assignment.element_size() if hasattr(h_assignment, "data_ptr") else h_assignment.itemsize
+        if isz * 8 != self.label_bits:
+            raise ValueError(f"h_assignment must hold {self.label_bits}-bit labels")
         if h_out is not None and (tuple(h_out.shape) != (n, N) or pitch(h_out) != pitch(h_assignment)):
             raise ValueError("h_out must have the shape and row pitch of h_assignment")
         _check(self.lib, self.lib.rc_engine_step_host(
@@ -248,7 +265,7 @@ class Engine:
             keep.append(x)
             return x.data_ptr()
 
-        trace = t.zeros((n_steps, self.csr.n_nodes), dtype=t.uint8, device=dev)
+        trace = t.zeros((n_steps, self.csr.n_nodes), dtype=self.torch_label, device=dev)
         info = t.zeros((n_steps, 4), dtype=t.int32, device=dev)
         rp = _abi.RcReplay()
         rp.n_steps = n_steps
@@ -263,14 +280,14 @@ class Engine:
         rp.info_trace = info.data_ptr()
         _check(self.lib, self.lib.rc_engine_replay(self._handle, C.byref(rp), self._stream()))
         t.cuda.synchronize(dev)
-        return trace.cpu().numpy(), info.cpu().numpy()
+        return self._labels_to_numpy(trace), info.cpu().numpy()
 
     # -- read-backs --------------------------------------------------------------------
     def synchronize(self):
         self.torch.cuda.synchronize(self.device)
 
     def assignments(self) -> np.ndarray:
-        return self.assignment[:, : self.csr.n_nodes].cpu().numpy()
+        return self._labels_to_numpy(self.assignment[:, : self.csr.n_nodes])
 
     def check_status(self):
         """Raise the reference's exception for the first chain that stopped."""

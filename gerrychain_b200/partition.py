@@ -147,12 +147,13 @@ class Partition:
         if set(mapping) != set(ctx.labels):
             raise KeyError("The graph's node labels do not match the Assignment's keys")
         labels = sorted(set(mapping.values()))  # tree_proposals.py:113 relies on this order
-        if len(labels) > 255:
-            raise ValueError("the device engine stores district ids in uint8: at most 255 districts")
+        if len(labels) > 32767:
+            raise ValueError("the device engine stores district ids in 16 bits: at most 32767 districts")
         self._district_labels = labels
         self._rank = {p: i for i, p in enumerate(labels)}
-        self._vec = np.fromiter((self._rank[mapping[lab]] for lab in ctx.labels), dtype=np.uint8,
-                                count=ctx.n_nodes)
+        # one byte per node up to 255 districts, two beyond (the engine's two label widths)
+        self._vec = np.fromiter((self._rank[mapping[lab]] for lab in ctx.labels),
+                                dtype=np.uint8 if len(labels) <= 255 else np.uint16, count=ctx.n_nodes)
         if updaters is None:
             updaters = dict()
         self.updaters = dict(self.default_updaters) if use_default_updaters else {}

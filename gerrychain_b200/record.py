@@ -118,6 +118,7 @@ class Record:
                     header = json.dumps({
                         "n_nodes": int(vec.shape[0]),
                         "district_labels": [_jsonable(x) for x in state._district_labels],
+                        "label_bytes": int(vec.dtype.itemsize),
                         "format": "initial plan + per-step (gap, district) varints, zlib",
                     }).encode()
                     fh.write(MAGIC + struct.pack("<I", len(header)) + header)
@@ -165,7 +166,8 @@ class Replay:
                 raise ValueError(f"recording has {n} nodes, the graph has {ctx.n_nodes}")
             labels = [tuple(x) if isinstance(x, list) else x for x in header["district_labels"]]
             rd = _Reader(fh)
-            vec = np.frombuffer(rd.take(n), dtype=np.uint8).copy()
+            lb = int(header.get("label_bytes", 1))  # 2 for plans with more than 255 districts
+            vec = np.frombuffer(rd.take(n * lb), dtype=np.uint8 if lb == 1 else np.dtype("<u2")).copy()
             first = self.partition_class(self.graph, {lab: labels[d] for lab, d in zip(ctx.labels, vec.tolist())},
                                          self.updaters, use_default_updaters=self.use_default_updaters)
             # the recorded ranks index the recorded label list; keep exactly that order

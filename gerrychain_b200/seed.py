@@ -19,8 +19,8 @@ from .config import EngineConfig
 def random_plans(graph, n_parts: int, epsilon: float, pop_col: str, n_plans: int = 1,
                  pop_target: Optional[float] = None, seed: Optional[int] = None,
                  max_attempts: Optional[int] = 10000, device=None) -> np.ndarray:
-    """``n_plans`` independent random plans as a ``uint8 [n_plans, N]`` array of district
-    indices (node order of ``graph.nodes``); every district within ``epsilon`` of
+    """``n_plans`` independent random plans as a ``uint8 [n_plans, N]`` array (``uint16``
+    beyond 255 districts) of district indices (node order of ``graph.nodes``); every district within ``epsilon`` of
     ``pop_target`` (default: total / n_parts) and contiguous."""
     from .engine import Engine
     from .proposals import raise_for_status

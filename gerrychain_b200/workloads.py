@@ -67,6 +67,22 @@ def delaunay_workload(n_nodes: int, k: int, eps: float, n_chains: int, counties:
     return csr, vec.astype(np.uint8), cfg
 
 
+def many_districts(m: int = 60, n: int = 60, bh: int = 3, bw: int = 4, eps: float = 0.1, n_chains: int = 1, **kw):
+    """An m x n grid cut into bh x bw blocks: (m / bh) * (n / bw) small districts (300 by
+    default) - the shape of a plan with more than 255 districts (16-bit district labels)."""
+    if m % bh or n % bw:
+        raise ValueError("the blocks must tile the grid")
+    g = syn.grid_graph(m, n)
+    csr = csr_from_networkx(g, "population")
+    plan = {(i, j): (i // bh) * (n // bw) + j // bw for i in range(m) for j in range(n)}
+    vec, _ = assignment_vector(csr, plan)
+    k = (m // bh) * (n // bw)
+    ideal, lo, hi = _bounds(csr, k, eps)
+    cfg = EngineConfig(n_districts=k, n_chains=n_chains, pop_target=ideal, epsilon=eps,
+                       pop_lower=lo, pop_upper=hi, **kw)
+    return csr, vec.astype(np.uint8 if k <= 255 else np.uint16), cfg
+
+
 def config1(n_chains=1, **kw):
     """Grid 20x20, 4 districts, eps 0.05 (BASELINE.json configs[0])."""
     return grid_workload(20, 20, 4, 0.05, n_chains, **kw)

@@ -31,6 +31,25 @@ extern "C" {
 
 #define RC_ABI_VERSION 1
 
+/* ---- district labels ----------------------------------------------------------------
+ * One label per node in the assignment rows.  The default build (librecom_b200.so) keeps
+ * them in one byte (plans with up to 255 districts: a 10 KB row for a 10k-node graph);
+ * the same sources compiled with -DRC_LABEL_BITS=16 (librecom_b200_l16.so, identical entry
+ * points) carry 16-bit labels for plans with up to 32 767 districts.  rc_label_bits() says
+ * which build is loaded; the host side (gerrychain_b200/_abi.py) picks the library by k. */
+#ifndef RC_LABEL_BITS
+#define RC_LABEL_BITS 8
+#endif
+#if RC_LABEL_BITS == 16
+typedef uint16_t rc_label_t;
+#define RC_MAX_DISTRICTS 32767
+#elif RC_LABEL_BITS == 8
+typedef uint8_t rc_label_t;
+#define RC_MAX_DISTRICTS 255
+#else
+#error "RC_LABEL_BITS must be 8 or 16"
+#endif
+
 /* ---- status codes (per call and per chain) -------------------------------------- */
 enum {
   RC_OK = 0,
@@ -50,7 +69,7 @@ enum {
 
 /* seed plans (tree.py:971-1085): label of nodes not yet assigned, and the proposal-number
  * space of the seed splits in the random-draw schedule */
-#define RC_SEED_REMAINING 255
+#define RC_SEED_REMAINING ((1 << RC_LABEL_BITS) - 1)
 #define RC_SEED_PROPOSAL 0x40000000u
 
 /* per-chain flag bits (RcState.d_flags), sticky */
@@ -119,7 +138,7 @@ typedef struct RcConfig {
 
 /* ---- chain state, resident in HBM, owned by the caller --------------------------- */
 typedef struct RcState {
-  uint8_t* d_assignment;   /* [n_chains][assign_stride] district index per node
+  rc_label_t* d_assignment; /* [n_chains][assign_stride] district index per node
                               (partition/assignment.py:9 Assignment.mapping)          */
   int64_t* d_tally;        /* [n_chains][k]  updaters/tally.py:69 Tally               */
   uint32_t* d_cut_mask;    /* [n_chains][mask_stride] bit e set <=> edge e is cut
@@ -130,7 +149,7 @@ typedef struct RcState {
   int32_t* d_status;       /* [n_chains] RC_OK or the RC_ERR_* that stopped the chain */
   uint32_t* d_flags;       /* [n_chains] RC_FLAG_*                                    */
   int64_t* d_counters;     /* [n_chains][RC_N_COUNTERS] see below                     */
-  int64_t assign_stride;   /* bytes between chains in d_assignment (multiple of 16)   */
+  int64_t assign_stride;   /* labels between chains in d_assignment (rows 16-byte aligned) */
   int64_t mask_stride;     /* uint32 words between chains in d_cut_mask (multiple of 4) */
   int32_t* d_last_pair;    /* [n_chains][2] optional (may be NULL): the district pair (a < b)
                               merged by the chain's last committed proposal, i.e. the keys of
@@ -170,7 +189,7 @@ typedef struct RcReplay {
   const int32_t* wilson_root;    /* Wilson: [n_trees_total] root (tree.py:112)          */
   const int64_t* stack_ptr;      /* Wilson: [n_trees_total][N+1] into stack_val         */
   const int32_t* stack_val;      /* Wilson: chosen neighbour node index per draw        */
-  uint8_t* assign_trace;         /* out, optional: [n_steps][N] assignment after step   */
+  rc_label_t* assign_trace;      /* out, optional: [n_steps][N] assignment after step   */
   int32_t* info_trace;           /* out, optional: [n_steps][4] {trees used, #balanced
                                     cuts of the last tree, cut count after, status}    */
 } RcReplay;
@@ -180,6 +199,7 @@ typedef struct RcEngine RcEngine;
 
 const char* rc_last_error(void);
 int rc_abi_version(void);
+int rc_label_bits(void); /* 8 or 16: width of rc_label_t in the loaded build */
 
 /* Device-side sizes the caller must honour when allocating RcState buffers. */
 int rc_state_strides(const RcGraph* g, const RcConfig* c, int64_t* assign_stride,
@@ -205,8 +225,8 @@ int rc_engine_init_state(RcEngine* e, void* stream);
 int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream);
 
 /* The same call with HOST buffers: the whole reference-facing round trip of a batch of
- * chains.  Copies h_assignment ([n_chains][h_stride] bytes, district index per node, only
- * the first N bytes of a row are read) to the device, recomputes Tally / cut_edges
+ * chains.  Copies h_assignment ([n_chains][h_stride] labels, district index per node, only
+ * the first N labels of a row are read) to the device, recomputes Tally / cut_edges
  * (rc_engine_init_state), advances every chain by n_steps accepted steps (rc_engine_run)
  * and copies back: the assignment (same layout, may alias h_assignment), Tally
  * [n_chains][k] int64, len(cut_edges) [n_chains] int32 and the per-chain status
@@ -215,8 +235,8 @@ int rc_engine_run(RcEngine* e, int64_t n_steps, void* stream);
  * to the device pitch (rc_state_strides) each direction is one contiguous copy.  Synchronises
  * `stream` before returning.  This is what one MarkovChain batch costs a caller who keeps
  * its partitions on the host, as the reference does (chain.py:166-196). */
-int rc_engine_step_host(RcEngine* e, const uint8_t* h_assignment, int64_t h_stride,
-                        int64_t n_steps, uint8_t* h_assignment_out, int64_t* h_tally_out,
+int rc_engine_step_host(RcEngine* e, const rc_label_t* h_assignment, int64_t h_stride,
+                        int64_t n_steps, rc_label_t* h_assignment_out, int64_t* h_tally_out,
                         int32_t* h_cut_count_out, int32_t* h_status_out, void* stream);
 
 /* Random seed plans for every chain: recursive_tree_part (tree.py:971-1085) with

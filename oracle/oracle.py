@@ -16,20 +16,22 @@ from gerrychain_b200 import _abi
 from gerrychain_b200.config import EngineConfig, strides
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-_lib = None
+_libs = {}  # label width (8 / 16) -> CDLL
 
 
 def build():
     subprocess.run(["make", "-s", "-C", HERE], check=True)
 
 
-def load():
-    global _lib
+def load(label_bits=8):
+    """The oracle built with ``label_bits``-wide district labels (as the engine: 8 up to 255
+    districts, 16 beyond)."""
+    _lib = _libs.get(label_bits)
     if _lib is None:
-        path = os.path.join(HERE, "librecom_oracle.so")
+        path = os.path.join(HERE, "librecom_oracle.so" if label_bits == 8 else "librecom_oracle_l16.so")
         if not os.path.exists(path):
             build()
-        _lib = C.CDLL(path)
+        _lib = _libs[label_bits] = C.CDLL(path)
         _lib.rco_work_create.restype = C.c_void_p
         _lib.rco_work_create.argtypes = [C.POINTER(_abi.RcGraph)]
         _lib.rco_work_destroy.argtypes = [C.c_void_p]
@@ -83,32 +85,35 @@ def mst_of_graph(csr, weights):
 
 def region_splits(csr, k, assignment, region_ids, n_regions=None):
     """(regions with an inner cut edge, regions over > 1 district, pieces) of one plan."""
-    a = np.ascontiguousarray(assignment, dtype=np.uint8)
+    bits = _abi.label_bits_for(k)
+    a = np.ascontiguousarray(assignment, dtype=_abi.label_dtype(bits))
     r = np.ascontiguousarray(region_ids, dtype=np.int32)
     if n_regions is None:
         n_regions = int(r.max()) + 1
     out = np.zeros(3, dtype=np.int32)
     g = _abi.graph_struct(csr)
-    load().rco_region_splits(C.byref(g), k, a.ctypes.data, r.ctypes.data, n_regions, out.ctypes.data)
+    load(bits).rco_region_splits(C.byref(g), k, a.ctypes.data, r.ctypes.data, n_regions, out.ctypes.data)
     return tuple(int(x) for x in out)
 
 
 def contiguity(csr, k, assignment):
     """int32 [k]: connected pieces of every district of one plan."""
-    a = np.ascontiguousarray(assignment, dtype=np.uint8)
+    bits = _abi.label_bits_for(k)
+    a = np.ascontiguousarray(assignment, dtype=_abi.label_dtype(bits))
     out = np.zeros(k, dtype=np.int32)
     g = _abi.graph_struct(csr)
-    load().rco_contiguity(C.byref(g), k, a.ctypes.data, out.ctypes.data)
+    load(bits).rco_contiguity(C.byref(g), k, a.ctypes.data, out.ctypes.data)
     return out
 
 
 def seed_plans(csr, cfg: EngineConfig, n_plans=1, max_attempts=10000, rec=None):
     """recursive_tree_part on the CPU: (status [n], plans [n][N] uint8, tally [n][k]).
     rec: tests/_golden.ReplayArrays of recorded reference randomness (one plan)."""
-    lib = load()
+    bits = _abi.label_bits_for(cfg.n_districts)
+    lib = load(bits)
     g = _abi.graph_struct(csr)
     c = cfg.to_struct()
-    plans = np.zeros((n_plans, csr.n_nodes), dtype=np.uint8)
+    plans = np.zeros((n_plans, csr.n_nodes), dtype=_abi.label_dtype(bits))
     tally = np.zeros((n_plans, cfg.n_districts), dtype=np.int64)
     status = np.zeros(n_plans, dtype=np.int32)
     counters = np.zeros((n_plans, _abi.RC_N_COUNTERS), dtype=np.int64)
@@ -132,18 +137,20 @@ def seed_plans(csr, cfg: EngineConfig, n_plans=1, max_attempts=10000, rec=None):
 class OracleChains:
     """Host-resident twin of the device engine's state, advanced by the C oracle."""
 
-    def __init__(self, csr, cfg: EngineConfig, assignment):
-        self.lib = load()
+    def __init__(self, csr, cfg: EngineConfig, assignment, label_bits=None):
+        self.label_bits = label_bits or _abi.label_bits_for(cfg.n_districts)
+        self.label_dtype = _abi.label_dtype(self.label_bits)
+        self.lib = load(self.label_bits)
         self.csr = csr
         self.cfg = cfg
         self.cstruct = cfg.to_struct()
         self.gstruct = _abi.graph_struct(csr)
         n, k = cfg.n_chains, cfg.n_districts
         self.assign_stride, self.mask_stride = strides(csr.n_nodes, csr.n_edges)
-        a = np.asarray(assignment, dtype=np.uint8)
+        a = np.asarray(assignment, dtype=self.label_dtype)
         if a.ndim == 1:
             a = np.broadcast_to(a, (n, csr.n_nodes))
-        self.assignment = np.zeros((n, self.assign_stride), dtype=np.uint8)
+        self.assignment = np.zeros((n, self.assign_stride), dtype=self.label_dtype)
         self.assignment[:, : csr.n_nodes] = a
         self.tally = np.zeros((n, k), dtype=np.int64)
         self.cut_mask = np.zeros((n, self.mask_stride), dtype=np.uint32)
@@ -183,7 +190,7 @@ class OracleChains:
     def replay(self, rec, chain=0):
         """rec: tests/_golden.ReplayArrays (host numpy).  Returns (assign_trace, info)."""
         n_steps = len(rec.steps)
-        trace = np.zeros((n_steps, self.csr.n_nodes), dtype=np.uint8)
+        trace = np.zeros((n_steps, self.csr.n_nodes), dtype=self.label_dtype)
         info = np.zeros((n_steps, 4), dtype=np.int32)
         rp = _abi.RcReplay()
         rp.n_steps = n_steps

@@ -118,7 +118,7 @@ void rco_work_destroy(RcoWork* w) {
 
 /* ------------------------------------------------------------------------------------ */
 /* updaters/tally.py:118-141 + updaters/cut_edges.py:110-114: first-time scans.         */
-int rco_init_state(const RcGraph* g, const RcConfig* c, const uint8_t* assign,
+int rco_init_state(const RcGraph* g, const RcConfig* c, const rc_label_t* assign,
                    int64_t* tally, uint32_t* mask, int32_t* cut_count) {
   int k = c->n_districts;
   for (int d = 0; d < k; ++d) tally[d] = 0;
@@ -155,7 +155,7 @@ static int32_t kth_cut_edge(const uint32_t* mask, int words, uint32_t kth) {
 }
 
 /* proposals/tree_proposals.py:118-120 + tree.py:670: induced subgraph of the pair.      */
-static void rco_gather(const RcGraph* g, RcoWork* w, const uint8_t* assign, int a, int b) {
+static void rco_gather(const RcGraph* g, RcoWork* w, const rc_label_t* assign, int a, int b) {
   int n = 0;
   int64_t tot = 0;
   for (int v = 0; v < g->n_nodes; ++v)
@@ -533,7 +533,7 @@ static int rco_bipartition(const RcGraph* g, const RcConfig* c, RcoWork* w, uint
 /* One call of recom (proposals/tree_proposals.py:36-146) followed by the chain's validity
  * check; returns RC_OK with *accepted = 1 when the proposal was committed. */
 static int rco_propose(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t chain,
-                       uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
+                       rc_label_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
                        uint32_t prop_no, int64_t* counters, uint32_t* flags,
                        const RcReplay* rp, const RcReplayStep* rs, int32_t* info,
                        int* accepted, int32_t* last_pair) {
@@ -556,7 +556,8 @@ static int rco_propose(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t
     }
     a = assign[g->edge_uv[2 * e]]; b = assign[g->edge_uv[2 * e + 1]];
     if (a > b) { int t = a; a = b; b = t; }               /* tree_proposals.py:113 */
-    if (w->bad_pairs[(a * 256 + b) >> 6] >> ((a * 256 + b) & 63) & 1) continue;
+    /* (256 x 256 bits: the engine accepts allow_pair_reselection up to 256 districts) */
+    if (c->allow_pair_reselection && (w->bad_pairs[(a * 256 + b) >> 6] >> ((a * 256 + b) & 63) & 1)) continue;
     rco_gather(g, w, assign, a, b);
     counters[RC_CTR_NODES] += w->n;
     for (int i = 0; i < w->n; ++i)
@@ -595,7 +596,7 @@ static int rco_propose(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t
     }
   }
   if (valid) {
-    for (int i = 0; i < w->n; ++i) assign[w->nodes[i]] = (uint8_t)(w->side[i] ? b : a);
+    for (int i = 0; i < w->n; ++i) assign[w->nodes[i]] = (rc_label_t)(w->side[i] ? b : a);
     tally[a] = pop_a; tally[b] = pop_b;                   /* updaters/tally.py:162-165 */
     int delta = 0;
     for (int j = 0; j < w->m; ++j) {                      /* updaters/cut_edges.py:118-120 */
@@ -617,7 +618,7 @@ static int rco_propose(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t
 /* proposals/tree_proposals.py:149-267 reversible_recom; *accepted = 1 also for self-loops
  * (the chain counts every call as a step), 0 only when the proposal fails the Bounds. */
 static int rco_propose_reversible(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t chain,
-                                  uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
+                                  rc_label_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
                                   uint32_t prop_no, int64_t* counters, int* accepted, int32_t* last_pair) {
   int k = c->n_districts, M = c->rev_M > 0 ? c->rev_M : 1;
   *accepted = 1;
@@ -680,7 +681,7 @@ static int rco_propose_reversible(const RcGraph* g, const RcConfig* c, RcoWork* 
     double lo = (double)(pop_root < pop_other ? pop_root : pop_other), hi = (double)(pop_root < pop_other ? pop_other : pop_root);
     if (!(c->pop_lower <= lo && hi <= c->pop_upper)) { counters[RC_CTR_INVALID]++; *accepted = 0; rco_ungather(w); return RC_OK; }
   }
-  for (int i = 0; i < w->n; ++i) assign[w->nodes[i]] = (uint8_t)(w->side[i] ? lab_other : lab_root);
+  for (int i = 0; i < w->n; ++i) assign[w->nodes[i]] = (rc_label_t)(w->side[i] ? lab_other : lab_root);
   tally[lab_root] = pop_root; tally[lab_other] = pop_other;
   for (int j = 0; j < w->m; ++j) {
     int e = w->eid[j];
@@ -696,7 +697,7 @@ static int rco_propose_reversible(const RcGraph* g, const RcConfig* c, RcoWork* 
 
 /* chain.py:185-195: propose until a valid state, accept (always), count the step. */
 int rco_step(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t global_chain,
-             uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
+             rc_label_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
              uint32_t* proposal_no, int64_t* counters, uint32_t* flags, int32_t* last_pair) {
   int streak_cap = c->max_invalid_streak > 0 ? c->max_invalid_streak : 1000;
   for (int streak = 0; streak < streak_cap; ++streak) {
@@ -714,7 +715,7 @@ int rco_step(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t global_ch
 }
 
 int rco_replay(const RcGraph* g, const RcConfig* c, RcoWork* w, const RcReplay* rp,
-               uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
+               rc_label_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
                int64_t* counters, uint32_t* flags) {
   for (int s = 0; s < rp->n_steps; ++s) {
     int accepted = 0;
@@ -738,7 +739,7 @@ int rco_replay(const RcGraph* g, const RcConfig* c, RcoWork* w, const RcReplay* 
  * the subtree if THAT fits.  rp (optional): recorded reference randomness, one
  * RcReplayStep per split (pair_edge unused). */
 int rco_seed_plan(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t chain,
-                  int32_t seed_max_attempts, uint8_t* assign, int64_t* tally,
+                  int32_t seed_max_attempts, rc_label_t* assign, int64_t* tally,
                   int64_t* counters, const RcReplay* rp) {
   const int k = c->n_districts;
   const double pt = c->pop_target, eps = c->epsilon;
@@ -811,7 +812,7 @@ int rco_seed_plan(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t chai
       mark_subtree(w, child);
       int64_t part_pop = take_below ? below : w->totpop - below;
       for (int i = 0; i < w->n; ++i)
-        if ((w->side[i] != 0) == (take_below != 0)) assign[w->nodes[i]] = (uint8_t)part;
+        if ((w->side[i] != 0) == (take_below != 0)) assign[w->nodes[i]] = (rc_label_t)part;
       tally[part] = part_pop;
       counters[RC_CTR_ATTEMPTS] += (int64_t)t + 1;
       if (!(lb_pop <= (double)part_pop && (double)part_pop <= ub_pop)) { rco_ungather(w); return RC_ERR_BALANCE; }
@@ -835,7 +836,7 @@ int rco_seed_plan(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t chai
     uint32_t flags = 0;
     int rc = rco_bipartition(g, &c2, w, chain, prop_no, rp, rs, counters, &flags, &child_pop, NULL);
     if (rc) { rco_ungather(w); return rc == -1 ? RC_ERR_MAX_ATTEMPTS : rc; }
-    for (int i = 0; i < w->n; ++i) assign[w->nodes[i]] = (uint8_t)(w->side[i] ? k - 1 : k - 2);
+    for (int i = 0; i < w->n; ++i) assign[w->nodes[i]] = (rc_label_t)(w->side[i] ? k - 1 : k - 2);
     tally[k - 1] = child_pop;
     tally[k - 2] = w->totpop - child_pop;
     rco_ungather(w);
@@ -882,7 +883,7 @@ int rco_balanced_cuts_of_tree(int32_t n, const int32_t* tree_uv, const int32_t* 
  * arbitrary connected graph -> tree edge ids (ascending). */
 int rco_mst_of_graph(const RcGraph* g, const double* weights, int32_t* out_eids) {
   RcoWork* w = rco_work_create(g);
-  uint8_t* assign = (uint8_t*)xcalloc((size_t)g->n_nodes, 1);
+  rc_label_t* assign = (rc_label_t*)xcalloc((size_t)g->n_nodes, sizeof(rc_label_t));
   rco_gather(g, w, assign, 0, 0);
   for (int j = 0; j < w->m; ++j) w->w[j] = weights[w->eid[j]];
   int rc = rco_kruskal(w);
@@ -897,7 +898,7 @@ int rco_mst_of_graph(const RcGraph* g, const double* weights, int32_t* out_eids)
 /* ---- multi-chain driver for the CPU baseline: one chain per task, T host threads ---- */
 typedef struct {
   const RcGraph* g; const RcConfig* c; int64_t n_steps;
-  uint8_t* assign; int64_t assign_stride; int64_t* tally; uint32_t* mask; int64_t mask_stride;
+  rc_label_t* assign; int64_t assign_stride; int64_t* tally; uint32_t* mask; int64_t mask_stride;
   int32_t* cut_count; uint32_t* proposal_no; int32_t* status; uint32_t* flags; int64_t* counters;
   int64_t* step_no; int32_t* last_pair;
   int n_chains; volatile int next; pthread_mutex_t mu;
@@ -974,7 +975,7 @@ void rco_philox(uint32_t k0, uint32_t k1, const uint32_t* ctr, uint32_t* out) {
  * both ends of a cut edge lie in it, count the marked regions -> out[0];
  * updaters/county_splits.py:82-99 compute_county_splits (no parent): the set of districts
  * seen in every county; counties with more than one -> out[1]; total set sizes -> out[2]. */
-int rco_region_splits(const RcGraph* g, int32_t k, const uint8_t* assign, const int32_t* region,
+int rco_region_splits(const RcGraph* g, int32_t k, const rc_label_t* assign, const int32_t* region,
                       int32_t n_regions, int32_t* out) {
   uint8_t* marked = (uint8_t*)xcalloc((size_t)n_regions, 1);
   uint8_t* seen = (uint8_t*)xcalloc((size_t)n_regions * (size_t)k, 1);
@@ -1001,7 +1002,7 @@ int rco_region_splits(const RcGraph* g, int32_t k, const uint8_t* assign, const 
 /* constraints/contiguity.py:169-181 contiguous -> is_connected_bfs per district
  * (contiguity.py:184-204, :244-270) and contiguous_components (:226-241): here one breadth-first sweep
  * that never crosses a cut edge counts the pieces of every district.  out[d] = pieces of d. */
-int rco_contiguity(const RcGraph* g, int32_t k, const uint8_t* assign, int32_t* out) {
+int rco_contiguity(const RcGraph* g, int32_t k, const rc_label_t* assign, int32_t* out) {
   const int n = g->n_nodes;
   uint8_t* visited = (uint8_t*)xcalloc((size_t)n, 1);
   int32_t* queue = (int32_t*)xcalloc((size_t)n, sizeof(int32_t));

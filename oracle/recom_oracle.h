@@ -18,16 +18,16 @@ typedef struct RcoWork RcoWork;
 RcoWork* rco_work_create(const RcGraph* g);
 void rco_work_destroy(RcoWork* w);
 
-int rco_init_state(const RcGraph* g, const RcConfig* c, const uint8_t* assign,
+int rco_init_state(const RcGraph* g, const RcConfig* c, const rc_label_t* assign,
                    int64_t* tally, uint32_t* mask, int32_t* cut_count);
 int rco_step(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t global_chain,
-             uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
+             rc_label_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
              uint32_t* proposal_no, int64_t* counters, uint32_t* flags, int32_t* last_pair);
 int rco_replay(const RcGraph* g, const RcConfig* c, RcoWork* w, const RcReplay* rp,
-               uint8_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
+               rc_label_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
                int64_t* counters, uint32_t* flags);
 int rco_seed_plan(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t chain,
-                  int32_t seed_max_attempts, uint8_t* assign, int64_t* tally,
+                  int32_t seed_max_attempts, rc_label_t* assign, int64_t* tally,
                   int64_t* counters, const RcReplay* rp);
 int rco_balanced_cuts_of_tree(int32_t n, const int32_t* tree_uv, const int32_t* pops,
                               double ideal, double eps, int32_t root, int32_t* out_uv);
@@ -35,9 +35,9 @@ int rco_mst_of_graph(const RcGraph* g, const double* weights, int32_t* out_eids)
 int rco_init_chains(const RcGraph* g, const RcConfig* c, const RcState* st);
 int rco_run_chains(const RcGraph* g, const RcConfig* c, int64_t n_steps, const RcState* st,
                    int n_threads);
-int rco_region_splits(const RcGraph* g, int32_t k, const uint8_t* assign, const int32_t* region,
+int rco_region_splits(const RcGraph* g, int32_t k, const rc_label_t* assign, const int32_t* region,
                       int32_t n_regions, int32_t* out);
-int rco_contiguity(const RcGraph* g, int32_t k, const uint8_t* assign, int32_t* out);
+int rco_contiguity(const RcGraph* g, int32_t k, const rc_label_t* assign, int32_t* out);
 void rco_philox(uint32_t k0, uint32_t k1, const uint32_t* ctr, uint32_t* out);
 
 #ifdef __cplusplus
