@@ -58,6 +58,10 @@ def method_config(method) -> Dict:
         raise NotImplementedError(
             f"recom(method={getattr(func, '__name__', func)!r}): the CUDA engine implements "
             "bipartition_tree (tree.py:581); other bipartition methods have no device path")
+    import random
+
+    if kw.get("choice", random.choice) is random.choice:  # the reference's default, spelled out
+        kw.pop("choice", None)
     unknown = set(kw) - set(tree.ENGINE_KWARGS) - {"region_surcharge"}
     if unknown:
         raise NotImplementedError(f"bipartition_tree hooks without a device path: {sorted(unknown)}")
@@ -67,8 +71,10 @@ def method_config(method) -> Dict:
         tree_kind = _abi.RC_TREE_WILSON
     else:
         raise NotImplementedError("spanning_tree_fn must be random_spanning_tree or uniform_spanning_tree")
-    if kw["balance_edge_fn"] is not tree.find_balanced_edge_cuts_memoization:
-        raise NotImplementedError("balance_edge_fn must be find_balanced_edge_cuts_memoization")
+    if kw["balance_edge_fn"] not in (tree.find_balanced_edge_cuts_memoization,
+                                     tree.find_balanced_edge_cuts_contraction):
+        raise NotImplementedError("balance_edge_fn must be find_balanced_edge_cuts_memoization or "
+                                  "find_balanced_edge_cuts_contraction (the same set of balanced cuts)")
     if kw["one_sided_cut"]:
         raise NotImplementedError("one_sided_cut=True is the seeding path, not ReCom (tree.py:386-409)")
     if kw["cut_choice"] is tree._region_preferred_max_weight_choice:

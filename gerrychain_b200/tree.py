@@ -39,6 +39,11 @@ def _selector_only(name):
 random_spanning_tree = _selector_only("random_spanning_tree")  # tree.py:60-94  -> RC_TREE_MST
 uniform_spanning_tree = _selector_only("uniform_spanning_tree")  # tree.py:97-132 -> RC_TREE_WILSON
 find_balanced_edge_cuts_memoization = _selector_only("find_balanced_edge_cuts_memoization")  # tree.py:351
+# tree.py:243-286: the leaf-contraction variant finds the SAME set of balanced cuts (both test
+# has_ideal_population on every non-root node of the rooted tree) and the cut is then drawn
+# uniformly from it, so it selects the same device path (the order of the list differs, which
+# only matters to a replay of recorded choices)
+find_balanced_edge_cuts_contraction = _selector_only("find_balanced_edge_cuts_contraction")
 _region_preferred_max_weight_choice = _selector_only("_region_preferred_max_weight_choice")  # tree.py:501
 _max_weight_choice = _selector_only("_max_weight_choice")  # tree.py:446
 

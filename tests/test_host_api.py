@@ -103,6 +103,14 @@ def test_method_config_reads_partials_like_the_reference():
                        allow_pair_reselection=True)
     with pytest.raises(NotImplementedError):
         method_config(functools.partial(gc.bipartition_tree, choice=min))
+    import random
+
+    # the reference's defaults spelled out, and the contraction variant of the balance test
+    assert method_config(functools.partial(gc.bipartition_tree, choice=random.choice,
+                                           balance_edge_fn=gc.tree.find_balanced_edge_cuts_contraction)) \
+        == method_config(gc.bipartition_tree)
+    with pytest.raises(NotImplementedError):
+        method_config(functools.partial(gc.bipartition_tree, balance_edge_fn=len))
     with pytest.raises(NotImplementedError):
         method_config(lambda *a, **k: None)
     kw = engine_kwargs(100, 0.1, 2, {"county": 0.5}, gc.bipartition_tree)
