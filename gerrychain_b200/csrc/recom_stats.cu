@@ -49,6 +49,7 @@ __global__ void region_splits_kernel(const Params p, const int32_t* __restrict__
       const int r = __ldg(region + v);
       if (r < 0 || r >= R) continue;
       const uint32_t d = assign[v];
+      if (d >= (uint32_t)k) continue;  // a plan that never completed (RC_SEED_REMAINING): its status says so
       atomicOr(&seen[r * kw + (d >> 5)], 1u << (d & 31u));
     }
     __syncthreads();
