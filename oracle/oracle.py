@@ -52,6 +52,9 @@ def load(label_bits=8):
         _lib.rco_region_splits.argtypes = [C.POINTER(_abi.RcGraph), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                            C.c_void_p]
         _lib.rco_contiguity.argtypes = [C.POINTER(_abi.RcGraph), C.c_int32, C.c_void_p, C.c_void_p]
+        _lib.rco_replay_reversible.argtypes = [
+            C.POINTER(_abi.RcGraph), C.POINTER(_abi.RcConfig), C.c_void_p, C.c_int32, C.c_void_p,
+            C.POINTER(_abi.RcReplay)] + [C.c_void_p] * 7
         _lib.rco_philox.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.rco_philox.restype = None
     return _lib
@@ -104,6 +107,50 @@ def contiguity(csr, k, assignment):
     g = _abi.graph_struct(csr)
     load(bits).rco_contiguity(C.byref(g), k, a.ctypes.data, out.ctypes.data)
     return out
+
+
+#: oracle/recom_oracle.h: RcoRevStep
+REV_STEP_DTYPE = np.dtype([("d_out", "<i4"), ("d_in", "<i4"), ("pair_edge", "<i4"), ("root", "<i4"),
+                           ("cut_edge", "<i4"), ("pad", "<i4"), ("tree_idx", "<i8"), ("accept_u", "<f8")])
+REV_NO_PAIR, REV_NO_CUT, REV_REJECTED, REV_MOVED = range(4)
+
+
+def replay_reversible(csr, cfg: EngineConfig, init_assignment, steps, wilson_root, stack_ptr, stack_val):
+    """Apply recorded reference calls of reversible_recom (oracle/record_reversible.py) to one plan.
+    steps: REV_STEP_DTYPE array; the Wilson arrays as in tests/_golden.ReplayArrays.
+    Returns (status, assignment after every call [S][N], info [S][4] = trees, balanced cuts, seam
+    length, outcome REV_*)."""
+    bits = _abi.label_bits_for(cfg.n_districts)
+    lib = load(bits)
+    assert steps.dtype == REV_STEP_DTYPE and steps.flags.c_contiguous
+    g = _abi.graph_struct(csr)
+    c = cfg.to_struct()
+    S, N, k = len(steps), csr.n_nodes, cfg.n_districts
+    assign = np.ascontiguousarray(init_assignment, dtype=_abi.label_dtype(bits)).copy()
+    tally = np.zeros(k, dtype=np.int64)
+    mask = np.zeros(strides(csr.n_nodes, csr.n_edges)[1], dtype=np.uint32)
+    cut_count = np.zeros(1, dtype=np.int32)
+    counters = np.zeros(_abi.RC_N_COUNTERS, dtype=np.int64)
+    trace = np.zeros((S, N), dtype=assign.dtype)
+    info = np.zeros((S, 4), dtype=np.int32)
+    rw = _abi.RcReplay()
+    wr = np.ascontiguousarray(wilson_root, dtype=np.int32)
+    sp = np.ascontiguousarray(stack_ptr, dtype=np.int64)
+    sv = np.ascontiguousarray(stack_val, dtype=np.int32)
+    rw.wilson_root, rw.stack_ptr, rw.stack_val = wr.ctypes.data, sp.ctypes.data, sv.ctypes.data
+    lib.rco_init_state.argtypes = [C.POINTER(_abi.RcGraph), C.POINTER(_abi.RcConfig)] + [C.c_void_p] * 4
+    rc = lib.rco_init_state(C.byref(g), C.byref(c), assign.ctypes.data, tally.ctypes.data, mask.ctypes.data,
+                            cut_count.ctypes.data)
+    assert rc == 0, rc
+    w = lib.rco_work_create(C.byref(g))
+    try:
+        rc = lib.rco_replay_reversible(C.byref(g), C.byref(c), w, S, steps.ctypes.data, C.byref(rw),
+                                       assign.ctypes.data, tally.ctypes.data, mask.ctypes.data,
+                                       cut_count.ctypes.data, counters.ctypes.data, trace.ctypes.data,
+                                       info.ctypes.data)
+    finally:
+        lib.rco_work_destroy(w)
+    return rc, trace, info, tally, int(cut_count[0])
 
 
 def seed_plans(csr, cfg: EngineConfig, n_plans=1, max_attempts=10000, rec=None):

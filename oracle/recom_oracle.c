@@ -617,25 +617,41 @@ static int rco_propose(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t
 
 /* proposals/tree_proposals.py:149-267 reversible_recom; *accepted = 1 also for self-loops
  * (the chain counts every call as a step), 0 only when the proposal fails the Bounds. */
+/* rv / rw (TEST HOOK, optional): the recorded randomness of one reference call - the ordered pair,
+ * the edge between the two districts, the walk stacks of the tree (rw, tree index rv->tree_idx),
+ * the BFS root, the chosen cut and the acceptance draw - replayed by identity like rco_propose's
+ * RcReplayStep; info (optional): {trees, balanced cuts, -, outcome RCO_REV_*}. */
 static int rco_propose_reversible(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t chain,
                                   rc_label_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
-                                  uint32_t prop_no, int64_t* counters, int* accepted, int32_t* last_pair) {
+                                  uint32_t prop_no, int64_t* counters, int* accepted, int32_t* last_pair,
+                                  const RcoRevStep* rv, const RcReplay* rw, int32_t* info) {
   int k = c->n_districts, M = c->rev_M > 0 ? c->rev_M : 1;
   *accepted = 1;
+  if (info) info[3] = RCO_REV_NO_PAIR;
   RcPhilox rp = rc_draw(c->seed, chain, RC_DRAW_PAIR, 0, 0, prop_no, 0);
   int pr = (int)rc_below(rp.v[0], rp.v[1], (uint32_t)(k * k));
   int d_out = pr / k, d_in = pr % k;
+  if (rv) {
+    d_out = rv->d_out; d_in = rv->d_in;
+    if (d_out < 0 || d_out >= k || d_in < 0 || d_in >= k) return RC_ERR_REPLAY;
+  }
   if (d_out == d_in) return RC_OK;
   int n_pair = 0;
   for (int e = 0; e < g->n_edges; ++e) {
     int la = assign[g->edge_uv[2 * e]], lb = assign[g->edge_uv[2 * e + 1]];
     if ((la == d_out && lb == d_in) || (la == d_in && lb == d_out)) ++n_pair;
   }
-  if (!n_pair) return RC_OK;
+  if (!n_pair) return (rv && rv->pair_edge >= 0) ? RC_ERR_REPLAY : RC_OK;
   int kth = (int)rc_below(rp.v[2], rp.v[3], (uint32_t)n_pair), e_star = -1;
   for (int e = 0; e < g->n_edges; ++e) {
     int la = assign[g->edge_uv[2 * e]], lb = assign[g->edge_uv[2 * e + 1]];
     if (((la == d_out && lb == d_in) || (la == d_in && lb == d_out)) && kth-- == 0) { e_star = e; break; }
+  }
+  if (rv) {  /* the recorded edge must join the recorded pair */
+    e_star = rv->pair_edge;
+    if (e_star < 0 || e_star >= g->n_edges) return RC_ERR_REPLAY;
+    int la = assign[g->edge_uv[2 * e_star]], lb = assign[g->edge_uv[2 * e_star + 1]];
+    if (!((la == d_out && lb == d_in) || (la == d_in && lb == d_out))) return RC_ERR_REPLAY;
   }
   int lab_root = assign[g->edge_uv[2 * e_star]], lab_other = assign[g->edge_uv[2 * e_star + 1]];
   int a = lab_root < lab_other ? lab_root : lab_other, b = lab_root < lab_other ? lab_other : lab_root;
@@ -643,8 +659,9 @@ static int rco_propose_reversible(const RcGraph* g, const RcConfig* c, RcoWork* 
   counters[RC_CTR_NODES] += w->n;
   for (int i = 0; i < w->n; ++i) counters[RC_CTR_SLOTS] += g->row_ptr[w->nodes[i] + 1] - g->row_ptr[w->nodes[i]];
   if (w->n < 3) { rco_ungather(w); return RC_ERR_NO_ROOT; }
-  int rc = rco_wilson(g, c, w, chain, 0, prop_no, NULL, 0, &counters[RC_CTR_WALK]);
+  int rc = rco_wilson(g, c, w, chain, 0, prop_no, rv ? rw : NULL, rv ? rv->tree_idx : 0, &counters[RC_CTR_WALK]);
   counters[RC_CTR_TREES]++; counters[RC_CTR_ATTEMPTS]++;
+  if (info) { info[0] = 1; info[3] = RCO_REV_NO_CUT; }
   if (rc) { rco_ungather(w); return rc; }
   build_tree_adj(w);
   int n_int = 0, root = -1;
@@ -656,13 +673,28 @@ static int rco_propose_reversible(const RcGraph* g, const RcConfig* c, RcoWork* 
     for (int i = 0; i < w->n; ++i)
       if ((w->toff[i + 1] - w->toff[i]) > 1 && q-- == 0) { root = i; break; }
   }
+  if (rv) {  /* tree.py:377: the recorded root must be a node of tree degree > 1 */
+    root = (rv->root >= 0 && rv->root < g->n_nodes) ? w->g2l[rv->root] : -1;
+    if (root < 0 || (w->toff[root + 1] - w->toff[root]) <= 1) { rco_ungather(w); return RC_ERR_REPLAY; }
+  }
   rco_bfs(w, root);
   rco_subtree_pops(g, w);
   int nb = rco_balanced_cuts(w, c->pop_target, c->epsilon, root);
+  if (info) info[1] = nb;
   if (nb > M) { rco_ungather(w); return RC_ERR_REVERSIBILITY; }
-  if (!nb) { rco_ungather(w); return RC_OK; }
+  if (!nb) { rco_ungather(w); return (rv && rv->cut_edge >= 0) ? RC_ERR_REPLAY : RC_OK; }
   RcPhilox pc = rc_draw(c->seed, chain, RC_DRAW_CUT, 0, 0, prop_no, 0);
   int pick = (int)rc_below(pc.v[0], pc.v[1], (uint32_t)nb);
+  if (rv) {  /* the recorded Cut.edge must be one of the balanced cuts found here */
+    pick = -1;
+    for (int q = 0; q < nb; ++q) {
+      int ch = w->bal_child[q], par = w->parent[ch], eid = -1;
+      for (int t = 0; t < w->nt; ++t)
+        if ((w->tu[t] == ch && w->tv[t] == par) || (w->tu[t] == par && w->tv[t] == ch)) eid = w->tw_eid[t];
+      if (eid == rv->cut_edge) pick = q;
+    }
+    if (pick < 0) { rco_ungather(w); return RC_ERR_REPLAY; }
+  }
   int child = w->bal_child[pick];
   int64_t pop_other = w->subpop[child], pop_root = w->totpop - pop_other;
   mark_subtree(w, child);  /* side = 1: cut away from the root -> lab_other */
@@ -676,7 +708,10 @@ static int rco_propose_reversible(const RcGraph* g, const RcConfig* c, RcoWork* 
   double prob = (double)nb / (double)((int64_t)M * seam);
   if (prob > 1.0) { rco_ungather(w); return RC_ERR_REVERSIBILITY; }
   RcPhilox pa = rc_draw(c->seed, chain, RC_DRAW_ACCEPT, 0, 0, prop_no, 0);
-  if (!(rc_unit_double(pa.v[0], pa.v[1]) < prob)) { rco_ungather(w); return RC_OK; }
+  double u_acc = rv ? rv->accept_u : rc_unit_double(pa.v[0], pa.v[1]);
+  if (info) { info[2] = seam; info[3] = RCO_REV_REJECTED; }
+  if (!(u_acc < prob)) { rco_ungather(w); return RC_OK; }
+  if (info) info[3] = RCO_REV_MOVED;
   if (c->pop_lower <= c->pop_upper) {
     double lo = (double)(pop_root < pop_other ? pop_root : pop_other), hi = (double)(pop_root < pop_other ? pop_other : pop_root);
     if (!(c->pop_lower <= lo && hi <= c->pop_upper)) { counters[RC_CTR_INVALID]++; *accepted = 0; rco_ungather(w); return RC_OK; }
@@ -705,7 +740,7 @@ int rco_step(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t global_ch
     uint32_t p = (*proposal_no)++;
     int rc = c->proposal_kind == RC_PROPOSAL_REVERSIBLE
                  ? rco_propose_reversible(g, c, w, global_chain, assign, tally, mask, cut_count, p, counters,
-                                          &accepted, last_pair)
+                                          &accepted, last_pair, NULL, NULL, NULL)
                  : rco_propose(g, c, w, global_chain, assign, tally, mask, cut_count, p, counters,
                                flags, NULL, NULL, NULL, &accepted, last_pair);
     if (rc) return rc;
@@ -726,6 +761,26 @@ int rco_replay(const RcGraph* g, const RcConfig* c, RcoWork* w, const RcReplay* 
     if (rp->info_trace) memcpy(rp->info_trace + 4 * s, info, sizeof info);
     if (rp->assign_trace) memcpy(rp->assign_trace + (size_t)s * g->n_nodes, assign, (size_t)g->n_nodes);
     if (rc) return rc;
+  }
+  return RC_OK;
+}
+
+/* TEST HOOK: recorded reference calls of reversible_recom (oracle/record_reversible.py) applied to one
+ * plan.  rw carries the Wilson arrays of the recorded trees (wilson_root, stack_ptr, stack_val);
+ * assign_trace [n_steps][N] and info_trace [n_steps][4] are optional outputs. */
+int rco_replay_reversible(const RcGraph* g, const RcConfig* c, RcoWork* w, int32_t n_steps,
+                          const RcoRevStep* steps, const RcReplay* rw, rc_label_t* assign, int64_t* tally,
+                          uint32_t* mask, int32_t* cut_count, int64_t* counters,
+                          rc_label_t* assign_trace, int32_t* info_trace) {
+  for (int s = 0; s < n_steps; ++s) {
+    int accepted = 0;
+    int32_t info[4] = {0, 0, 0, 0};
+    int rc = rco_propose_reversible(g, c, w, 0, assign, tally, mask, cut_count, (uint32_t)s, counters,
+                                    &accepted, NULL, &steps[s], rw, info);
+    if (info_trace) memcpy(info_trace + 4 * s, info, sizeof info);
+    if (assign_trace) memcpy(assign_trace + (size_t)s * g->n_nodes, assign, (size_t)g->n_nodes * sizeof(rc_label_t));
+    if (rc) return rc;
+    if (!accepted) return RC_ERR_INVALID_STREAK;  /* the recorded chains run without Bounds */
   }
   return RC_OK;
 }

@@ -26,6 +26,25 @@ int rco_step(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t global_ch
 int rco_replay(const RcGraph* g, const RcConfig* c, RcoWork* w, const RcReplay* rp,
                rc_label_t* assign, int64_t* tally, uint32_t* mask, int32_t* cut_count,
                int64_t* counters, uint32_t* flags);
+/* TEST HOOK: the recorded randomness of one reference reversible_recom call
+ * (proposals/tree_proposals.py:149-267), replayed by identity (oracle/record_reversible.py). */
+typedef struct RcoRevStep {
+  int32_t d_out, d_in;   /* random.choice(dist_pairs), tree_proposals.py:224 (district indices)   */
+  int32_t pair_edge;     /* random.choice(list(pair_edges)), :230; -1: self-loop before any tree  */
+  int32_t root;          /* node index chosen at tree.py:377; -1: no tree                         */
+  int32_t cut_edge;      /* edge id of choice(all_cuts).edge, :244; -1: no balanced cut            */
+  int32_t pad;
+  int64_t tree_idx;      /* index of this call's tree in the Wilson arrays of the RcReplay         */
+  double accept_u;       /* random.random() at :262 (NaN when the call never got there)            */
+} RcoRevStep;
+enum { RCO_REV_NO_PAIR = 0,   /* :227 self-loop: equal districts or not adjacent                  */
+       RCO_REV_NO_CUT = 1,    /* :241 self-loop: the tree has no balanced edge                    */
+       RCO_REV_REJECTED = 2,  /* :265 self-loop: the acceptance draw failed                       */
+       RCO_REV_MOVED = 3 };   /* :263 the new partition                                           */
+int rco_replay_reversible(const RcGraph* g, const RcConfig* c, RcoWork* w, int32_t n_steps,
+                          const RcoRevStep* steps, const RcReplay* rw, rc_label_t* assign, int64_t* tally,
+                          uint32_t* mask, int32_t* cut_count, int64_t* counters,
+                          rc_label_t* assign_trace, int32_t* info_trace);
 int rco_seed_plan(const RcGraph* g, const RcConfig* c, RcoWork* w, uint32_t chain,
                   int32_t seed_max_attempts, rc_label_t* assign, int64_t* tally,
                   int64_t* counters, const RcReplay* rp);

@@ -115,3 +115,52 @@ def test_oracle_seed_plans_free_running_are_valid():
         m = coo_matrix((np.ones(same.sum()), (uv[same, 0], uv[same, 1])), shape=(csr.n_nodes,) * 2)
         assert connected_components(m, directed=False)[0] == cfg.n_districts
     assert len({pl.tobytes() for pl in plans}) == 20
+
+
+@pytest.mark.parametrize("name", ["reversible_grid8", "reversible_grid12"])
+def test_reversible_replay_matches_reference(name):
+    """reversible_recom (tree_proposals.py:149-267) pinned bit-exactly, not only statistically: the
+    reference's recorded calls (oracle/record_reversible.py: ordered pair, edge, walk stacks, BFS
+    root, chosen cut, acceptance draw) replayed through the oracle give the reference's plan after
+    every call, the same number of balanced cuts per tree and the same outcome (self-loop kinds /
+    move).  The device runs the same code path bit-exactly with the oracle on Philox draws
+    (tests/test_gpu_parity.py::test_reversible_recom_bit_exact_with_oracle)."""
+    import json
+    import os
+
+    from oracle import oracle
+    from gerrychain_b200.config import EngineConfig
+    from gerrychain_b200.csr import csr_from_edges
+
+    z = np.load(os.path.join(_golden.GOLDEN, name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    N = int(z["pop"].shape[0])
+    csr = csr_from_edges(N, z["edge_uv"], z["pop"])
+    assert np.array_equal(csr.edge_uv, z["edge_uv"])
+    cfg = EngineConfig(n_districts=meta["k"], n_chains=1, pop_target=meta["pop_target"], epsilon=meta["epsilon"],
+                       tree_kind=_abi.RC_TREE_WILSON, proposal_kind=_abi.RC_PROPOSAL_REVERSIBLE, rev_M=meta["M"])
+    S = meta["n_steps"]
+    steps = np.zeros(S, dtype=oracle.REV_STEP_DTYPE)
+    for f in ("d_out", "d_in", "pair_edge", "root", "cut_edge", "tree_idx", "accept_u"):
+        steps[f] = z[f]
+    T = len(z["wilson_root"])
+    sp = np.zeros((T, N + 1), dtype=np.int64)  # dense per-tree stack pointers, as _golden.load builds them
+    wn_ptr, wn_node, ws_ptr = z["wn_ptr"], z["wn_node"], z["ws_ptr"]
+    for t in range(T):
+        lo, hi = int(wn_ptr[t]), int(wn_ptr[t + 1])
+        cnt = np.zeros(N, dtype=np.int64)
+        cnt[wn_node[lo:hi]] = ws_ptr[lo + 1:hi + 1] - ws_ptr[lo:hi]
+        sp[t, 0] = ws_ptr[lo]
+        sp[t, 1:] = ws_ptr[lo] + np.cumsum(cnt)
+    rc, trace, info, tally, cut_count = oracle.replay_reversible(csr, cfg, z["init_assignment"], steps,
+                                                                z["wilson_root"], sp, z["ws_val"])
+    assert rc == 0, _abi.STATUS_NAMES.get(rc, rc)
+    assert np.array_equal(trace, z["assignment"])
+    assert np.array_equal(info[:, 3], z["outcome"])
+    had_tree = z["outcome"] >= oracle.REV_NO_CUT
+    assert np.array_equal(info[had_tree, 1], z["n_balanced"][had_tree])
+    assert np.array_equal(info[:, 0], had_tree.astype(np.int32))
+    assert cut_count == int(z["n_cut_edges"][-1])
+    assert (z["outcome"] == oracle.REV_MOVED).sum() >= 5  # the record does contain accepted moves
+    last = z["assignment"][-1].astype(np.int64)
+    assert np.array_equal(tally, np.bincount(last, weights=csr.pop, minlength=meta["k"]).astype(np.int64))
