@@ -200,7 +200,8 @@ class Partition:
         self = cls.__new__(cls)
         self._inherit(parent)
         self._flips = None
-        self._vec = vec
+        # (the 16-bit-label engine hands back signed torch rows; labels <= 32767, so the cast is exact)
+        self._vec = np.asarray(vec).astype(parent._vec.dtype, copy=False)
         self._dev_tally[tuple(tally_fields)] = tally
         self._cut_count = int(cut_count)
         self._cut_mask = cut_mask
