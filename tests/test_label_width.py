@@ -273,3 +273,40 @@ def test_batched_chain_of_a_300_district_partition():
     part = last.partition(3)
     assert len(part) == 300 and len(part["cut_edges"]) == int(ora.cut_count[3])
     assert sorted(part["population"].values()) == sorted(int(x) for x in ora.tally[3])
+
+
+@pytest.mark.gpu
+def test_single_chain_recom_with_300_districts():
+    """The literal drop-in (MarkovChain + recom, host Partition per state) on a 300-district plan:
+    incremental cut_edges / Tally equal the naive recomputation at every step, the child keeps the
+    parent's uint16 dense plan, districts stay contiguous."""
+    import functools
+
+    import networkx
+
+    from gerrychain_b200 import MarkovChain, Partition
+    from gerrychain_b200.accept import always_accept
+    from gerrychain_b200.constraints import within_percent_of_ideal_population
+    from gerrychain_b200.proposals import recom
+    from gerrychain_b200.updaters import Tally, cut_edges
+
+    g = networkx.grid_2d_graph(60, 60)
+    networkx.set_node_attributes(g, 1, "population")
+    plan = {v: (v[0] // 3) * 15 + v[1] // 4 for v in g.nodes}
+    init = Partition(g, plan, {"population": Tally("population"), "cut_edges": cut_edges})
+    p = functools.partial(recom, pop_col="population", pop_target=12.0, epsilon=0.1)
+    chain = MarkovChain(p, [within_percent_of_ideal_population(init, 0.1)], always_accept, init, total_steps=40)
+    moved = 0
+    for state in chain:
+        assert len(state) == 300 and state.assignment_vector().dtype == np.uint16
+        m = state.assignment.mapping
+        assert state["cut_edges"] == {tuple(sorted(e)) for e in g.edges if m[e[0]] != m[e[1]]}
+        pops = {}
+        for node, part in m.items():
+            pops[part] = pops.get(part, 0) + 1
+        assert state["population"] == pops and set(pops.values()) <= {11, 12, 13}
+        if state.parent is not None:
+            moved += len(state.flips) > 0
+            for d in set(state.flips.values()):  # the districts that gained nodes
+                assert networkx.is_connected(g.subgraph(state.assignment.parts[d]))
+    assert moved >= 10
