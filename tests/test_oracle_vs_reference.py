@@ -164,3 +164,26 @@ def test_reversible_replay_matches_reference(name):
     assert (z["outcome"] == oracle.REV_MOVED).sum() >= 5  # the record does contain accepted moves
     last = z["assignment"][-1].astype(np.int64)
     assert np.array_equal(tally, np.bincount(last, weights=csr.pop, minlength=meta["k"]).astype(np.int64))
+
+
+@pytest.mark.parametrize("name", ["policy_8x8_region4", "policy_grid10_empty_surcharge"])
+def test_max_weight_cut_policy_matches_reference(oracle_lib, name):
+    """The branches of the cut choice the replay_* fixtures do not reach (tree.py:548-549): more
+    than three region columns, and ``region_surcharge={}`` - in both the reference takes the
+    balanced cut of maximum weight (oracle/record_policy_fixtures.py).  Replayed with and without
+    the reference's chosen cut injected."""
+    for inject in (True, False):
+        g = _golden.load(name, inject_cut=inject)
+        if "empty" in name:  # the fixture stores no region column: {} -> _max_weight_choice
+            assert g.cfg.cut_policy == _abi.RC_CUT_UNIFORM
+            g.cfg.cut_policy = _abi.RC_CUT_MAX_WEIGHT
+        else:
+            assert g.csr.n_region_cols == 4
+        assert g.cfg.cut_policy == _abi.RC_CUT_MAX_WEIGHT
+        ch = oracle.OracleChains(g.csr, g.cfg, g.init_assignment)
+        rc, trace, info = ch.replay(g.rec)
+        assert rc == 0, _abi.STATUS_NAMES.get(rc)
+        assert np.array_equal(trace, g.assignment)
+        assert np.array_equal(info[:, 1], np.diff(g.balanced_ptr))
+    # the choice is not vacuous: most steps offered more than one balanced cut
+    assert (np.diff(g.balanced_ptr) > 1).mean() > 0.3
