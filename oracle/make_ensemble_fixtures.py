@@ -52,6 +52,11 @@ CASES = {
                              plan_file="plan_delaunay9000_k18.npy"),
     "delaunay9000_wilson": dict(graph="delaunay", n=9000, k=18, eps=0.02, tree="wilson", steps=50, chains=192,
                                 plan_file="plan_delaunay9000_k18.npy"),
+    # BASELINE config 4 at its stated size: Delaunay 200k nodes, 50 districts, eps 0.05,
+    # uniform_spanning_tree, the committed seed plan.  ~1.7 s per reference step: each worker
+    # process builds the graph once and runs a block of chains (chains_per_task)
+    "delaunay200000_wilson": dict(graph="delaunay", n=200000, k=50, eps=0.05, tree="wilson", steps=20, chains=128,
+                                  plan_file="plan_delaunay200000_k50.npy", pop_range=[20, 200], chains_per_task=16),
 }
 
 
@@ -65,7 +70,7 @@ def _build(case):
         from gerrychain.tree import recursive_tree_part
         from gerrychain_b200 import synthetic as syn
 
-        g = syn.delaunay_graph(case["n"], seed=0)
+        g = syn.delaunay_graph(case["n"], seed=0, **({"pop_range": tuple(case["pop_range"])} if case.get("pop_range") else {}))
         if case.get("counties"):
             syn.voronoi_counties(g, case["counties"], seed=1, key="county")
         graph = Graph.from_networkx(g)
@@ -89,13 +94,19 @@ def _build(case):
     return graph, part, plan
 
 
-def run_chain(seed, case):
+def run_chain_block(first_seed, case):
+    """chains first_seed .. first_seed + chains_per_task - 1 on ONE build of the graph (big graphs)."""
+    built = _build(case)
+    return [run_chain(seed, case, built) for seed in range(first_seed, first_seed + case["chains_per_task"])]
+
+
+def run_chain(seed, case, built=None):
     import_reference()
     from gerrychain import MarkovChain, accept, constraints
     from gerrychain.proposals import recom
     from gerrychain.tree import bipartition_tree, uniform_spanning_tree
 
-    graph, part, plan = _build(case)
+    graph, part, plan = built if built is not None else _build(case)
     random.seed(seed)
     ideal = sum(part["population"].values()) / len(part)
     method = bipartition_tree
@@ -132,7 +143,11 @@ def main():
         if only and name not in only:
             continue
         with ProcessPoolExecutor(max_workers=os.cpu_count()) as ex:
-            rows = list(ex.map(partial(run_chain, case=case), range(case["chains"])))
+            if case.get("chains_per_task"):
+                blocks = ex.map(partial(run_chain_block, case=case), range(0, case["chains"], case["chains_per_task"]))
+                rows = [r for b in blocks for r in b]
+            else:
+                rows = list(ex.map(partial(run_chain, case=case), range(case["chains"])))
         _, part, plan = _build(case)
         labels = list(part.graph.nodes)
         out = os.path.join(GOLDEN, f"ensemble_{name}.npz")

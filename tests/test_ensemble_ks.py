@@ -104,6 +104,24 @@ def test_oracle_ensemble_matches_reference_9k(name):
     _compare(z, meta, g, csr, cfg, ideal, ora.cut_count, ora.tally, ora.assignments())
 
 
+def test_oracle_ensemble_matches_reference_200k():
+    """BASELINE config 4 at its stated size (Delaunay 200k nodes, 50 districts, eps 0.05,
+    uniform_spanning_tree): 128 chains x 20 steps of the unmodified reference
+    (oracle/make_ensemble_fixtures.py delaunay200000_wilson, ~1.7 s per reference step) against the
+    oracle from the same committed seed plan."""
+    from oracle import oracle
+    from gerrychain_b200 import workloads
+
+    z = np.load(os.path.join(GOLDEN, "ensemble_delaunay200000_wilson.npz"))
+    meta = json.loads(str(z["meta"]))
+    csr, plan, cfg = workloads.config4(n_chains=256, seed=11)
+    assert csr.n_nodes == meta["n"] and cfg.n_districts == meta["k"] and cfg.epsilon == meta["eps"]
+    assert np.array_equal(plan, z["plan"])
+    ora = oracle.OracleChains(csr, cfg, plan).run(meta["steps"], n_threads=os.cpu_count() or 1)
+    assert (ora.status == 0).all()
+    _compare(z, meta, None, csr, cfg, cfg.pop_target, ora.cut_count, ora.tally, ora.assignments())
+
+
 def meta_tree(name):
     return "wilson" if "wilson" in name else "mst"
 
