@@ -639,6 +639,13 @@ def run_b200(args):
             except Exception:
                 ref = None
         line["cpu_baseline"] = ref if ref else line["cpu_baseline_port"]
+        # the north star quotes its target ratio on the 9k-node config: the unmodified reference
+        # timed there too (same box, same run), so that extra.config3.value / this is that ratio
+        if have_reference() and "value" in extra.get("config3", {}):
+            try:
+                extra["config3"]["cpu_baseline"] = reference_sample("config3", False, min(args.cpu_seconds, 10.0))
+            except Exception:
+                extra["config3"]["cpu_baseline"] = None
     emit(line)
     D.close()
 
