@@ -3,8 +3,8 @@
 Reference: /root/reference/gerrychain/partition/partition.py:12-213 (Partition),
 partition/assignment.py:9-191 (Assignment), partition/geographic.py:13 (GeographicPartition).
 
-What differs underneath: the state of a partition is a dense ``uint8`` district-index
-vector in node order (the layout the engine keeps in HBM), not a dict copied at every step
+What differs underneath: the state of a partition is a dense ``uint8`` (``uint16`` beyond 255
+districts) district-index vector in node order (the layout the engine keeps in HBM), not a dict copied at every step
 (assignment.py:69-74).  ``Tally`` values and the cut-edge set come from the device: from
 the chain-step kernel's incremental updates when the partition was produced by ``recom``,
 from ``rc_engine_init_state`` (the first-time scans, updaters/tally.py:118-141 and
